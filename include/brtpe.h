@@ -1,0 +1,233 @@
+/*
+ * brtpe.h -- C ABI of libbrtpe.so: hand-written sm_100a CUDA kernels for the
+ * HigherHRNet-W48 teacher-inference hot path of andres-fr/realtime-pose-estimation.
+ *
+ * Every entry point replaces a piece of the reference's Python hot path (file:line
+ * are into /root/reference).  Conventions:
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless a
+ *     parameter is documented as host memory;
+ *   - every function returns 0 on success or a negative BRTPE_E* code;
+ *     brtpe_last_error() returns a thread-local, human readable message;
+ *   - no hidden device allocation: scratch comes from the caller
+ *     (*_workspace_bytes() queries), nothing is retained after the call except by the
+ *     explicit plan objects (brtpe_plan_*);
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*), no host
+ *     synchronisation inside unless documented.
+ */
+#ifndef BRTPE_H_
+#define BRTPE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRTPE_OK 0
+#define BRTPE_EINVAL (-1)      /* bad argument / unsupported configuration           */
+#define BRTPE_ECUDA (-2)       /* a CUDA runtime / driver call failed                */
+#define BRTPE_EWORKSPACE (-3)  /* workspace too small                                */
+#define BRTPE_EOVERFLOW (-4)   /* a caller-sized output capacity was exceeded        */
+
+#define BRTPE_MAX_TAG_DIMS 4   /* T: tag copies per joint (1 = no flip, 2 = flip)    */
+#define BRTPE_MAX_TOPK 64      /* K = max_num_people for top-k                        */
+#define BRTPE_MAX_GROUP_K 32   /* K supported by the grouping (Hungarian) kernel      */
+#define BRTPE_MAX_JOINTS 32
+
+const char* brtpe_last_error(void);
+int brtpe_version(void);
+/* 1 if the library was built with the tcgen05 convolution path */
+int brtpe_has_umma(void);
+
+/* ------------------------------------------------------------------------------------
+ * Decode: HeatmapParser (rtpe/third_party/group.py:125-287)
+ * ---------------------------------------------------------------------------------- */
+
+/* Mirror of Params (group.py:100-122) + HeatmapParser ctor kwargs (group.py:126-132). */
+typedef struct brtpe_decode_params {
+  int32_t num_joints;            /* J                                                  */
+  int32_t max_num_people;        /* K                                                  */
+  double detection_threshold;    /* compared in float64 like the reference (group.py:41) */
+  double tag_threshold;          /* group.py:85                                        */
+  int32_t use_detection_val;
+  int32_t ignore_too_much;
+  int32_t tag_per_joint;         /* 1: tag has J planes, 0: one plane shared by joints */
+  int32_t nms_ksize;             /* odd; 2*nms_padding must equal nms_ksize-1          */
+  int32_t nms_padding;
+  int32_t munkres_start_rule;    /* 0: munkres 1.1.x (restart at previous hit), 1: <=1.0.x */
+} brtpe_decode_params;
+
+/* HeatmapParser.nms (group.py:134-138): out = det * (maxpool_{k,1,p}(det) == det).
+ * det, out: (N*J, H, W) float32. */
+int brtpe_nms(const float* det, float* out, int planes, int H, int W, int ksize,
+              int padding, void* stream);
+
+/* HeatmapParser.top_k (group.py:144-179), fused NMS + per-(image, joint) top-K +
+ * tag gather.  Tie rule: value descending, flat index ascending.
+ *   det   (N, J, H, W) f32          tag (N, Jt, H, W, T) f32, Jt = J or 1
+ *   val_k (N, J, K) f32             ind_k (N, J, K) i32 (flat index y*W+x)
+ *   loc_k (N, J, K, 2) i64 (x, y)   tag_k (N, J, K, T) f32
+ * loc_k may be NULL. */
+size_t brtpe_topk_workspace_bytes(int N, int J, int H, int W, int K);
+int brtpe_nms_topk_gather(const float* det, const float* tag, int N, int J, int Jt, int H,
+                          int W, int T, int K, int ksize, int padding, float* val_k,
+                          int32_t* ind_k, int64_t* loc_k, float* tag_k, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* HeatmapParser.match / match_by_tag / py_max_match (group.py:19-97, :140-142):
+ * per-image greedy-by-joint grouping with an exact Kuhn-Munkres assignment per joint
+ * round (float64 cost, munkres 1.1.x tie-breaking), one warp per image.
+ *   val_k (N,J,K) f32, ind_k (N,J,K) i32, tag_k (N,J,K,T) f32, W = map width
+ *   ans   (N, Pmax, J, 3+T) f32  persons in creation order: [x, y, val, tag...]
+ *   count (N) i32                number of persons per image (<= Pmax or EOVERFLOW flag)
+ * Requires K <= BRTPE_MAX_GROUP_K, T <= BRTPE_MAX_TAG_DIMS.  Pmax = J*K always fits.
+ * overflow (1) i32 device flag is set to 1 if any image needed more than Pmax. */
+size_t brtpe_group_workspace_bytes(int N, int J, int K, int T, int Pmax);
+int brtpe_group_ae(const float* val_k, const int32_t* ind_k, const float* tag_k, int N,
+                   int W, int T, const brtpe_decode_params* params, float* ans,
+                   int32_t* count, int32_t* overflow, int Pmax, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* HeatmapParser.adjust (group.py:181-200): quarter-pixel shift + 0.5, in place on ans.
+ * det (N,J,H,W) f32 is the un-NMS'd map given to parse(). */
+int brtpe_adjust(float* ans, const int32_t* count, const float* det, int N, int J, int H,
+                 int W, int T, int Pmax, void* stream);
+
+/* scores = mean over joints of ans[..., 2] with numpy's float32 pairwise order
+ * (group.py:272).  scores (N, Pmax) f32. */
+int brtpe_scores(const float* ans, const int32_t* count, float* scores, int N, int J, int T,
+                 int Pmax, void* stream);
+
+/* HeatmapParser.refine (group.py:202-264) for every person of every image: one pass
+ * over det + tag per image evaluates argmax(det_j - round(||tag_j - mean_tag||)) for the
+ * joints a person is missing and fills them in place.
+ *   det (N,J,H,W) f32, tag (N,Jt,H,W,T) f32, ans (N,Pmax,J,3+T) f32 in/out. */
+size_t brtpe_refine_workspace_bytes(int N, int J, int T, int Pmax);
+int brtpe_refine(const float* det, const float* tag, float* ans, const int32_t* count, int N,
+                 int J, int Jt, int H, int W, int T, int Pmax, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Aggregation between network and parser
+ * ---------------------------------------------------------------------------------- */
+
+/* F.interpolate(src, (Ho,Wo), mode="bilinear", align_corners=ac) on NCHW float32
+ * (validate_hhrnet.py:94-98).  dst plane p / channel stride given in elements so the
+ * result can land inside a (N, J, Ho, Wo, T) tag tensor: dst[(p*Ho*Wo + y*Wo + x)*dst_inner + dst_off].
+ * src (planes, Hi, Wi) with plane stride src_plane_stride elements. */
+int brtpe_bilinear_resize(const float* src, long long src_plane_stride, int planes, int Hi,
+                          int Wi, float* dst, int Ho, int Wo, int dst_inner, int dst_off,
+                          int align_corners, void* stream);
+
+/* Flip-test / multi-scale aggregation of ONE scale (upstream HigherHRNet
+ * get_multi_stage_outputs + aggregate_results; in-tree callers legacy/valid_ae_avg.py:176-185,
+ * legacy/valid_ae1dim.py:176-191; configuration legacy/distillation.py:85-92):
+ *   y0 (N, J+A, H4, W4), y1 (N, J, H2, W2): network outputs of the image;
+ *   y0f, y1f: outputs of the x-mirrored image, or NULL (no flip test).
+ *   stage(y0,y1)[c] = ( bilinear_{H4->H2}(y0[c]) + y1[c] ) / 2          (align_corners=False)
+ *   heat = bilinear_{H2->Hb}(stage(y0,y1)); with flip: heat = (heat + heat_f) / 2 where
+ *          heat_f is the same on (y0f,y1f), mirrored in x and channel-permuted by flip_index
+ *   det (N, J, Hb, Wb) = accumulate ? det + heat : heat, then / final_div if final_div != 0
+ *   tag_out (N, A, Hb, Wb, T), T = 1 + (flip): slot 0 = bilinear_{H2->Hb}(bilinear_{H4->H2}(y0[J+a])),
+ *          slot 1 = the mirrored / permuted flipped-image tags.  tag_out may be NULL.
+ * flip_index_host: host int32[J] (also used for the A tag channels when A == J). */
+int brtpe_aggregate_scale(const float* y0, const float* y1, const float* y0f, const float* y1f,
+                          int N, int J, int A, int H4, int W4, int H2, int W2, int Hb, int Wb,
+                          const int32_t* flip_index_host, int accumulate, float final_div,
+                          float* det, float* tag_out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Convolution engine: PoseHigherResolutionNet.forward (pose_higher_hrnet.py:637-686)
+ * ---------------------------------------------------------------------------------- */
+
+enum { BRTPE_DT_F32 = 0, BRTPE_DT_BF16 = 1 };
+enum { BRTPE_ENGINE_AUTO = 0, BRTPE_ENGINE_FFMA = 1, BRTPE_ENGINE_UMMA = 2 };
+
+/* One fused conv launch: out = act( conv(in, w) + bias [+ residual] ), NHWC activations.
+ * Covers nn.Conv2d 3x3/1x1 stride 1/2 (pose_higher_hrnet.py:40-43,:83-89,:163,:202,:218,
+ * :460-482,:558-580) with eval BatchNorm folded into (w, bias), the ReLU / residual adds
+ * of BasicBlock/Bottleneck (:57-75,:96-116), and one output-parity phase of
+ * ConvTranspose2d(k4,s2,p1) (:514-521) expressed through the tap table. */
+typedef struct brtpe_conv_desc {
+  int32_t dtype;          /* BRTPE_DT_*: activation + weight storage type              */
+  int32_t engine;         /* BRTPE_ENGINE_*                                            */
+  int32_t N, Hin, Win;    /* input  tensor (N, Hin, Win, .) NHWC                        */
+  int32_t Cin;            /* logical input channels (K per tap)                         */
+  int32_t in_ld;          /* input pixel stride in elements (>= in_coff + Cin)          */
+  int32_t in_coff;        /* first input channel inside the pixel                       */
+  int32_t Hm, Wm;         /* GEMM-M domain (output pixels computed): m = (n, ym, xm)    */
+  int32_t in_stride;      /* input pixel = (ym*in_stride + dy, xm*in_stride + dx)       */
+  int32_t ntaps;          /* <= 9                                                       */
+  int32_t tap_dy[9], tap_dx[9];
+  int32_t Hout, Wout;     /* output tensor (N, Hout, Wout, .)                           */
+  int32_t out_scale;      /* output pixel = (ym*out_scale + out_oy, xm*out_scale + out_ox) */
+  int32_t out_oy, out_ox;
+  int32_t Cout;           /* logical output channels                                    */
+  int32_t out_ld, out_coff;
+  int32_t res_ld, res_coff;   /* residual tensor has the output's (N,Hout,Wout) geometry */
+  int32_t relu;
+  int32_t Cout_store;     /* channels written per pixel (>= Cout; extra ones get 0)     */
+} brtpe_conv_desc;
+
+/* FFMA path weights: float32 [ntaps][Cin][Cout].  UMMA path weights: bf16
+ * [ntaps][Cout_pad][Cin_pad] (K-major), Cin_pad = roundup(Cin, 64), Cout_pad = roundup(Cout,16).
+ * bias: float32 [Cout] (may be NULL).  residual may be NULL. */
+int brtpe_conv_run(const brtpe_conv_desc* d, const void* in, const void* weights,
+                   const float* bias, const void* residual, void* out, void* stream);
+
+/* Engine brtpe_conv_run / brtpe_plan_add_conv will use for this descriptor
+ * (BRTPE_ENGINE_FFMA or BRTPE_ENGINE_UMMA), or a negative error code. */
+int brtpe_conv_select_engine(const brtpe_conv_desc* d);
+/* Packed-weight geometry of the tcgen05 path: bf16 [ntaps][*cout_pad][*cin_pad]. */
+int brtpe_umma_weight_dims(int Cin, int Cout_store, int* cin_pad, int* cout_pad);
+
+/* Stem conv1 (pose_higher_hrnet.py:363-365,:638-640): NCHW float32/half image ->
+ * 3x3 s2 conv(3->Cout) + folded BN + ReLU -> NHWC (f32 or bf16).  w: float32 [27][Cout]
+ * ordered (ky, kx, cin). */
+int brtpe_stem_conv1(const void* img, int img_dtype_is_half, int N, int H, int W,
+                     const float* w, const float* bias, int Cout, void* out, int out_dtype,
+                     void* stream);
+
+/* y_i = relu?( sum_k up_{2^shift_k}(term_k) ) of HighResolutionModule.forward
+ * (pose_higher_hrnet.py:245-254); NHWC, nterms <= 4, nearest-neighbour upsample. */
+int brtpe_fuse_sum(int dtype, int nterms, const void* const* terms, const int32_t* shifts,
+                   const int32_t* term_ld, int N, int H, int W, int C, void* out, int out_ld,
+                   int relu, void* stream);
+
+/* NHWC (f32|bf16, pixel stride ld, channel offset coff) -> NCHW float32 or half
+ * network outputs (tofp32, fp16util.py:54-68). */
+int brtpe_nhwc_to_nchw(int dtype, const void* src, int N, int H, int W, int C, int ld,
+                       int coff, void* dst, int dst_is_half, void* stream);
+
+/* ---- execution plans: a recorded list of launches replayed natively / as a CUDA graph */
+typedef struct brtpe_plan brtpe_plan;
+brtpe_plan* brtpe_plan_create(void);
+void brtpe_plan_destroy(brtpe_plan*);
+int brtpe_plan_add_conv(brtpe_plan*, const brtpe_conv_desc* d, const void* in,
+                        const void* weights, const float* bias, const void* residual,
+                        void* out);
+int brtpe_plan_add_stem(brtpe_plan*, const void* img, int img_is_half, int N, int H, int W,
+                        const float* w, const float* bias, int Cout, void* out, int out_dtype);
+int brtpe_plan_add_fuse(brtpe_plan*, int dtype, int nterms, const void* const* terms,
+                        const int32_t* shifts, const int32_t* term_ld, int N, int H, int W,
+                        int C, void* out, int out_ld, int relu);
+int brtpe_plan_add_nhwc_to_nchw(brtpe_plan*, int dtype, const void* src, int N, int H, int W,
+                                int C, int ld, int coff, void* dst, int dst_is_half);
+int brtpe_plan_num_ops(const brtpe_plan*);
+/* total algorithmic conv FLOPs (2*MAC) of the plan's conv ops */
+double brtpe_plan_conv_flops(const brtpe_plan*);
+/* enqueue every op on `stream` */
+int brtpe_plan_run(brtpe_plan*, void* stream);
+/* capture the op list into a CUDA graph (once), then launch it */
+int brtpe_plan_graph_launch(brtpe_plan*, void* stream);
+/* run un-graphed with CUDA events around each op; ms_out[num_ops] (host) gets per-op
+ * device milliseconds; kinds_out[num_ops] (host): 0 conv-umma, 1 conv-ffma, 2 other.
+ * Synchronises the stream. */
+int brtpe_plan_profile(brtpe_plan*, void* stream, float* ms_out, int32_t* kinds_out,
+                       double* flops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRTPE_H_ */

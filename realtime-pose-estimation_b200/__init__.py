@@ -6,3 +6,9 @@ Drop-in for the reference's hot path (andres-fr/realtime-pose-estimation):
 sm_100a CUDA kernels behind the C ABI declared in include/brtpe.h.
 """
 from .synth import synth_decode_batch  # noqa: F401
+from .heatmap_parser import HeatmapParser, Params  # noqa: F401
+from .hhrnet import PoseHigherResolutionNet, BasicBlock, Bottleneck, HighResolutionModule, \
+    NoOpModule  # noqa: F401
+from .precision import network_to_half, tofp16, tofp32, BN_convert_float, \
+    get_hrnet_w48_teacher, W48_KWARGS  # noqa: F401
+from ._lib import BrtpeError, LIB_PATH  # noqa: F401

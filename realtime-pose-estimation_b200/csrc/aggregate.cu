@@ -1,0 +1,201 @@
+// Heat-map / tag aggregation between the network and the parser.
+//
+//  * brtpe_bilinear_resize : F.interpolate(..., mode="bilinear") of the in-tree path
+//    (validate_hhrnet.py:94-98, align_corners=True to the original image size); the
+//    destination addressing lets the tag result land directly in the (N,A,h,w,T) tensor
+//    the parser takes (the reference's aes.unsqueeze(-1)).
+//  * brtpe_aggregate_scale : flip-test + multi-scale mode (upstream HigherHRNet
+//    get_multi_stage_outputs / aggregate_results, used by legacy/valid_ae_avg.py:176-185):
+//    stage average, H/4 -> H/2 -> base-size bilinear cascade (align_corners=False),
+//    flip-back with left/right channel permutation, flip average, scale accumulation and
+//    the final division, fused into one pass that writes det and tag exactly once.
+//
+// Both are write-bound streaming kernels: one thread per output pixel, consecutive
+// threads on consecutive x, sources are 4-16x smaller than the output and stay in L1/L2.
+#include "common.cuh"
+
+namespace brtpe {
+
+// PyTorch's area_pixel_compute_source_index (float32 arithmetic).
+__device__ __forceinline__ float src_index(float scale, int dst, bool align_corners) {
+  if (align_corners) return scale * (float)dst;
+  const float s = scale * ((float)dst + 0.5f) - 0.5f;
+  return s < 0.0f ? 0.0f : s;
+}
+static inline float resize_scale(int in, int out, bool align_corners) {
+  if (align_corners) return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.0f;
+  return (float)in / (float)out;
+}
+
+struct Lerp {
+  int i0, i1;
+  float w0, w1;
+};
+__device__ __forceinline__ Lerp make_lerp(float scale, int dst, int in, bool ac) {
+  Lerp l;
+  const float s = src_index(scale, dst, ac);
+  l.i0 = (int)s;
+  if (l.i0 > in - 1) l.i0 = in - 1;
+  l.i1 = l.i0 + ((l.i0 < in - 1) ? 1 : 0);
+  l.w1 = s - (float)l.i0;
+  l.w0 = 1.0f - l.w1;
+  return l;
+}
+__device__ __forceinline__ float bilerp(const float* __restrict__ p, int W, const Lerp& ly,
+                                        const Lerp& lx) {
+  const float v00 = __ldg(p + (size_t)ly.i0 * W + lx.i0), v01 = __ldg(p + (size_t)ly.i0 * W + lx.i1);
+  const float v10 = __ldg(p + (size_t)ly.i1 * W + lx.i0), v11 = __ldg(p + (size_t)ly.i1 * W + lx.i1);
+  return ly.w0 * (lx.w0 * v00 + lx.w1 * v01) + ly.w1 * (lx.w0 * v10 + lx.w1 * v11);
+}
+
+__global__ void bilinear_resize_kernel(const float* __restrict__ src, long long src_plane_stride,
+                                       int planes, int Hi, int Wi, float* __restrict__ dst, int Ho,
+                                       int Wo, int dst_inner, int dst_off, float sy, float sx,
+                                       bool ac) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= Wo) return;
+  const Lerp ly = make_lerp(sy, y, Hi, ac);
+  const Lerp lx = make_lerp(sx, x, Wi, ac);
+  for (int p = blockIdx.z; p < planes; p += gridDim.z) {
+    const float v = bilerp(src + (size_t)p * src_plane_stride, Wi, ly, lx);
+    dst[((size_t)p * Ho * Wo + (size_t)y * Wo + x) * dst_inner + dst_off] = v;
+  }
+}
+
+struct AggArgs {
+  const float *y0, *y1, *y0f, *y1f;
+  float *det, *tag;
+  int N, J, A, H4, W4, H2, W2, Hb, Wb;
+  int accumulate;
+  float final_div;
+  float s42y, s42x, s2by, s2bx;
+  int flip_index[BRTPE_MAX_JOINTS];
+};
+
+// value of bilinear_{H2->Hb}(G) at (yb, xb) where G[y2][x2] is produced on the fly:
+//   G = (bilinear_{H4->H2}(q0)[y2][x2'] + q1[y2][x2']) * 0.5   (q1 != null: heat-maps)
+//   G =  bilinear_{H4->H2}(q0)[y2][x2']                        (q1 == null: tags)
+// with x2' = mirror ? W2-1-x2 : x2.
+__device__ __forceinline__ float cascade_sample(const AggArgs& a, const float* __restrict__ q0,
+                                                const float* __restrict__ q1, const Lerp& by,
+                                                const Lerp& bx, bool mirror) {
+  float g[2][2];
+#pragma unroll
+  for (int iy = 0; iy < 2; ++iy) {
+    const int y2 = iy ? by.i1 : by.i0;
+    const Lerp ly = make_lerp(a.s42y, y2, a.H4, false);
+#pragma unroll
+    for (int ix = 0; ix < 2; ++ix) {
+      int x2 = ix ? bx.i1 : bx.i0;
+      if (mirror) x2 = a.W2 - 1 - x2;
+      const Lerp lx = make_lerp(a.s42x, x2, a.W4, false);
+      float v = bilerp(q0, a.W4, ly, lx);
+      if (q1) v = (v + __ldg(q1 + (size_t)y2 * a.W2 + x2)) * 0.5f;
+      g[iy][ix] = v;
+    }
+  }
+  return by.w0 * (bx.w0 * g[0][0] + bx.w1 * g[0][1]) + by.w1 * (bx.w0 * g[1][0] + bx.w1 * g[1][1]);
+}
+
+__global__ void __launch_bounds__(256) aggregate_scale_kernel(AggArgs a) {
+  const int xb = blockIdx.x * blockDim.x + threadIdx.x;
+  const int yb = blockIdx.y;
+  if (xb >= a.Wb) return;
+  const Lerp by = make_lerp(a.s2by, yb, a.H2, false);
+  const Lerp bx = make_lerp(a.s2bx, xb, a.W2, false);
+  const int C0 = a.J + a.A;
+  const size_t p4 = (size_t)a.H4 * a.W4, p2 = (size_t)a.H2 * a.W2, pb = (size_t)a.Hb * a.Wb;
+  const bool flip = a.y0f != nullptr;
+  const int T = flip ? 2 : 1;
+  const int nch = a.J + (a.tag ? a.A : 0);
+  for (int nc = blockIdx.z; nc < a.N * nch; nc += gridDim.z) {
+    const int n = nc / nch, c = nc - n * nch;
+    if (c < a.J) {
+      float h = cascade_sample(a, a.y0 + ((size_t)n * C0 + c) * p4, a.y1 + ((size_t)n * a.J + c) * p2,
+                               by, bx, false);
+      if (flip) {
+        const int cf = a.flip_index[c];
+        const float hf = cascade_sample(a, a.y0f + ((size_t)n * C0 + cf) * p4,
+                                        a.y1f + ((size_t)n * a.J + cf) * p2, by, bx, true);
+        h = (h + hf) * 0.5f;
+      }
+      float* d = a.det + ((size_t)n * a.J + c) * pb + (size_t)yb * a.Wb + xb;
+      if (a.accumulate) h = *d + h;
+      if (a.final_div != 0.0f) h = __fdiv_rn(h, a.final_div);
+      *d = h;
+    } else {
+      const int t = c - a.J;
+      float* o = a.tag + (((size_t)n * a.A + t) * pb + (size_t)yb * a.Wb + xb) * T;
+      const float v = cascade_sample(a, a.y0 + ((size_t)n * C0 + a.J + t) * p4, nullptr, by, bx, false);
+      if (flip) {
+        const int tf = (a.A == a.J) ? a.flip_index[t] : t;
+        const float vf = cascade_sample(a, a.y0f + ((size_t)n * C0 + a.J + tf) * p4, nullptr, by, bx, true);
+        *reinterpret_cast<float2*>(o) = make_float2(v, vf);
+      } else {
+        *o = v;
+      }
+    }
+  }
+}
+
+}  // namespace brtpe
+
+using namespace brtpe;
+
+extern "C" int brtpe_bilinear_resize(const float* src, long long src_plane_stride, int planes,
+                                     int Hi, int Wi, float* dst, int Ho, int Wo, int dst_inner,
+                                     int dst_off, int align_corners, void* stream) {
+  BRTPE_CHECK_ARG(src && dst && planes > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0,
+                  "brtpe_bilinear_resize: bad arguments");
+  BRTPE_CHECK_ARG(dst_inner >= 1 && dst_off >= 0 && dst_off < dst_inner,
+                  "brtpe_bilinear_resize: bad destination addressing");
+  BRTPE_CHECK_ARG(Ho <= 65535, "brtpe_bilinear_resize: Ho too large");
+  const bool ac = align_corners != 0;
+  dim3 block(128);
+  int gz = planes < 64 ? planes : 64;
+  dim3 grid(ceil_div(Wo, 128), Ho, gz);
+  bilinear_resize_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+      src, src_plane_stride, planes, Hi, Wi, dst, Ho, Wo, dst_inner, dst_off,
+      resize_scale(Hi, Ho, ac), resize_scale(Wi, Wo, ac), ac);
+  BRTPE_LAUNCH_CHECK();
+  return BRTPE_OK;
+}
+
+extern "C" int brtpe_aggregate_scale(const float* y0, const float* y1, const float* y0f,
+                                     const float* y1f, int N, int J, int A, int H4, int W4, int H2,
+                                     int W2, int Hb, int Wb, const int32_t* flip_index_host,
+                                     int accumulate, float final_div, float* det, float* tag_out,
+                                     void* stream) {
+  BRTPE_CHECK_ARG(y0 && y1 && det, "brtpe_aggregate_scale: null y0/y1/det");
+  BRTPE_CHECK_ARG((y0f == nullptr) == (y1f == nullptr),
+                  "brtpe_aggregate_scale: y0f and y1f must both be given or both be NULL");
+  BRTPE_CHECK_ARG(N > 0 && J > 0 && J <= BRTPE_MAX_JOINTS && A >= 0 && A <= BRTPE_MAX_JOINTS,
+                  "brtpe_aggregate_scale: bad channel counts");
+  BRTPE_CHECK_ARG(H4 > 0 && W4 > 0 && H2 > 0 && W2 > 0 && Hb > 0 && Wb > 0 && Hb <= 65535,
+                  "brtpe_aggregate_scale: bad sizes");
+  BRTPE_CHECK_ARG(!y0f || flip_index_host, "brtpe_aggregate_scale: flip test needs flip_index");
+  BRTPE_CHECK_ARG(!tag_out || A > 0, "brtpe_aggregate_scale: tag_out given but A == 0");
+  if (tag_out && y0f)
+    BRTPE_CHECK_ARG((reinterpret_cast<uintptr_t>(tag_out) & 7) == 0,
+                    "brtpe_aggregate_scale: tag_out must be 8-byte aligned");
+  AggArgs a;
+  a.y0 = y0; a.y1 = y1; a.y0f = y0f; a.y1f = y1f; a.det = det; a.tag = tag_out;
+  a.N = N; a.J = J; a.A = A; a.H4 = H4; a.W4 = W4; a.H2 = H2; a.W2 = W2; a.Hb = Hb; a.Wb = Wb;
+  a.accumulate = accumulate;
+  a.final_div = final_div;
+  a.s42y = resize_scale(H4, H2, false);
+  a.s42x = resize_scale(W4, W2, false);
+  a.s2by = resize_scale(H2, Hb, false);
+  a.s2bx = resize_scale(W2, Wb, false);
+  for (int i = 0; i < BRTPE_MAX_JOINTS; ++i)
+    a.flip_index[i] = (flip_index_host && i < J) ? flip_index_host[i] : i;
+  for (int i = 0; i < J; ++i)
+    BRTPE_CHECK_ARG(a.flip_index[i] >= 0 && a.flip_index[i] < J,
+                    "brtpe_aggregate_scale: flip_index[%d] out of range", i);
+  const int nch = N * (J + (tag_out ? A : 0));
+  dim3 grid(ceil_div(Wb, 256), Hb, nch < 32 ? nch : 32);
+  aggregate_scale_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  BRTPE_LAUNCH_CHECK();
+  return BRTPE_OK;
+}

@@ -1,0 +1,368 @@
+// FP32-accurate convolution back end (CUDA-core implicit GEMM) + the small layout kernels.
+//
+// Role: (1) the fp32 precision mode of PoseHigherResolutionNet.forward -- the reference's
+// fp32 tolerance (<=1e-4 of the tensor max) rules out single-pass TF32 (SURVEY.md hard part
+// 2), so fp32 activations/weights are multiplied with FFMA and fp32 accumulation; (2) the
+// stem conv1 (Cin = 3, bandwidth bound) in both modes; (3) any layer shape the tcgen05
+// back end does not take.  Same brtpe_conv_desc contract as conv_umma.cu: NHWC
+// activations, a tap table (3x3 / 1x1 / stride 2 / one parity phase of the 4x4 s2
+// transposed conv), folded-BN bias, optional residual and ReLU in the epilogue.
+#include "conv_common.cuh"
+
+namespace brtpe {
+
+constexpr int FBM = 64, FBN = 64, FBK = 16, FTHREADS = 256;
+
+struct FfmaArgs {
+  brtpe_conv_desc d;
+  const void* in;
+  const float* w;      // [ntaps][Cin][Cout]
+  const float* bias;
+  const void* res;
+  void* out;
+  int M;               // N*Hm*Wm
+};
+
+template <typename TA>
+__global__ void __launch_bounds__(FTHREADS) conv_ffma_kernel(FfmaArgs a) {
+  __shared__ float As[FBK][FBM + 4];
+  __shared__ float Bs[FBK][FBN + 4];
+  __shared__ int s_pix_n[FBM], s_pix_y[FBM], s_pix_x[FBM];
+
+  const brtpe_conv_desc& d = a.d;
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * FBM;
+  const int n0 = blockIdx.y * FBN;
+  const TA* __restrict__ in = reinterpret_cast<const TA*>(a.in);
+
+  if (tid < FBM) {
+    int m = m0 + tid;
+    if (m < a.M) {
+      const int hw = d.Hm * d.Wm;
+      const int n = m / hw;
+      const int r = m - n * hw;
+      s_pix_n[tid] = n;
+      s_pix_y[tid] = r / d.Wm;
+      s_pix_x[tid] = r - (r / d.Wm) * d.Wm;
+    } else {
+      s_pix_n[tid] = -1;
+      s_pix_y[tid] = 0;
+      s_pix_x[tid] = 0;
+    }
+  }
+  __syncthreads();
+
+  const int tx = tid & 15;   // 16 column groups of 4 couts
+  const int ty = tid >> 4;   // 16 row groups of 4 pixels
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  // A loader: thread -> (pixel = tid / 4, k chunk = (tid % 4) * 4)
+  const int a_pix = tid >> 2;
+  const int a_k = (tid & 3) * 4;
+  // B loader: thread -> (k = tid / 16, cout chunk = (tid % 16) * 4)
+  const int b_k = tid >> 4;
+  const int b_c = (tid & 15) * 4;
+
+  for (int tap = 0; tap < d.ntaps; ++tap) {
+    const int pn = s_pix_n[a_pix];
+    const int iy = s_pix_y[a_pix] * d.in_stride + d.tap_dy[tap];
+    const int ix = s_pix_x[a_pix] * d.in_stride + d.tap_dx[tap];
+    const bool pvalid = (pn >= 0) && iy >= 0 && iy < d.Hin && ix >= 0 && ix < d.Win;
+    const TA* __restrict__ prow =
+        in + (((size_t)(pn < 0 ? 0 : pn) * d.Hin + (pvalid ? iy : 0)) * d.Win + (pvalid ? ix : 0)) *
+                 (size_t)d.in_ld + d.in_coff;
+    const float* __restrict__ wtap = a.w + (size_t)tap * d.Cin * d.Cout;
+    for (int c0 = 0; c0 < d.Cin; c0 += FBK) {
+      float av[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = c0 + a_k + e;
+        av[e] = (pvalid && c < d.Cin) ? to_f32(prow[c]) : 0.0f;
+      }
+      float bv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = c0 + b_k;
+        const int co = n0 + b_c + e;
+        bv[e] = (c < d.Cin && co < d.Cout) ? __ldg(wtap + (size_t)c * d.Cout + co) : 0.0f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 4; ++e) As[a_k + e][a_pix] = av[e];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) Bs[b_k][b_c + e] = bv[e];
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < FBK; ++k) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float ar[4] = {a4.x, a4.y, a4.z, a4.w};
+        const float br[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+      }
+    }
+  }
+
+  // ---- epilogue
+  TA* __restrict__ out = reinterpret_cast<TA*>(a.out);
+  const TA* __restrict__ res = reinterpret_cast<const TA*>(a.res);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pl = ty * 4 + i;
+    const int pn = s_pix_n[pl];
+    if (pn < 0) continue;
+    const int oy = s_pix_y[pl] * d.out_scale + d.out_oy;
+    const int ox = s_pix_x[pl] * d.out_scale + d.out_ox;
+    const size_t opix = ((size_t)pn * d.Hout + oy) * d.Wout + ox;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = n0 + tx * 4 + j;
+      if (co >= d.Cout_store) continue;
+      float v = 0.0f;
+      if (co < d.Cout) {
+        v = acc[i][j];
+        if (a.bias) v += __ldg(a.bias + co);
+        if (res) v += to_f32(res[opix * d.res_ld + d.res_coff + co]);
+        if (d.relu) v = fmaxf(v, 0.0f);
+      }
+      out[opix * d.out_ld + d.out_coff + co] = from_f32<TA>(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// stem conv1: NCHW float/half image -> 3x3 s2 p1 conv (3 -> Cout) + bias + ReLU -> NHWC
+// ------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+stem_conv1_kernel(const TI* __restrict__ img, int N, int H, int W, const float* __restrict__ w,
+                  const float* __restrict__ bias, int Cout, TO* __restrict__ out) {
+  extern __shared__ float sw[];  // [27][Cout] + [Cout]
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias ? bias[i] : 0.0f;
+  __syncthreads();
+  const int Ho = H / 2, Wo = W / 2;
+  const int groups = Cout / 16;
+  const size_t total = (size_t)N * Ho * Wo * groups;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(t % groups);
+    const size_t pix = t / groups;
+    const int ox = (int)(pix % Wo);
+    const int oy = (int)((pix / Wo) % Ho);
+    const int n = (int)(pix / ((size_t)Wo * Ho));
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = sw[27 * Cout + g * 16 + c];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 + ky - 1;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 + kx - 1;
+        const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          float v = 0.0f;
+          if (ok) {
+            const TI raw = img[(((size_t)n * 3 + ci) * H + iy) * W + ix];
+            v = to_f32(raw);
+          }
+          const float* wr = sw + ((ky * 3 + kx) * 3 + ci) * Cout + g * 16;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
+        }
+      }
+    }
+    TO* o = out + pix * Cout + g * 16;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) o[c] = from_f32<TO>(fmaxf(acc[c], 0.0f));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// cross-resolution fuse: out = relu?( sum_k nearest_up_{2^s_k}(term_k) ), NHWC
+// ------------------------------------------------------------------------------------------
+struct FuseArgs {
+  const void* terms[4];
+  int shifts[4];
+  int ld[4];
+  int nterms, N, H, W, C, out_ld, relu;
+  void* out;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) fuse_sum_kernel(FuseArgs a) {
+  const int cv = a.C / 4;  // 4 channels per thread
+  const size_t total = (size_t)a.N * a.H * a.W * cv;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % cv) * 4;
+    const size_t pix = t / cv;
+    const int x = (int)(pix % a.W);
+    const int y = (int)((pix / a.W) % a.H);
+    const int n = (int)(pix / ((size_t)a.W * a.H));
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < a.nterms; ++k) {
+      const int sh = a.shifts[k];
+      const int hk = a.H >> sh, wk = a.W >> sh;
+      const T* p = reinterpret_cast<const T*>(a.terms[k]) +
+                   (((size_t)n * hk + (y >> sh)) * wk + (x >> sh)) * a.ld[k] + c;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[e] = (k == 0) ? to_f32(p[e]) : s[e] + to_f32(p[e]);
+    }
+    T* o = reinterpret_cast<T*>(a.out) + pix * a.out_ld + c;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = from_f32<T>(a.relu ? fmaxf(s[e], 0.0f) : s[e]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// NHWC (f32 | bf16) -> NCHW (f32 | f16) network outputs
+// ------------------------------------------------------------------------------------------
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const TS* __restrict__ src, int N, int HW, int C, int ld, int coff,
+                    TD* __restrict__ dst) {
+  __shared__ float tile[64][65];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int pl = i / 64, cl = i % 64;
+    const int p = p0 + pl, c = c0 + cl;
+    tile[pl][cl] = (p < HW && c < C) ? to_f32(src[((size_t)n * HW + p) * ld + coff + c]) : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int cl = i / 64, pl = i % 64;
+    const int p = p0 + pl, c = c0 + cl;
+    if (p < HW && c < C) dst[((size_t)n * C + c) * HW + p] = from_f32<TD>(tile[pl][cl]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+int conv_validate(const brtpe_conv_desc* d) {
+  BRTPE_CHECK_ARG(d != nullptr, "conv: null descriptor");
+  BRTPE_CHECK_ARG(d->dtype == BRTPE_DT_F32 || d->dtype == BRTPE_DT_BF16, "conv: bad dtype %d",
+                  d->dtype);
+  BRTPE_CHECK_ARG(d->N > 0 && d->Hin > 0 && d->Win > 0 && d->Cin > 0 && d->Cout > 0,
+                  "conv: bad tensor sizes");
+  BRTPE_CHECK_ARG(d->Hm > 0 && d->Wm > 0 && d->in_stride >= 1 && d->out_scale >= 1,
+                  "conv: bad GEMM-M domain");
+  BRTPE_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= 9, "conv: ntaps=%d outside [1,9]", d->ntaps);
+  BRTPE_CHECK_ARG(d->in_ld >= d->in_coff + d->Cin, "conv: in_ld %d < in_coff %d + Cin %d", d->in_ld,
+                  d->in_coff, d->Cin);
+  BRTPE_CHECK_ARG(d->Cout_store >= d->Cout && d->out_ld >= d->out_coff + d->Cout_store,
+                  "conv: out_ld %d too small for out_coff %d + Cout_store %d", d->out_ld,
+                  d->out_coff, d->Cout_store);
+  BRTPE_CHECK_ARG((d->Hm - 1) * d->out_scale + d->out_oy < d->Hout &&
+                      (d->Wm - 1) * d->out_scale + d->out_ox < d->Wout && d->out_oy >= 0 &&
+                      d->out_ox >= 0,
+                  "conv: output mapping leaves the output tensor");
+  return BRTPE_OK;
+}
+
+double conv_flops(const brtpe_conv_desc* d) {
+  return 2.0 * (double)d->N * d->Hm * d->Wm * (double)d->ntaps * d->Cin * d->Cout;
+}
+
+int conv_ffma_launch(const brtpe_conv_desc* d, const void* in, const void* weights,
+                     const float* bias, const void* residual, void* out, cudaStream_t st) {
+  FfmaArgs a;
+  a.d = *d;
+  a.in = in;
+  a.w = reinterpret_cast<const float*>(weights);
+  a.bias = bias;
+  a.res = residual;
+  a.out = out;
+  a.M = d->N * d->Hm * d->Wm;
+  dim3 grid(ceil_div(a.M, FBM), ceil_div(d->Cout_store, FBN));
+  if (d->dtype == BRTPE_DT_F32)
+    conv_ffma_kernel<float><<<grid, FTHREADS, 0, st>>>(a);
+  else
+    conv_ffma_kernel<__nv_bfloat16><<<grid, FTHREADS, 0, st>>>(a);
+  BRTPE_LAUNCH_CHECK();
+  return BRTPE_OK;
+}
+
+int stem_conv1_launch(const void* img, int img_is_half, int N, int H, int W, const float* w,
+                      const float* bias, int Cout, void* out, int out_dtype, cudaStream_t st) {
+  BRTPE_CHECK_ARG(img && w && out && N > 0 && H > 0 && W > 0, "stem_conv1: bad arguments");
+  BRTPE_CHECK_ARG((H % 2) == 0 && (W % 2) == 0, "stem_conv1: H and W must be even");
+  BRTPE_CHECK_ARG(Cout % 16 == 0 && Cout <= 256, "stem_conv1: Cout must be a multiple of 16");
+  const size_t total = (size_t)N * (H / 2) * (W / 2) * (Cout / 16);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  const size_t smem = (size_t)28 * Cout * sizeof(float);
+#define BRTPE_STEM(TI, TO)                                                                        \
+  stem_conv1_kernel<TI, TO><<<blocks, 256, smem, st>>>(reinterpret_cast<const TI*>(img), N, H, W, \
+                                                      w, bias, Cout, reinterpret_cast<TO*>(out))
+  if (img_is_half) {
+    if (out_dtype == BRTPE_DT_F32) BRTPE_STEM(__half, float);
+    else BRTPE_STEM(__half, __nv_bfloat16);
+  } else {
+    if (out_dtype == BRTPE_DT_F32) BRTPE_STEM(float, float);
+    else BRTPE_STEM(float, __nv_bfloat16);
+  }
+#undef BRTPE_STEM
+  BRTPE_LAUNCH_CHECK();
+  return BRTPE_OK;
+}
+
+int fuse_sum_launch(int dtype, int nterms, const void* const* terms, const int32_t* shifts,
+                    const int32_t* term_ld, int N, int H, int W, int C, void* out, int out_ld,
+                    int relu, cudaStream_t st) {
+  BRTPE_CHECK_ARG(nterms >= 1 && nterms <= 4 && terms && shifts && term_ld && out,
+                  "fuse_sum: bad arguments");
+  BRTPE_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && (C % 4) == 0, "fuse_sum: C must be a multiple of 4");
+  FuseArgs a;
+  for (int k = 0; k < 4; ++k) {
+    a.terms[k] = k < nterms ? terms[k] : nullptr;
+    a.shifts[k] = k < nterms ? shifts[k] : 0;
+    a.ld[k] = k < nterms ? term_ld[k] : 0;
+    if (k < nterms) {
+      BRTPE_CHECK_ARG(terms[k] != nullptr, "fuse_sum: null term %d", k);
+      BRTPE_CHECK_ARG(shifts[k] >= 0 && (H % (1 << shifts[k])) == 0 && (W % (1 << shifts[k])) == 0,
+                      "fuse_sum: term %d shift %d does not divide %dx%d", k, shifts[k], H, W);
+    }
+  }
+  a.nterms = nterms; a.N = N; a.H = H; a.W = W; a.C = C; a.out_ld = out_ld; a.relu = relu;
+  a.out = out;
+  const size_t total = (size_t)N * H * W * (C / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  if (dtype == BRTPE_DT_F32) fuse_sum_kernel<float><<<blocks, 256, 0, st>>>(a);
+  else fuse_sum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a);
+  BRTPE_LAUNCH_CHECK();
+  return BRTPE_OK;
+}
+
+int nhwc_to_nchw_launch(int dtype, const void* src, int N, int H, int W, int C, int ld, int coff,
+                        void* dst, int dst_is_half, cudaStream_t st) {
+  BRTPE_CHECK_ARG(src && dst && N > 0 && H > 0 && W > 0 && C > 0 && ld >= coff + C,
+                  "nhwc_to_nchw: bad arguments");
+  dim3 grid(ceil_div(H * W, 64), ceil_div(C, 64), N);
+#define BRTPE_T(TS, TD)                                                                    \
+  nhwc_to_nchw_kernel<TS, TD><<<grid, 256, 0, st>>>(reinterpret_cast<const TS*>(src), N, H * W, C, \
+                                                   ld, coff, reinterpret_cast<TD*>(dst))
+  if (dtype == BRTPE_DT_F32) {
+    if (dst_is_half) BRTPE_T(float, __half);
+    else BRTPE_T(float, float);
+  } else {
+    if (dst_is_half) BRTPE_T(__nv_bfloat16, __half);
+    else BRTPE_T(__nv_bfloat16, float);
+  }
+#undef BRTPE_T
+  BRTPE_LAUNCH_CHECK();
+  return BRTPE_OK;
+}
+
+}  // namespace brtpe

@@ -1,0 +1,261 @@
+// C ABI of the convolution engine + the execution plan (a recorded launch list that is
+// replayed natively or as a CUDA graph).  One plan = one PoseHigherResolutionNet.forward for
+// a fixed (batch chunk, H, W); the host (Python) records it once and replays it per chunk.
+#include "conv_common.cuh"
+
+#include <vector>
+
+namespace brtpe {
+
+enum OpKind { OP_CONV = 0, OP_STEM = 1, OP_FUSE = 2, OP_TONCHW = 3 };
+
+struct Op {
+  int kind;
+  // conv
+  brtpe_conv_desc d;
+  const void* in;
+  const void* w;
+  const float* bias;
+  const void* res;
+  void* out;
+  UmmaConvPrepared* umma;  // non-null: tcgen05 path
+  // stem / tonchw / fuse
+  int i[12];
+  const void* terms[4];
+  int shifts[4], lds[4];
+  const float* stem_w;
+};
+
+static int choose_engine(const brtpe_conv_desc* d) {
+  if (d->engine == BRTPE_ENGINE_FFMA) return BRTPE_ENGINE_FFMA;
+  const char* why = nullptr;
+  const bool ok = umma_conv_supported(d, &why);
+  if (d->engine == BRTPE_ENGINE_UMMA) {
+    if (!ok) {
+      set_error("conv: tcgen05 engine requested but unsupported: %s", why ? why : "?");
+      return -1;
+    }
+    return BRTPE_ENGINE_UMMA;
+  }
+  return ok ? BRTPE_ENGINE_UMMA : BRTPE_ENGINE_FFMA;
+}
+
+static int run_op(const Op& op, cudaStream_t st) {
+  switch (op.kind) {
+    case OP_CONV:
+      if (op.umma) return umma_conv_launch(op.umma, op.bias, op.res, op.out, st);
+      return conv_ffma_launch(&op.d, op.in, op.w, op.bias, op.res, op.out, st);
+    case OP_STEM:
+      return stem_conv1_launch(op.in, op.i[0], op.i[1], op.i[2], op.i[3], op.stem_w, op.bias,
+                               op.i[4], op.out, op.i[5], st);
+    case OP_FUSE:
+      return fuse_sum_launch(op.i[0], op.i[1], op.terms, op.shifts, op.lds, op.i[2], op.i[3],
+                             op.i[4], op.i[5], op.out, op.i[6], op.i[7], st);
+    case OP_TONCHW:
+      return nhwc_to_nchw_launch(op.i[0], op.in, op.i[1], op.i[2], op.i[3], op.i[4], op.i[5],
+                                 op.i[6], op.out, op.i[7], st);
+  }
+  return BRTPE_EINVAL;
+}
+
+}  // namespace brtpe
+
+using namespace brtpe;
+
+struct brtpe_plan {
+  std::vector<Op> ops;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  ~brtpe_plan() {
+    for (auto& op : ops)
+      if (op.umma) umma_conv_release(op.umma);
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+  }
+};
+
+extern "C" int brtpe_conv_run(const brtpe_conv_desc* d, const void* in, const void* weights,
+                              const float* bias, const void* residual, void* out, void* stream) {
+  int rc = conv_validate(d);
+  if (rc) return rc;
+  BRTPE_CHECK_ARG(in && weights && out, "brtpe_conv_run: null tensor");
+  const int eng = choose_engine(d);
+  if (eng < 0) return BRTPE_EINVAL;
+  if (eng == BRTPE_ENGINE_UMMA) {
+    UmmaConvPrepared* p = umma_conv_prepare(d, in, weights);
+    if (!p) return BRTPE_ECUDA;
+    rc = umma_conv_launch(p, bias, residual, out, (cudaStream_t)stream);
+    umma_conv_release(p);
+    return rc;
+  }
+  return conv_ffma_launch(d, in, weights, bias, residual, out, (cudaStream_t)stream);
+}
+
+extern "C" int brtpe_conv_select_engine(const brtpe_conv_desc* d) {
+  int rc = conv_validate(d);
+  if (rc) return rc;
+  return choose_engine(d);
+}
+
+extern "C" int brtpe_stem_conv1(const void* img, int img_is_half, int N, int H, int W,
+                                const float* w, const float* bias, int Cout, void* out,
+                                int out_dtype, void* stream) {
+  return stem_conv1_launch(img, img_is_half, N, H, W, w, bias, Cout, out, out_dtype,
+                           (cudaStream_t)stream);
+}
+
+extern "C" int brtpe_fuse_sum(int dtype, int nterms, const void* const* terms,
+                              const int32_t* shifts, const int32_t* term_ld, int N, int H, int W,
+                              int C, void* out, int out_ld, int relu, void* stream) {
+  return fuse_sum_launch(dtype, nterms, terms, shifts, term_ld, N, H, W, C, out, out_ld, relu,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int brtpe_nhwc_to_nchw(int dtype, const void* src, int N, int H, int W, int C, int ld,
+                                  int coff, void* dst, int dst_is_half, void* stream) {
+  return nhwc_to_nchw_launch(dtype, src, N, H, W, C, ld, coff, dst, dst_is_half,
+                             (cudaStream_t)stream);
+}
+
+extern "C" brtpe_plan* brtpe_plan_create(void) { return new brtpe_plan(); }
+extern "C" void brtpe_plan_destroy(brtpe_plan* p) { delete p; }
+
+extern "C" int brtpe_plan_add_conv(brtpe_plan* pl, const brtpe_conv_desc* d, const void* in,
+                                   const void* weights, const float* bias, const void* residual,
+                                   void* out) {
+  BRTPE_CHECK_ARG(pl, "brtpe_plan_add_conv: null plan");
+  int rc = conv_validate(d);
+  if (rc) return rc;
+  BRTPE_CHECK_ARG(in && weights && out, "brtpe_plan_add_conv: null tensor");
+  const int eng = choose_engine(d);
+  if (eng < 0) return BRTPE_EINVAL;
+  Op op{};
+  op.kind = OP_CONV;
+  op.d = *d;
+  op.in = in; op.w = weights; op.bias = bias; op.res = residual; op.out = out;
+  op.umma = nullptr;
+  if (eng == BRTPE_ENGINE_UMMA) {
+    op.umma = umma_conv_prepare(d, in, weights);
+    if (!op.umma) return BRTPE_ECUDA;
+  }
+  pl->ops.push_back(op);
+  return BRTPE_OK;
+}
+
+extern "C" int brtpe_plan_add_stem(brtpe_plan* pl, const void* img, int img_is_half, int N, int H,
+                                   int W, const float* w, const float* bias, int Cout, void* out,
+                                   int out_dtype) {
+  BRTPE_CHECK_ARG(pl && img && w && out, "brtpe_plan_add_stem: null argument");
+  Op op{};
+  op.kind = OP_STEM;
+  op.in = img; op.stem_w = w; op.bias = bias; op.out = out;
+  op.i[0] = img_is_half; op.i[1] = N; op.i[2] = H; op.i[3] = W; op.i[4] = Cout; op.i[5] = out_dtype;
+  pl->ops.push_back(op);
+  return BRTPE_OK;
+}
+
+extern "C" int brtpe_plan_add_fuse(brtpe_plan* pl, int dtype, int nterms, const void* const* terms,
+                                   const int32_t* shifts, const int32_t* term_ld, int N, int H,
+                                   int W, int C, void* out, int out_ld, int relu) {
+  BRTPE_CHECK_ARG(pl && terms && shifts && term_ld && out && nterms >= 1 && nterms <= 4,
+                  "brtpe_plan_add_fuse: bad arguments");
+  Op op{};
+  op.kind = OP_FUSE;
+  for (int k = 0; k < nterms; ++k) {
+    op.terms[k] = terms[k];
+    op.shifts[k] = shifts[k];
+    op.lds[k] = term_ld[k];
+  }
+  op.out = out;
+  op.i[0] = dtype; op.i[1] = nterms; op.i[2] = N; op.i[3] = H; op.i[4] = W; op.i[5] = C;
+  op.i[6] = out_ld; op.i[7] = relu;
+  pl->ops.push_back(op);
+  return BRTPE_OK;
+}
+
+extern "C" int brtpe_plan_add_nhwc_to_nchw(brtpe_plan* pl, int dtype, const void* src, int N, int H,
+                                           int W, int C, int ld, int coff, void* dst,
+                                           int dst_is_half) {
+  BRTPE_CHECK_ARG(pl && src && dst, "brtpe_plan_add_nhwc_to_nchw: null argument");
+  Op op{};
+  op.kind = OP_TONCHW;
+  op.in = src; op.out = dst;
+  op.i[0] = dtype; op.i[1] = N; op.i[2] = H; op.i[3] = W; op.i[4] = C; op.i[5] = ld; op.i[6] = coff;
+  op.i[7] = dst_is_half;
+  pl->ops.push_back(op);
+  return BRTPE_OK;
+}
+
+extern "C" int brtpe_plan_num_ops(const brtpe_plan* pl) { return pl ? (int)pl->ops.size() : 0; }
+
+extern "C" double brtpe_plan_conv_flops(const brtpe_plan* pl) {
+  double f = 0;
+  if (pl)
+    for (auto& op : pl->ops)
+      if (op.kind == OP_CONV) f += conv_flops(&op.d);
+  return f;
+}
+
+extern "C" int brtpe_plan_run(brtpe_plan* pl, void* stream) {
+  BRTPE_CHECK_ARG(pl, "brtpe_plan_run: null plan");
+  for (auto& op : pl->ops) {
+    int rc = run_op(op, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return BRTPE_OK;
+}
+
+extern "C" int brtpe_plan_graph_launch(brtpe_plan* pl, void* stream) {
+  BRTPE_CHECK_ARG(pl, "brtpe_plan_graph_launch: null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!pl->exec) {
+    BRTPE_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = BRTPE_OK;
+    for (auto& op : pl->ops) {
+      rc = run_op(op, st);
+      if (rc) break;
+    }
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (rc) {
+      if (g) cudaGraphDestroy(g);
+      return rc;
+    }
+    if (e != cudaSuccess) {
+      set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+      return BRTPE_ECUDA;
+    }
+    pl->graph = g;
+    BRTPE_CUDA(cudaGraphInstantiate(&pl->exec, g, 0));
+  }
+  BRTPE_CUDA(cudaGraphLaunch(pl->exec, st));
+  return BRTPE_OK;
+}
+
+extern "C" int brtpe_plan_profile(brtpe_plan* pl, void* stream, float* ms_out, int32_t* kinds_out,
+                                  double* flops_out) {
+  BRTPE_CHECK_ARG(pl && ms_out, "brtpe_plan_profile: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = pl->ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) BRTPE_CUDA(cudaEventCreate(&e));
+  int rc = BRTPE_OK;
+  BRTPE_CUDA(cudaEventRecord(ev[0], st));
+  for (size_t i = 0; i < n && !rc; ++i) {
+    rc = run_op(pl->ops[i], st);
+    cudaEventRecord(ev[i + 1], st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (!rc && e != cudaSuccess) {
+    set_error("plan_profile: %s", cudaGetErrorString(e));
+    rc = BRTPE_ECUDA;
+  }
+  for (size_t i = 0; i < n && !rc; ++i) {
+    cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+    const Op& op = pl->ops[i];
+    if (kinds_out) kinds_out[i] = op.kind == OP_CONV ? (op.umma ? 0 : 1) : 2;
+    if (flops_out) flops_out[i] = op.kind == OP_CONV ? conv_flops(&op.d) : 0.0;
+  }
+  for (auto& evt : ev) cudaEventDestroy(evt);
+  return rc;
+}

@@ -1,0 +1,753 @@
+"""``PoseHigherResolutionNet`` -- drop-in for
+rtpe/third_party/pose_higher_hrnet.py:259-739, executed by libbrtpe.so.
+
+The module tree (names, shapes, buffers) is the reference's, so
+``network_to_half(model).load_state_dict(ckpt, strict=True)`` (rtpe/helpers.py:69-70)
+works unchanged and ``state_dict()`` has the same 1810 entries.  The parameters are only
+*containers*: ``forward`` never calls a torch operator on them.  At the first call for a
+given (chunk, H, W, precision) the model
+
+  1. folds every eval BatchNorm into its convolution (w' = w*gamma/sqrt(var+eps),
+     b' = beta - mean*gamma/sqrt(var+eps)), re-lays the weights out per tap / K-major and
+     rounds them to bf16 for the tcgen05 path (fp32 for the CUDA-core path),
+  2. records the whole network as a launch plan in the native library
+     (brtpe_plan_*: NHWC activations from a liveness-packed arena, one fused launch per
+     conv+BN[+residual][+ReLU], one per cross-resolution fuse sum, the 4x4/s2 transposed
+     conv as four parity phases writing the 2x map, the 48+34 channel concat as two
+     writers of one 96-channel buffer),
+  3. replays that plan as a CUDA graph per chunk of images.
+
+Precision follows the parameters like the reference: fp32 parameters -> fp32 activations
+on the FFMA path (error ~1e-6 of the tensor max); half/bfloat16 parameters (what
+``network_to_half`` produces) -> bf16 activations, bf16 tcgen05 MMA with fp32 accumulate.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+BN_MOMENTUM = 0.1
+logger = logging.getLogger(__name__)
+
+_TAPS3 = [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+
+
+class NoOpModule(nn.Module):
+    """Parameter-free placeholder (pose_higher_hrnet.py:24-32)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+
+    def forward(self, *args, **kwargs):
+        return args
+
+
+def _conv(cin, cout, k, stride=1, bias=False):
+    return nn.Conv2d(cin, cout, kernel_size=k, stride=stride, padding=(k - 1) // 2, bias=bias)
+
+
+class BasicBlock(nn.Module):
+    """Parameter container of pose_higher_hrnet.py:46-75."""
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = _conv(inplanes, planes, 3, stride)
+        self.bn1 = nn.BatchNorm2d(planes, momentum=BN_MOMENTUM)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = _conv(planes, planes, 3)
+        self.bn2 = nn.BatchNorm2d(planes, momentum=BN_MOMENTUM)
+        self.downsample = downsample
+        self.stride = stride
+
+
+class Bottleneck(nn.Module):
+    """Parameter container of pose_higher_hrnet.py:78-116."""
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = _conv(inplanes, planes, 1)
+        self.bn1 = nn.BatchNorm2d(planes, momentum=BN_MOMENTUM)
+        self.conv2 = _conv(planes, planes, 3, stride)
+        self.bn2 = nn.BatchNorm2d(planes, momentum=BN_MOMENTUM)
+        self.conv3 = _conv(planes, planes * self.expansion, 1)
+        self.bn3 = nn.BatchNorm2d(planes * self.expansion, momentum=BN_MOMENTUM)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.stride = stride
+
+
+class HighResolutionModule(nn.Module):
+    """Parameter container of pose_higher_hrnet.py:119-256 (BASIC blocks)."""
+
+    def __init__(self, num_branches, blocks, num_blocks, num_inchannels, num_channels,
+                 fuse_method, multi_scale_output=True):
+        super().__init__()
+        for what, seq in (("NUM_BLOCKS", num_blocks), ("NUM_CHANNELS", num_channels),
+                          ("NUM_INCHANNELS", num_inchannels)):
+            if num_branches != len(seq):
+                msg = "NUM_BRANCHES({}) <> {}({})".format(num_branches, what, len(seq))
+                logger.error(msg)
+                raise ValueError(msg)
+        self.num_inchannels = num_inchannels
+        self.fuse_method = fuse_method
+        self.num_branches = num_branches
+        self.multi_scale_output = multi_scale_output
+        branches = []
+        for i in range(num_branches):
+            cin, cout = num_inchannels[i], num_channels[i] * blocks.expansion
+            down = None
+            if cin != cout:
+                down = nn.Sequential(_conv(cin, cout, 1),
+                                     nn.BatchNorm2d(cout, momentum=BN_MOMENTUM))
+            layers = [blocks(cin, num_channels[i], 1, down)]
+            num_inchannels[i] = cout
+            layers += [blocks(cout, num_channels[i]) for _ in range(1, num_blocks[i])]
+            branches.append(nn.Sequential(*layers))
+        self.branches = nn.ModuleList(branches)
+        self.fuse_layers = self._make_fuse_layers()
+        self.relu = nn.ReLU(True)
+
+    def _make_fuse_layers(self):
+        if self.num_branches == 1:
+            return None
+        ch = self.num_inchannels
+        rows = []
+        for i in range(self.num_branches if self.multi_scale_output else 1):
+            row = []
+            for j in range(self.num_branches):
+                if j > i:       # 1x1 + BN, then nearest upsample x2^(j-i)
+                    row.append(nn.Sequential(
+                        _conv(ch[j], ch[i], 1), nn.BatchNorm2d(ch[i]),
+                        nn.Upsample(scale_factor=2 ** (j - i), mode="nearest")))
+                elif j == i:
+                    row.append(None)
+                else:           # chain of (i-j) stride-2 3x3 convs
+                    chain = []
+                    for k in range(i - j):
+                        last = k == i - j - 1
+                        cout = ch[i] if last else ch[j]
+                        mods = [_conv(ch[j], cout, 3, 2), nn.BatchNorm2d(cout)]
+                        if not last:
+                            mods.append(nn.ReLU(True))
+                        chain.append(nn.Sequential(*mods))
+                    row.append(nn.Sequential(*chain))
+            rows.append(nn.ModuleList(row))
+        return nn.ModuleList(rows)
+
+    def get_num_inchannels(self):
+        return self.num_inchannels
+
+
+# ---------------------------------------------------------------------------------------
+# plan recording (a tiny IR -> liveness-packed arena -> native plan)
+# ---------------------------------------------------------------------------------------
+class _T:
+    """virtual NHWC tensor"""
+    __slots__ = ("n", "h", "w", "ld", "first", "last", "buf", "keep")
+
+    def __init__(self, n, h, w, ld):
+        self.n, self.h, self.w, self.ld = n, h, w, ld
+        self.first = None
+        self.last = None
+        self.buf = None
+        self.keep = False
+
+    def numel(self):
+        return self.n * self.h * self.w * self.ld
+
+
+class _Recorder:
+    def __init__(self, model, n, h, w, mode, engine, device, in_is_half):
+        self.model = model
+        self.n, self.h, self.w = n, h, w
+        self.mode = mode                          # "fp32" | "bf16"
+        self.engine = engine                      # ENGINE_AUTO | FFMA | UMMA
+        self.device = device
+        self.dt = L.DT_F32 if mode == "fp32" else L.DT_BF16
+        self.tdtype = torch.float32 if mode == "fp32" else torch.bfloat16
+        self.ops = []
+        self.tensors = []
+        self.keepalive = []                       # packed weights / biases
+        self.in_is_half = in_is_half
+
+    # -- tensors
+    def new(self, n, h, w, ld):
+        t = _T(n, h, w, ld)
+        self.tensors.append(t)
+        return t
+
+    def _touch(self, t, idx):
+        if t.first is None:
+            t.first = idx
+        t.last = idx
+
+    # -- weights
+    def _fold(self, conv, bn):
+        """-> (w (Cout,Cin,kh,kw) f32, bias (Cout,) f32) with eval BN folded in."""
+        w = conv.weight.detach().to(self.device, torch.float32)
+        if bn is None:
+            b = conv.bias.detach().to(self.device, torch.float32) if conv.bias is not None \
+                else torch.zeros(w.shape[0], device=self.device)
+            return w, b
+        g = bn.weight.detach().to(self.device, torch.float32)
+        beta = bn.bias.detach().to(self.device, torch.float32)
+        mu = bn.running_mean.detach().to(self.device, torch.float32)
+        var = bn.running_var.detach().to(self.device, torch.float32)
+        scale = g / torch.sqrt(var + bn.eps)
+        w = w * scale.view(-1, 1, 1, 1)
+        b = beta - mu * scale
+        if conv.bias is not None:
+            b = b + conv.bias.detach().to(self.device, torch.float32) * scale
+        return w, b
+
+    def _pack(self, wt, desc, cin_store):
+        """wt: (ntaps, Cout, Cin) f32 -> packed weight tensor for the chosen engine."""
+        lib = L.load()
+        ntaps, cout, cin = wt.shape
+        if cin_store > cin:                                   # zero weights for pad channels
+            wt = torch.cat((wt, wt.new_zeros(ntaps, cout, cin_store - cin)), dim=2)
+        eng = lib.brtpe_conv_select_engine(C.byref(desc))
+        if eng < 0:
+            L.check(eng, "brtpe_conv_select_engine")
+        if eng == L.ENGINE_UMMA:
+            cin_pad, cout_pad = C.c_int(0), C.c_int(0)
+            lib.brtpe_umma_weight_dims(cin_store, desc.Cout_store, C.byref(cin_pad),
+                                       C.byref(cout_pad))
+            packed = torch.zeros((ntaps, cout_pad.value, cin_pad.value), dtype=torch.bfloat16,
+                                 device=self.device)
+            packed[:, :cout, :cin_store] = wt.to(torch.bfloat16)
+        else:
+            if self.mode == "bf16":                            # same operand rounding as tcgen05
+                wt = wt.to(torch.bfloat16).to(torch.float32)
+            packed = wt.permute(0, 2, 1).contiguous()          # (ntaps, Cin, Cout) f32
+        return packed
+
+    # -- ops
+    def conv(self, x, conv, bn, relu, residual=None, out=None, out_coff=0, in_coff=0,
+             cin_store=None, cout_store=None):
+        """conv (+BN) (+residual) (+ReLU) over virtual tensor x -> virtual tensor."""
+        k = conv.kernel_size[0]
+        s = conv.stride[0]
+        cin, cout = conv.in_channels, conv.out_channels
+        cin_store = cin if cin_store is None else cin_store
+        cout_store = cout if cout_store is None else cout_store
+        ho, wo = x.h // s, x.w // s
+        if out is None:
+            out = self.new(x.n, ho, wo, max(cout_store, (cout_store + 7) // 8 * 8))
+        taps = _TAPS3 if k == 3 else [(0, 0)]
+        w, b = self._fold(conv, bn)
+        wt = torch.stack([w[:, :, dy + (k // 2), dx + (k // 2)] for dy, dx in taps], 0)
+        d = self._desc(x, in_coff, cin_store, taps, s, ho, wo, out, 1, 0, 0, cout, cout_store,
+                       out_coff, residual, relu)
+        self._emit_conv(d, x, wt, b, residual, out, cin_store)
+        return out
+
+    def deconv4x4s2(self, x, deconv, bn, cin_store):
+        """ConvTranspose2d(k4,s2,p1)+BN+ReLU as four output-parity 2x2 convs."""
+        cin, cout = deconv.in_channels, deconv.out_channels
+        out = self.new(x.n, 2 * x.h, 2 * x.w, cout)
+        w = deconv.weight.detach().to(self.device, torch.float32)          # (Cin,Cout,4,4)
+        g = bn.weight.detach().to(self.device, torch.float32)
+        scale = g / torch.sqrt(bn.running_var.detach().to(self.device, torch.float32) + bn.eps)
+        b = bn.bias.detach().to(self.device, torch.float32) - \
+            bn.running_mean.detach().to(self.device, torch.float32) * scale
+        w = w * scale.view(1, -1, 1, 1)
+        for a in (0, 1):
+            ysel = [(0, 1), (-1, 3)] if a == 0 else [(1, 0), (0, 2)]       # (dy, kh)
+            for bb in (0, 1):
+                xsel = [(0, 1), (-1, 3)] if bb == 0 else [(1, 0), (0, 2)]
+                taps, mats = [], []
+                for dy, kh in ysel:
+                    for dx, kw in xsel:
+                        taps.append((dy, dx))
+                        mats.append(w[:, :, kh, kw].t())                   # (Cout, Cin)
+                wt = torch.stack(mats, 0)
+                d = self._desc(x, 0, cin_store, taps, 1, x.h, x.w, out, 2, a, bb, cout, cout, 0,
+                               None, True)
+                self._emit_conv(d, x, wt, b, None, out, cin_store)
+        return out
+
+    def _desc(self, x, in_coff, cin, taps, stride, hm, wm, out, out_scale, oy, ox, cout,
+              cout_store, out_coff, residual, relu):
+        d = L.ConvDesc()
+        d.dtype = self.dt
+        d.engine = self.engine if self.mode == "bf16" else L.ENGINE_FFMA
+        d.N, d.Hin, d.Win = x.n, x.h, x.w
+        d.Cin, d.in_ld, d.in_coff = cin, x.ld, in_coff
+        d.Hm, d.Wm, d.in_stride = hm, wm, stride
+        d.ntaps = len(taps)
+        for i, (dy, dx) in enumerate(taps):
+            d.tap_dy[i], d.tap_dx[i] = dy, dx
+        d.Hout, d.Wout = out.h, out.w
+        d.out_scale, d.out_oy, d.out_ox = out_scale, oy, ox
+        d.Cout, d.out_ld, d.out_coff = cout, out.ld, out_coff
+        d.res_ld = residual.ld if residual is not None else 0
+        d.res_coff = 0
+        d.relu = int(bool(relu))
+        d.Cout_store = cout_store
+        return d
+
+    def _emit_conv(self, d, x, wt, bias, residual, out, cin_store):
+        packed = self._pack(wt, d, cin_store)
+        bias = bias.contiguous()
+        self.keepalive += [packed, bias]
+        idx = len(self.ops)
+        self.ops.append(("conv", d, x, packed, bias, residual, out))
+        self._touch(x, idx)
+        if residual is not None:
+            self._touch(residual, idx)
+        self._touch(out, idx)
+
+    def stem(self, conv, bn):
+        w, b = self._fold(conv, bn)                                        # (64,3,3,3)
+        wp = w.permute(2, 3, 1, 0).reshape(27, w.shape[0]).contiguous()    # (ky,kx,ci) x Cout
+        out = self.new(self.n, self.h // 2, self.w // 2, w.shape[0])
+        self.keepalive += [wp, b]
+        idx = len(self.ops)
+        self.ops.append(("stem", wp, b.contiguous(), out))
+        self._touch(out, idx)
+        return out
+
+    def fuse(self, terms, shifts, c, relu, out=None):
+        t0 = terms[0]
+        if out is None:
+            out = self.new(t0.n, t0.h << shifts[0], t0.w << shifts[0], c)
+        idx = len(self.ops)
+        self.ops.append(("fuse", list(terms), list(shifts), c, relu, out))
+        for t in terms:
+            self._touch(t, idx)
+        self._touch(out, idx)
+        return out
+
+    def to_nchw(self, x, c, coff, dst):
+        idx = len(self.ops)
+        self.ops.append(("nchw", x, c, coff, dst))
+        self._touch(x, idx)
+
+    # -- arena + native plan
+    def build(self, in_buf):
+        lib = L.load()
+        esize = 4 if self.mode == "fp32" else 2
+        free = []                                  # (bytes, tensor) of released buffers
+        release_at = {}
+        for t in self.tensors:
+            if t.first is not None and not t.keep:
+                release_at.setdefault(t.last, []).append(t)
+        total = 0
+        for idx, op in enumerate(self.ops):
+            for t in self.tensors:
+                if t.first == idx and t.buf is None:
+                    need = t.numel() * esize
+                    best = None
+                    for k, (nb, buf) in enumerate(free):
+                        if nb >= need and (best is None or nb < free[best][0]):
+                            best = k
+                    if best is not None:
+                        nb, buf = free.pop(best)
+                    else:
+                        nb = (need + 255) // 256 * 256
+                        buf = torch.zeros(nb, dtype=torch.uint8, device=self.device)
+                        total += nb
+                    t.buf = (nb, buf)
+            for t in release_at.get(idx, []):
+                free.append(t.buf)
+        self.arena_bytes = total
+
+        plan = lib.brtpe_plan_create()
+        try:
+            for op in self.ops:
+                kind = op[0]
+                if kind == "conv":
+                    _, d, x, packed, bias, residual, out = op
+                    L.check(lib.brtpe_plan_add_conv(
+                        plan, C.byref(d), L.ptr(x.buf[1]), L.ptr(packed), L.ptr(bias),
+                        L.ptr(residual.buf[1]) if residual is not None else None,
+                        L.ptr(out.buf[1])), "brtpe_plan_add_conv")
+                elif kind == "stem":
+                    _, wp, b, out = op
+                    L.check(lib.brtpe_plan_add_stem(
+                        plan, L.ptr(in_buf), int(self.in_is_half), self.n, self.h, self.w,
+                        L.ptr(wp), L.ptr(b), wp.shape[1], L.ptr(out.buf[1]), self.dt),
+                        "brtpe_plan_add_stem")
+                elif kind == "fuse":
+                    _, terms, shifts, c, relu, out = op
+                    nt = len(terms)
+                    tp = (C.c_void_p * nt)(*[t.buf[1].data_ptr() for t in terms])
+                    sh = (C.c_int32 * nt)(*shifts)
+                    ld = (C.c_int32 * nt)(*[t.ld for t in terms])
+                    L.check(lib.brtpe_plan_add_fuse(
+                        plan, self.dt, nt, tp, sh, ld, out.n, out.h, out.w, c,
+                        L.ptr(out.buf[1]), out.ld, int(bool(relu))), "brtpe_plan_add_fuse")
+                elif kind == "nchw":
+                    _, x, c, coff, dst = op
+                    L.check(lib.brtpe_plan_add_nhwc_to_nchw(
+                        plan, self.dt, L.ptr(x.buf[1]), x.n, x.h, x.w, c, x.ld, coff,
+                        L.ptr(dst), int(dst.dtype == torch.float16)),
+                        "brtpe_plan_add_nhwc_to_nchw")
+        except Exception:
+            lib.brtpe_plan_destroy(plan)
+            raise
+        return plan
+
+
+class _CompiledPlan:
+    def __init__(self, handle, in_buf, outs, recorder):
+        self.handle = handle
+        self.in_buf = in_buf
+        self.outs = outs
+        self.recorder = recorder            # keeps arena + packed weights alive
+        self.num_ops = L.load().brtpe_plan_num_ops(handle)
+        self.conv_flops = L.load().brtpe_plan_conv_flops(handle)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                L.load(require_cuda=False).brtpe_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class PoseHigherResolutionNet(nn.Module):
+    """Same constructor and ``forward(x) -> [y0, y1]`` as the reference
+    (pose_higher_hrnet.py:266-287, :637-686)."""
+
+    BLOCK_TYPES = {"BASIC": BasicBlock, "BOTTLENECK": Bottleneck}
+
+    def __init__(self, num_joints=17, tag_per_joint=True, final_conv_ksize=1,
+                 pretrained_layers=["*"], inplanes=64,
+                 s2_modules=1, s2_branches=2, s2_block_type="BASIC",
+                 s2_blocks=[4, 4], s2_chans=[48, 96], s2_fuse_method="SUM",
+                 s3_modules=4, s3_branches=3, s3_block_type="BASIC",
+                 s3_blocks=[4, 4, 4], s3_chans=[48, 96, 192], s3_fuse_method="SUM",
+                 s4_modules=3, s4_branches=4, s4_block_type="BASIC",
+                 s4_blocks=[4, 4, 4, 4], s4_chans=[48, 96, 192, 384], s4_fuse_method="SUM",
+                 deconvs=1, deconv_chans=[48], deconv_ksize=[4], deconv_num_blocks=4,
+                 deconv_cat=[True], with_ae_loss=(True, False)):
+        super().__init__()
+        for bt in (s2_block_type, s3_block_type, s4_block_type):
+            if bt != "BASIC":
+                raise NotImplementedError("stage block type %r: only BASIC stages (the W32/W48 "
+                                          "configurations) are implemented" % bt)
+        if final_conv_ksize != 1:
+            raise NotImplementedError("final_conv_ksize=%r: only the 1x1 heads of the W48 "
+                                      "configuration are implemented" % final_conv_ksize)
+        if deconvs > 1 or any(k != 4 for k in deconv_ksize[:deconvs]):
+            raise NotImplementedError("only one 4x4/stride-2 deconv stage is implemented")
+        self.inplanes = inplanes
+        self.cfg = {"NUM_JOINTS": num_joints, "TAG_PER_JOINT": tag_per_joint,
+                    "FINAL_CONV_KSIZE": final_conv_ksize, "PRETRAINED_LAYERS": pretrained_layers}
+        stages = [("STAGE2", s2_modules, s2_branches, s2_blocks, s2_chans, s2_fuse_method),
+                  ("STAGE3", s3_modules, s3_branches, s3_blocks, s3_chans, s3_fuse_method),
+                  ("STAGE4", s4_modules, s4_branches, s4_blocks, s4_chans, s4_fuse_method)]
+        for name, nm, nb, blocks, chans, fm in stages:
+            self.cfg[name] = {"num_modules": nm, "num_branches": nb, "block_cls": BasicBlock,
+                              "num_blocks": blocks, "num_channels": chans, "fuse_method": fm}
+        self.cfg["DECONV"] = {"num_deconvs": deconvs, "num_channels": deconv_chans,
+                              "kernel_size": deconv_ksize, "num_basic_blocks": deconv_num_blocks,
+                              "cat_output": deconv_cat}
+
+        # stem
+        self.conv1 = _conv(3, 64, 3, 2)
+        self.bn1 = nn.BatchNorm2d(64, momentum=BN_MOMENTUM)
+        self.conv2 = _conv(64, 64, 3, 2)
+        self.bn2 = nn.BatchNorm2d(64, momentum=BN_MOMENTUM)
+        self.relu = nn.ReLU(inplace=True)
+        self.layer1 = self._make_layer(Bottleneck, 64, 4)
+
+        pre = [256]
+        for si, (name, nm, nb, blocks, chans, fm) in enumerate(stages):
+            cur = [c * BasicBlock.expansion for c in chans]
+            setattr(self, "transition%d" % (si + 1), self._make_transition_layer(pre, cur))
+            last_stage = si == len(stages) - 1
+            mods = []
+            inch = cur
+            for m in range(nm):
+                multi = not (last_stage and m == nm - 1)
+                mods.append(HighResolutionModule(nb, BasicBlock, blocks, inch, chans, fm, multi))
+                inch = mods[-1].get_num_inchannels()
+            setattr(self, "stage%d" % (si + 2), nn.Sequential(*mods))
+            pre = inch
+
+        ae_dims = num_joints if tag_per_joint else 1
+        heads = []
+        cin = pre[0]
+        for i in range(deconvs + 1):
+            if i > 0:
+                cin = deconv_chans[i - 1]
+            cout = num_joints + (ae_dims if with_ae_loss[i] else 0)
+            heads.append(nn.Conv2d(cin, cout, final_conv_ksize, 1,
+                                   1 if final_conv_ksize == 3 else 0))
+        self.final_layers = nn.ModuleList(heads)
+
+        dls = []
+        cin = pre[0]
+        for i in range(deconvs):
+            if deconv_cat[i]:
+                cin += num_joints + (ae_dims if with_ae_loss[i] else 0)
+            cout = deconv_chans[i]
+            layers = [nn.Sequential(
+                nn.ConvTranspose2d(cin, cout, kernel_size=4, stride=2, padding=1,
+                                   output_padding=0, bias=False),
+                nn.BatchNorm2d(cout, momentum=BN_MOMENTUM), nn.ReLU(inplace=True))]
+            layers += [nn.Sequential(BasicBlock(cout, cout)) for _ in range(deconv_num_blocks)]
+            dls.append(nn.Sequential(*layers))
+            cin = cout
+        self.deconv_layers = nn.ModuleList(dls)
+
+        self.num_deconvs = deconvs
+        self.pretrained_layers = pretrained_layers
+        self.deconv_cat = deconv_cat
+        self.num_joints = num_joints
+
+        # execution options (not part of the reference API)
+        self.chunk_size = 8            # images per plan replay (keeps a layer's in+out in L2)
+        self.conv_engine = L.ENGINE_AUTO
+        self.use_cuda_graph = True
+        self._plans = {}
+        self._sig = None
+        self._frozen = False
+
+    # ---------------------------------------------------------------- construction helpers
+    def _make_layer(self, block, planes, blocks, stride=1):
+        down = None
+        if stride != 1 or self.inplanes != planes * block.expansion:
+            down = nn.Sequential(
+                nn.Conv2d(self.inplanes, planes * block.expansion, kernel_size=1, stride=stride,
+                          bias=False),
+                nn.BatchNorm2d(planes * block.expansion, momentum=BN_MOMENTUM))
+        layers = [block(self.inplanes, planes, stride, down)]
+        self.inplanes = planes * block.expansion
+        layers += [block(self.inplanes, planes) for _ in range(1, blocks)]
+        return nn.Sequential(*layers)
+
+    def _make_transition_layer(self, pre, cur):
+        out = []
+        for i, c in enumerate(cur):
+            if i < len(pre):
+                if c != pre[i]:
+                    out.append(nn.Sequential(_conv(pre[i], c, 3), nn.BatchNorm2d(c),
+                                             nn.ReLU(inplace=True)))
+                else:
+                    out.append(NoOpModule())
+            else:
+                chain = []
+                for j in range(i + 1 - len(pre)):
+                    cout = c if j == i - len(pre) else pre[-1]
+                    chain.append(nn.Sequential(_conv(pre[-1], cout, 3, 2), nn.BatchNorm2d(cout),
+                                               nn.ReLU(inplace=True)))
+                out.append(nn.Sequential(*chain))
+        return nn.ModuleList(out)
+
+    # ---------------------------------------------------------------- weights bookkeeping
+    def invalidate_plans(self):
+        """Drop the compiled plans (packed weights are rebuilt at the next forward)."""
+        self._plans = {}
+        self._sig = None
+
+    def _signature(self):
+        """Cheap fingerprint of every parameter / buffer (storage address + in-place version
+        counter): load_state_dict, .half(), .to() and optimizer steps all change it."""
+        acc = 0
+        for t in list(self.parameters()) + list(self.buffers()):
+            acc = (acc * 1000003 + t.data_ptr() * 31 + t._version) & 0xFFFFFFFFFFFFFFFF
+        return acc
+
+    def freeze(self, frozen=True):
+        """Skip the per-forward parameter fingerprint (weights promised not to change)."""
+        self._frozen = bool(frozen)
+        return self
+
+    def init_weights(self, pretrained="", verbose=True):
+        """pose_higher_hrnet.py:688-727: N(0, 0.001) convs, unit BN, optional partial load."""
+        import os
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+                nn.init.normal_(m.weight, std=0.001)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+        if os.path.isfile(pretrained):
+            sd = torch.load(pretrained)
+            own = set(n for n, _ in self.named_parameters()) | set(n for n, _ in self.named_buffers())
+            pick = {n: v for n, v in sd.items()
+                    if (n.split(".")[0] in self.pretrained_layers or self.pretrained_layers[0] == "*")
+                    and n in own}
+            self.load_state_dict(pick, strict=False)
+        self.invalidate_plans()
+
+    # ---------------------------------------------------------------- plan
+    def _record(self, n, h, w, mode, device, in_is_half, out_half):
+        R = _Recorder(self, n, h, w, mode, self.conv_engine, device, in_is_half)
+        x = R.stem(self.conv1, self.bn1)
+        x = R.conv(x, self.conv2, self.bn2, True)
+        for blk in self.layer1:
+            res = x
+            if blk.downsample is not None:
+                res = R.conv(x, blk.downsample[0], blk.downsample[1], False)
+            t = R.conv(x, blk.conv1, blk.bn1, True)
+            t = R.conv(t, blk.conv2, blk.bn2, True)
+            x = R.conv(t, blk.conv3, blk.bn3, True, residual=res)
+
+        ys = [x]
+        nj = self.num_joints
+        head0 = self.final_layers[0]
+        cat = self.deconv_cat[0] if self.num_deconvs else False
+        cat_ld = None
+        for si in (1, 2, 3):
+            trans = getattr(self, "transition%d" % si)
+            stage = getattr(self, "stage%d" % (si + 1))
+            xs = []
+            for i, tr in enumerate(trans):
+                if isinstance(tr, NoOpModule):
+                    xs.append(ys[i])
+                elif i < len(ys) and not isinstance(tr[0], nn.Sequential):
+                    xs.append(R.conv(ys[i], tr[0], tr[1], True))
+                else:
+                    t = ys[-1]
+                    for sub in tr:
+                        t = R.conv(t, sub[0], sub[1], True)
+                    xs.append(t)
+            for mi, mod in enumerate(stage):
+                for i in range(mod.num_branches):
+                    for blk in mod.branches[i]:
+                        t = R.conv(xs[i], blk.conv1, blk.bn1, True)
+                        xs[i] = R.conv(t, blk.conv2, blk.bn2, True, residual=xs[i])
+                outs = []
+                final_module = si == 3 and mi == len(stage) - 1
+                for i in range(len(mod.fuse_layers)):
+                    terms, shifts = [], []
+                    for j in range(mod.num_branches):
+                        f = mod.fuse_layers[i][j]
+                        if j == i:
+                            terms.append(xs[j]); shifts.append(0)
+                        elif j > i:
+                            terms.append(R.conv(xs[j], f[0], f[1], False)); shifts.append(j - i)
+                        else:
+                            t = xs[j]
+                            for k, sub in enumerate(f):
+                                t = R.conv(t, sub[0], sub[1], k != len(f) - 1)
+                            terms.append(t); shifts.append(0)
+                    c = mod.num_inchannels[i]
+                    dst = None
+                    if final_module and i == 0 and cat:
+                        # stage-4 output lands in channels [0, c) of the concat buffer
+                        cat_ld = (c + head0.out_channels + 15) // 16 * 16
+                        dst = R.new(n, xs[0].h, xs[0].w, cat_ld)
+                    outs.append(R.fuse(terms, shifts, c, True, out=dst))
+                xs = outs
+            ys = xs
+
+        x = ys[0]
+        c0 = head0.in_channels
+        odt = torch.float16 if out_half else torch.float32
+        y0_out = torch.empty((n, head0.out_channels, x.h, x.w), dtype=odt, device=device)
+        outs = [y0_out]
+        if cat:
+            pad_store = cat_ld - c0
+            R.conv(x, head0, None, False, out=x, out_coff=c0, in_coff=0, cin_store=c0,
+                   cout_store=pad_store)
+            R.to_nchw(x, head0.out_channels, c0, y0_out)
+        else:
+            y = R.conv(x, head0, None, False)
+            R.to_nchw(y, head0.out_channels, 0, y0_out)
+        for i in range(self.num_deconvs):
+            dl = self.deconv_layers[i]
+            x = R.deconv4x4s2(x, dl[0][0], dl[0][1], x.ld if cat else dl[0][0].in_channels)
+            for k in range(1, len(dl)):
+                blk = dl[k][0]
+                t = R.conv(x, blk.conv1, blk.bn1, True)
+                x = R.conv(t, blk.conv2, blk.bn2, True, residual=x)
+            head = self.final_layers[i + 1]
+            y = R.conv(x, head, None, False)
+            yo = torch.empty((n, head.out_channels, x.h, x.w), dtype=odt, device=device)
+            R.to_nchw(y, head.out_channels, 0, yo)
+            outs.append(yo)
+        return R, outs
+
+    def _get_plan(self, n, h, w, mode, device, in_dtype):
+        key = (n, h, w, mode, str(device), in_dtype, self.conv_engine)
+        plan = self._plans.get(key)
+        if plan is None:
+            in_is_half = in_dtype == torch.float16
+            in_buf = torch.empty((n, 3, h, w), dtype=in_dtype, device=device)
+            with torch.cuda.device(device):
+                R, outs = self._record(n, h, w, mode, device, in_is_half, in_is_half)
+                handle = R.build(in_buf)
+            plan = _CompiledPlan(handle, in_buf, outs, R)
+            self._plans[key] = plan
+        return plan
+
+    def _mode(self):
+        dt = self.conv1.weight.dtype
+        return "fp32" if dt == torch.float32 else "bf16"
+
+    # ---------------------------------------------------------------- forward
+    def forward(self, x):
+        lib = L.load()
+        if not isinstance(x, torch.Tensor) or not x.is_cuda:
+            raise L.BrtpeError("PoseHigherResolutionNet.forward needs a CUDA tensor "
+                               "(no CPU fallback); got %r" % (getattr(x, "device", type(x)),))
+        if self.training:
+            raise L.BrtpeError("this implementation is inference-only: call .eval() "
+                               "(BatchNorm is folded with its running statistics)")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError("expected input (N, 3, H, W), got %s" % (tuple(x.shape),))
+        n, _, h, w = x.shape
+        if h % 32 or w % 32:
+            raise ValueError("H and W must be multiples of 32 (got %dx%d)" % (h, w))
+        if x.dtype == torch.bfloat16:
+            x = x.to(torch.float32)
+        if x.dtype not in (torch.float32, torch.float16):
+            raise ValueError("input dtype must be float32 or float16")
+        mode = self._mode()
+        dev = x.device
+        x = x.contiguous()
+        if not self._frozen or self._sig is None:
+            sig = self._signature()
+            if sig != self._sig:
+                self._plans = {}
+                self._sig = sig
+        nb = min(self.chunk_size, n)
+        odt = torch.float16 if x.dtype == torch.float16 else torch.float32
+        results = None
+        with torch.cuda.device(dev):
+            st = L.stream_ptr(dev)
+            for s0 in range(0, n, nb):
+                cn = min(nb, n - s0)
+                plan = self._get_plan(cn, h, w, mode, dev, x.dtype)
+                plan.in_buf.copy_(x[s0:s0 + cn])
+                if self.use_cuda_graph:
+                    L.check(lib.brtpe_plan_graph_launch(plan.handle, st), "brtpe_plan_graph_launch")
+                else:
+                    L.check(lib.brtpe_plan_run(plan.handle, st), "brtpe_plan_run")
+                if results is None:
+                    results = [torch.empty((n,) + tuple(o.shape[1:]), dtype=odt, device=dev)
+                               for o in plan.outs]
+                for r, o in zip(results, plan.outs):
+                    r[s0:s0 + cn].copy_(o)
+        return results
+
+    # ---------------------------------------------------------------- introspection
+    def plan_profile(self, n, h, w, in_dtype=torch.float32):
+        """Per-launch device times of one plan replay: (ms[], kind[], flops[])."""
+        lib = L.load()
+        dev = self.conv1.weight.device
+        plan = self._get_plan(n, h, w, self._mode(), dev, in_dtype)
+        k = plan.num_ops
+        ms = (C.c_float * k)()
+        kinds = (C.c_int32 * k)()
+        fl = (C.c_double * k)()
+        with torch.cuda.device(dev):
+            L.check(lib.brtpe_plan_profile(plan.handle, L.stream_ptr(dev), ms, kinds, fl),
+                    "brtpe_plan_profile")
+        return list(ms), list(kinds), list(fl)

@@ -1,0 +1,80 @@
+"""Helpers for the conv parity tests: drive brtpe_conv_run for a standard Conv2d and build
+the torch reference of the same op (the product never uses torch convs)."""
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+
+from rtpe_b200 import _lib as L
+
+TAPS3 = [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+
+
+def make_desc(dtype, engine, n, h, w, cin, cout, k, stride, relu, in_ld=None, in_coff=0,
+              out_ld=None, out_coff=0, cout_store=None, res_ld=0):
+    d = L.ConvDesc()
+    taps = TAPS3 if k == 3 else [(0, 0)]
+    ho, wo = h // stride, w // stride
+    cout_store = cout if cout_store is None else cout_store
+    d.dtype, d.engine = dtype, engine
+    d.N, d.Hin, d.Win = n, h, w
+    d.Cin, d.in_ld, d.in_coff = cin, (in_ld or cin), in_coff
+    d.Hm, d.Wm, d.in_stride = ho, wo, stride
+    d.ntaps = len(taps)
+    for i, (dy, dx) in enumerate(taps):
+        d.tap_dy[i], d.tap_dx[i] = dy, dx
+    d.Hout, d.Wout, d.out_scale, d.out_oy, d.out_ox = ho, wo, 1, 0, 0
+    d.Cout = cout
+    d.out_ld = out_ld or ((cout_store + 7) // 8 * 8)
+    d.out_coff = out_coff
+    d.res_ld, d.res_coff = res_ld, 0
+    d.relu = int(relu)
+    d.Cout_store = cout_store
+    return d, taps
+
+
+def pack_weights(lib, w, taps, k, desc, engine_used, bf16_round):
+    """w (Cout,Cin,k,k) f32 -> packed tensor for engine_used."""
+    wt = torch.stack([w[:, :, dy + k // 2, dx + k // 2] for dy, dx in taps], 0)  # (T,Cout,Cin)
+    if engine_used == L.ENGINE_UMMA:
+        cp, op = C.c_int(0), C.c_int(0)
+        lib.brtpe_umma_weight_dims(desc.Cin, desc.Cout_store, C.byref(cp), C.byref(op))
+        packed = torch.zeros((len(taps), op.value, cp.value), dtype=torch.bfloat16, device=w.device)
+        packed[:, :w.shape[0], :w.shape[1]] = wt.to(torch.bfloat16)
+        return packed
+    if bf16_round:
+        wt = wt.to(torch.bfloat16).float()
+    return wt.permute(0, 2, 1).contiguous()
+
+
+def run_conv(engine, mode, n, h, w, cin, cout, k, stride, relu, use_res, seed=0, device="cuda"):
+    """-> (out NCHW f32 from the library, reference NCHW f32, engine used)."""
+    lib = L.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    bf = mode == "bf16"
+    tdt = torch.bfloat16 if bf else torch.float32
+    x = torch.randn((n, cin, h, w), generator=g).to(device)
+    wgt = (torch.randn((cout, cin, k, k), generator=g) / (cin * k * k) ** 0.5).to(device)
+    bias = torch.randn((cout,), generator=g).to(device) * 0.1
+    ho, wo = h // stride, w // stride
+    res = torch.randn((n, cout, ho, wo), generator=g).to(device) if use_res else None
+    d, taps = make_desc(L.DT_BF16 if bf else L.DT_F32, engine, n, h, w, cin, cout, k, stride,
+                        relu, res_ld=(cout if use_res else 0))
+    eng = lib.brtpe_conv_select_engine(C.byref(d))
+    assert eng in (L.ENGINE_FFMA, L.ENGINE_UMMA), lib.brtpe_last_error()
+    xin = x.permute(0, 2, 3, 1).contiguous().to(tdt)
+    rin = res.permute(0, 2, 3, 1).contiguous().to(tdt) if use_res else None
+    packed = pack_weights(lib, wgt, taps, k, d, eng, bf)
+    out = torch.full((n, ho, wo, d.out_ld), float("nan"), dtype=tdt, device=device)
+    L.check(lib.brtpe_conv_run(C.byref(d), L.ptr(xin), L.ptr(packed), L.ptr(bias), L.ptr(rin),
+                               L.ptr(out), L.stream_ptr()), "brtpe_conv_run")
+    torch.cuda.synchronize()
+    xr = xin.float().permute(0, 3, 1, 2)
+    wr = wgt.to(torch.bfloat16).float() if bf else wgt
+    ref = F.conv2d(xr.double(), wr.double(), bias.double(), stride=stride, padding=k // 2)
+    if use_res:
+        ref = ref + rin.double().permute(0, 3, 1, 2)
+    if relu:
+        ref = F.relu(ref)
+    got = out[..., :cout].float().permute(0, 3, 1, 2)
+    return got, ref.float(), eng

@@ -1,0 +1,50 @@
+"""GPU parity of the convolution engine against a float64 torch convolution of the same
+(bf16-rounded) operands.  Metric: max|delta| / max|ref| per output tensor.
+fp32 (FFMA) <= 1e-5; bf16 storage of the output bounds the bf16 path at 2^-8 relative."""
+import pytest
+import torch
+
+from rtpe_b200 import _lib as L
+from _convutil import run_conv
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [
+    # n, h, w, cin, cout, k, stride, relu, res
+    (2, 32, 48, 48, 48, 3, 1, True, True),
+    (1, 40, 40, 96, 96, 3, 1, True, False),
+    (2, 20, 20, 192, 192, 3, 1, False, True),
+    (1, 20, 20, 384, 384, 3, 1, True, True),
+    (2, 32, 32, 64, 256, 1, 1, True, True),
+    (1, 32, 32, 256, 64, 1, 1, True, False),
+    (2, 32, 32, 48, 96, 3, 2, True, False),
+    (1, 64, 64, 64, 64, 3, 2, True, False),
+    (1, 16, 16, 256, 48, 3, 1, True, False),
+    (3, 24, 40, 48, 34, 1, 1, False, False),
+    (1, 16, 16, 384, 48, 1, 1, False, False),
+]
+
+
+def _err(got, ref):
+    return ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_ffma_fp32(cuda_device, shape):
+    got, ref, eng = run_conv(L.ENGINE_FFMA, "fp32", *shape)
+    assert eng == L.ENGINE_FFMA
+    assert _err(got, ref) <= 1e-5
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_ffma_bf16(cuda_device, shape):
+    got, ref, eng = run_conv(L.ENGINE_FFMA, "bf16", *shape)
+    assert _err(got, ref) <= 6e-3
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_umma_bf16(cuda_device, shape):
+    got, ref, eng = run_conv(L.ENGINE_UMMA, "bf16", *shape)
+    assert eng == L.ENGINE_UMMA
+    assert torch.isfinite(got).all()
+    assert _err(got, ref) <= 6e-3

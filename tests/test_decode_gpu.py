@@ -1,0 +1,179 @@
+"""GPU parity of the HeatmapParser drop-in against the CPU oracle (oracle/group_ref.py,
+itself pinned to the reference's group.py).  Everything here is BIT-EXACT: NMS values,
+top-k values / indices / tags, person count, person order, coordinates, scores."""
+import numpy as np
+import pytest
+import torch
+
+import rtpe_b200
+from oracle import group_ref as G
+
+pytestmark = pytest.mark.gpu
+
+PARSER_KW = dict(num_joints=17, max_num_people=30, detection_threshold=0.1, tag_threshold=1.0,
+                 use_detection_val=True, ignore_too_much=False)
+
+
+def make_parser(**over):
+    kw = dict(PARSER_KW)
+    extra = {k: over.pop(k) for k in list(over) if k in ("tag_per_joint", "nms_ksize", "nms_padding")}
+    kw.update(over)
+    return rtpe_b200.HeatmapParser(**kw, **extra), G.DecodeParams(**kw, **extra)
+
+
+def assert_people_equal(got, want):
+    assert len(got) == len(want)
+    for (gp, gs), (wp, ws) in zip(got, want):
+        wp = np.asarray(wp)
+        assert gp.shape == wp.shape, (gp.shape, wp.shape)
+        assert np.array_equal(gp, wp)
+        assert len(gs) == len(ws)
+        assert np.array_equal(np.asarray(gs, np.float32), np.asarray(ws, np.float32))
+
+
+@pytest.mark.parametrize("h,w,k", [(64, 64, 5), (96, 128, 5), (50, 70, 3), (33, 47, 5), (64, 200, 1)])
+def test_nms_exact(cuda_device, h, w, k):
+    det = torch.randn(2, 17, h, w, generator=torch.Generator().manual_seed(h * w))
+    det[0, 0, :8, :8] = 0.5                      # plateau: every equal maximum survives
+    det[1, 3] = -det[1, 3].abs()                 # negative peaks stay negative
+    hp, _ = make_parser(nms_ksize=k, nms_padding=(k - 1) // 2)
+    got = hp.nms(det.cuda()).cpu().numpy()
+    want = G.nms_ref(det.numpy(), k, (k - 1) // 2)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("h,w,t,tpj", [(64, 64, 1, True), (96, 128, 2, True), (61, 83, 1, True),
+                                       (128, 96, 1, False), (320, 320, 1, True)])
+def test_topk_exact(cuda_device, h, w, t, tpj):
+    det, tag = rtpe_b200.synth_decode_batch(3, height=h, width=w, tag_dims=t, tag_per_joint=tpj,
+                                            seed=11)
+    hp, p = make_parser(tag_per_joint=tpj)
+    got = hp.top_k(det.cuda(), tag.cuda())
+    want = G.top_k_ref(det.numpy(), tag.numpy(), p)
+    for key in ("val_k", "loc_k", "tag_k"):
+        assert got[key].dtype == want[key].dtype, key
+        assert np.array_equal(got[key], want[key]), key
+
+
+def test_topk_sparse_and_negative_maps(cuda_device):
+    """fewer than K positive peaks: zero-valued positions in index order, then negative
+    peaks -- the canonical order of topk over the NMS'd map."""
+    n, j, h, w = 2, 17, 40, 56
+    det = torch.zeros(n, j, h, w)
+    det[0, 0, 5, 7] = 0.9
+    det[0, 0, 20, 30] = 0.4
+    det[0, 1] = -1.0                              # all-negative plateau: every pixel a peak
+    det[0, 2] = -torch.rand(h, w, generator=torch.Generator().manual_seed(3)) - 0.1
+    det[1, 4, 0, 0] = 0.3
+    tag = torch.randn(n, j, h, w, 1, generator=torch.Generator().manual_seed(4))
+    hp, p = make_parser()
+    got = hp.top_k(det.cuda(), tag.cuda())
+    want = G.top_k_ref(det.numpy(), tag.numpy(), p)
+    for key in ("val_k", "loc_k", "tag_k"):
+        assert np.array_equal(got[key], want[key]), key
+
+
+@pytest.mark.parametrize("seed,h,w,t,people", [(0, 96, 128, 1, 8), (1, 128, 128, 2, 20),
+                                               (2, 320, 320, 1, 30), (3, 75, 101, 1, 12)])
+def test_parse_batch_exact(cuda_device, seed, h, w, t, people):
+    det, tag = rtpe_b200.synth_decode_batch(4, height=h, width=w, tag_dims=t, max_people=people,
+                                            seed=100 + seed)
+    hp, p = make_parser()
+    got = hp.parse_batch(det.cuda(), tag.cuda(), True, True)
+    want = G.parse_batch_ref(det.numpy().copy(), tag.numpy().copy(), p, True, True)
+    assert_people_equal(got, want)
+
+
+@pytest.mark.parametrize("adjust,refine", [(False, False), (True, False), (False, True)])
+def test_parse_flags(cuda_device, adjust, refine):
+    det, tag = rtpe_b200.synth_decode_batch(2, height=80, width=96, max_people=6, seed=77)
+    hp, p = make_parser()
+    got = hp.parse_batch(det.cuda(), tag.cuda(), adjust, refine)
+    want = G.parse_batch_ref(det.numpy().copy(), tag.numpy().copy(), p, adjust, refine)
+    assert_people_equal(got, want)
+
+
+def test_parse_reference_structure(cuda_device):
+    """N=1 parse returns the reference's structure: ([ (P,J,3+T) f32 ], [np.float32...])."""
+    det, tag = rtpe_b200.synth_decode_batch(1, height=64, width=64, max_people=5, seed=5)
+    hp, p = make_parser()
+    ans, scores = hp.parse(det.cuda(), tag.cuda(), True, True)
+    wp, ws = G.parse_image_ref(det.numpy().copy(), tag.numpy().copy(), p, True, True)
+    assert isinstance(ans, list) and len(ans) == 1
+    assert ans[0].dtype == np.float32 and np.array_equal(ans[0], wp)
+    assert all(isinstance(s, np.float32) for s in scores)
+    assert np.array_equal(np.asarray(scores), np.asarray(ws))
+
+
+def test_adversarial_ties_and_collisions(cuda_device):
+    """tags quantised to bf16 (duplicate dict keys), persons closer than the tag threshold
+    (assignment ties), more than 30 peaks per joint."""
+    det, tag = rtpe_b200.synth_decode_batch(6, height=96, width=96, max_people=30, seed=900)
+    tag = tag.to(torch.bfloat16).to(torch.float32)
+    tag = (tag * 0.25)                           # people 0.375 apart: many candidates per person
+    hp, p = make_parser()
+    got = hp.parse_batch(det.cuda(), tag.cuda(), True, True)
+    want = G.parse_batch_ref(det.numpy().copy(), tag.numpy().copy(), p, True, True)
+    assert_people_equal(got, want)
+
+
+def test_more_than_30_people(cuda_device):
+    """the person list is not capped at max_num_people."""
+    h = w = 160
+    det = torch.rand(1, 17, h, w, generator=torch.Generator().manual_seed(1)) * 0.01
+    tag = torch.zeros(1, 17, h, w, 1)
+    pid = 0
+    for y in range(10, 150, 20):
+        for x in range(10, 150, 20):
+            if pid >= 40:
+                break
+            for j in range(17):
+                yy, xx = y + (j % 4), x + (j // 4)
+                det[0, j, yy, xx] = 0.5 + 0.01 * pid + 0.001 * j
+                tag[0, j, yy - 2:yy + 3, xx - 2:xx + 3, 0] = 3.0 * pid
+            pid += 1
+    hp, p = make_parser()
+    got = hp.parse_batch(det.cuda(), tag.cuda(), True, True)
+    want = G.parse_batch_ref(det.numpy().copy(), tag.numpy().copy(), p, True, True)
+    assert want[0][0].shape[0] > 30
+    assert_people_equal(got, want)
+
+
+def test_empty_detections(cuda_device):
+    det = torch.rand(2, 17, 48, 48, generator=torch.Generator().manual_seed(2)) * 0.05
+    tag = torch.zeros(2, 17, 48, 48, 1)
+    hp, p = make_parser()
+    got = hp.parse_batch(det.cuda(), tag.cuda(), True, True)
+    for people, scores in got:
+        assert people.size == 0 and scores == []
+    ans, scores = hp.parse(det.cuda(), tag.cuda(), True, True)
+    assert len(ans) == 1 and ans[0].size == 0 and scores == []
+
+
+def test_match_adjust_refine_methods(cuda_device):
+    """the individual public methods keep the reference's signatures and results."""
+    det, tag = rtpe_b200.synth_decode_batch(2, height=72, width=88, max_people=7, seed=31)
+    hp, p = make_parser()
+    tk = G.top_k_ref(det.numpy(), tag.numpy(), p)
+    got = hp.match(tk["tag_k"], tk["loc_k"], tk["val_k"])
+    want = G.match_ref(tk["tag_k"], tk["loc_k"], tk["val_k"], p)
+    for g, w_ in zip(got, want):
+        assert np.array_equal(g, w_)
+    got = hp.adjust(got, det)
+    want = G.adjust_ref(want, det.numpy())
+    for g, w_ in zip(got, want):
+        assert np.array_equal(g, w_)
+    for i in range(min(3, len(want[0]))):
+        a = hp.refine(det[0].numpy(), tag[0].numpy(), got[0][i].copy())
+        b = G.refine_ref(det[0].numpy(), tag[0].numpy(), want[0][i].copy())
+        assert np.array_equal(a, b)
+
+
+def test_errors_are_loud(cuda_device):
+    hp, _ = make_parser(max_num_people=100)
+    det, tag = rtpe_b200.synth_decode_batch(1, height=32, width=32)
+    with pytest.raises(rtpe_b200.BrtpeError):
+        hp.top_k(det.cuda(), tag.cuda())
+    hp2 = rtpe_b200.HeatmapParser(nms_ksize=5, nms_padding=1, **PARSER_KW)
+    with pytest.raises(rtpe_b200.BrtpeError):
+        hp2.nms(det.cuda())

@@ -1,0 +1,86 @@
+"""GPU parity of PoseHigherResolutionNet.forward against the CPU oracle
+(oracle/hhrnet_ref.py, pinned to the reference module).  Metric per output tensor:
+max|delta| / max|ref|.  fp32 mode <= 1e-4, bf16 mode <= 2e-2 (BASELINE.json north_star)."""
+import pytest
+import torch
+
+import rtpe_b200
+from rtpe_b200 import _lib as L
+from oracle.hhrnet_ref import hhrnet_forward_ref
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 1e-4
+TOL_BF16 = 2e-2
+
+
+def _rel(got, ref):
+    return ((got.double().cpu() - ref.double()).abs().max() / ref.double().abs().max()).item()
+
+
+@pytest.fixture(scope="module")
+def model_and_ref():
+    torch.manual_seed(0)
+    net = rtpe_b200.PoseHigherResolutionNet().eval()
+    # non-trivial BN statistics so that the folding is actually exercised
+    g = torch.Generator().manual_seed(1)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+    x = torch.randn(3, 3, 128, 192, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        ref = hhrnet_forward_ref(net.state_dict(), x)
+    return net, x, ref
+
+
+def test_forward_fp32(cuda_device, model_and_ref):
+    net, x, ref = model_and_ref
+    net = net.float().cuda()
+    net.chunk_size = 2                    # 3 images -> chunks of 2 + 1
+    with torch.no_grad():
+        out = net(x.cuda())
+    assert [tuple(o.shape) for o in out] == [tuple(r.shape) for r in ref]
+    for o, r in zip(out, ref):
+        assert o.dtype == torch.float32
+        assert _rel(o, r) <= TOL_FP32
+
+
+@pytest.mark.parametrize("engine", [L.ENGINE_FFMA, L.ENGINE_AUTO])
+def test_forward_bf16(cuda_device, model_and_ref, engine):
+    net, x, ref = model_and_ref
+    import copy
+    half = rtpe_b200.network_to_half(copy.deepcopy(net).float()).cuda().eval()
+    half[1].conv_engine = engine
+    with torch.no_grad():
+        out = half(x.cuda())
+    for o, r in zip(out, ref):
+        assert o.dtype == torch.float32
+        assert torch.isfinite(o).all()
+        assert _rel(o, r) <= TOL_BF16
+
+
+def test_graph_and_eager_agree(cuda_device, model_and_ref):
+    net, x, ref = model_and_ref
+    net = net.float().cuda()
+    with torch.no_grad():
+        net.use_cuda_graph = True
+        a = net(x.cuda())
+        a2 = net(x.cuda())
+        net.use_cuda_graph = False
+        net.invalidate_plans()
+        b = net(x.cuda())
+    for u, v, w_ in zip(a, a2, b):
+        assert torch.equal(u, v) and torch.equal(u, w_)
+
+
+def test_requires_cuda_and_eval(cuda_device):
+    net = rtpe_b200.PoseHigherResolutionNet()
+    with pytest.raises(rtpe_b200.BrtpeError):
+        net.eval()(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(rtpe_b200.BrtpeError):
+        net.train().cuda()(torch.zeros(1, 3, 64, 64).cuda())
+    with pytest.raises(ValueError):
+        net.eval().cuda()(torch.zeros(1, 3, 70, 64).cuda())
