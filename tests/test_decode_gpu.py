@@ -129,7 +129,7 @@ def test_more_than_30_people(cuda_device):
                 break
             for j in range(17):
                 yy, xx = y + (j % 4), x + (j // 4)
-                det[0, j, yy, xx] = 0.5 + 0.01 * pid + 0.001 * j
+                det[0, j, yy, xx] = 0.5 + 0.01 * ((pid + 7 * j) % 40) + 0.0001 * j
                 tag[0, j, yy - 2:yy + 3, xx - 2:xx + 3, 0] = 3.0 * pid
             pid += 1
     hp, p = make_parser()

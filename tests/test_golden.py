@@ -1,0 +1,64 @@
+"""CPU: the oracle restatements reproduce the fixtures that the UNMODIFIED reference
+produced (oracle/make_golden.py).  Decode is bit-exact; the model is float32 torch CPU on
+both sides, compared to 1e-5 of the tensor max (conv algorithm choice may differ by size)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import group_ref as G
+from oracle.hhrnet_ref import hhrnet_forward_ref
+from oracle.weights import fill_params_deterministic
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_decode_fixture(path):
+    z = np.load(path)
+    det = z["det"].astype(np.float32)
+    tag = z["tag"]
+    tpj = tag.shape[1] == det.shape[1]
+    return z, det, tag, tpj
+
+
+def split_people(z):
+    out, off = [], 0
+    for c in z["counts"]:
+        out.append((z["people"][off:off + c], z["scores"][off:off + c]))
+        off += c
+    return out
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "decode_*.npz"))))
+def test_decode_oracle_matches_reference_fixture(path):
+    z, det, tag, tpj = load_decode_fixture(path)
+    p = G.DecodeParams(tag_per_joint=tpj)
+    tk = G.top_k_ref(det, tag, p)
+    # values are order-independent among ties; the fixtures have none above the threshold
+    assert np.array_equal(tk["val_k"], z["val_k"])
+    live = z["val_k"] > 0
+    assert np.array_equal(tk["loc_k"][live], z["loc_k"].astype(np.int64)[live])
+    assert np.array_equal(tk["tag_k"][live], z["tag_k"][live])
+    got = G.parse_batch_ref(det.copy(), tag.copy(), p, True, True)
+    want = split_people(z)
+    assert len(got) == len(want)
+    for (gp, gs), (wp, ws) in zip(got, want):
+        gp = np.asarray(gp, np.float32).reshape((-1,) + wp.shape[1:])
+        assert np.array_equal(gp, wp)
+        assert np.array_equal(np.asarray(gs, np.float32), ws)
+
+
+def test_hhrnet_oracle_matches_reference_fixture():
+    import rtpe_b200
+    z = np.load(os.path.join(GOLD, "hhrnet_64x96.npz"))
+    net = rtpe_b200.PoseHigherResolutionNet()
+    assert sum(p.numel() for p in net.parameters()) == int(z["params"]) == 63827139
+    fill_params_deterministic(net, int(z["seed"]))
+    with torch.no_grad():
+        y0, y1 = hhrnet_forward_ref(net.state_dict(), torch.from_numpy(z["x"]))
+    for got, want in ((y0, z["y0"]), (y1, z["y1"])):
+        want = torch.from_numpy(want)
+        assert got.shape == want.shape
+        assert ((got - want).abs().max() / want.abs().max()).item() <= 1e-5

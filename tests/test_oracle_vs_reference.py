@@ -1,0 +1,69 @@
+"""CPU, this container only: the oracle restatements against the UNMODIFIED reference
+imported from /root/reference (skipped where the tree is absent, e.g. on the GPU box)."""
+import numpy as np
+import pytest
+import torch
+
+import rtpe_b200
+from oracle import group_ref as G
+from oracle.ref_loader import load_reference, reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="/root/reference not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return load_reference()
+
+
+@pytest.mark.parametrize("seed,h,w,t,people,tpj", [(1, 64, 80, 1, 8, True), (2, 72, 64, 2, 12, True),
+                                                   (3, 48, 48, 1, 30, True), (4, 56, 40, 1, 5, False)])
+def test_decode_oracle_vs_reference(ref, seed, h, w, t, people, tpj):
+    ref_group, _ = ref
+    det, tag = rtpe_b200.synth_decode_batch(2, height=h, width=w, tag_dims=t, max_people=people,
+                                            seed=seed, tag_per_joint=tpj)
+    hp = ref_group.HeatmapParser(17, 30, 0.1, 1.0, True, False, tpj, 5, 2)
+    p = G.DecodeParams(tag_per_joint=tpj)
+    for i in range(2):
+        ans, scores = hp.parse(det[i:i + 1].clone(), tag[i:i + 1].clone(), True, True)
+        gp, gs = G.parse_image_ref(det[i:i + 1].numpy().copy(), tag[i:i + 1].numpy().copy(), p)
+        assert np.array_equal(np.asarray(ans[0]), gp)
+        assert np.array_equal(np.asarray(scores, np.float32), np.asarray(gs, np.float32))
+
+
+def test_decode_oracle_vs_reference_collisions(ref):
+    ref_group, _ = ref
+    det, tag = rtpe_b200.synth_decode_batch(2, height=64, width=64, max_people=30, seed=55)
+    tag = tag.to(torch.bfloat16).float() * 0.25
+    hp = ref_group.HeatmapParser(17, 30, 0.1, 1.0, True, False, True, 5, 2)
+    p = G.DecodeParams()
+    for i in range(2):
+        ans, scores = hp.parse(det[i:i + 1].clone(), tag[i:i + 1].clone(), True, True)
+        gp, gs = G.parse_image_ref(det[i:i + 1].numpy().copy(), tag[i:i + 1].numpy().copy(), p)
+        assert np.array_equal(np.asarray(ans[0]), gp)
+
+
+def test_model_oracle_vs_reference(ref):
+    from oracle.hhrnet_ref import hhrnet_forward_ref
+    _, ref_model = ref
+    torch.manual_seed(0)
+    net = ref_model.PoseHigherResolutionNet().eval()
+    x = torch.randn(1, 3, 64, 64)
+    with torch.no_grad():
+        want = net(x)
+        got = hhrnet_forward_ref(net.state_dict(), x)
+    for a, b in zip(got, want):
+        assert ((a - b).abs().max() / b.abs().max()).item() <= 1e-5
+
+
+def test_dropin_state_dict_matches_reference(ref):
+    _, ref_model = ref
+    a = ref_model.PoseHigherResolutionNet().state_dict()
+    b = rtpe_b200.PoseHigherResolutionNet().state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+    from rtpe.third_party.fp16_utils.fp16util import network_to_half as ref_n2h
+    ra = ref_n2h(ref_model.PoseHigherResolutionNet()).state_dict()
+    rb = rtpe_b200.get_hrnet_w48_teacher(None).state_dict()
+    assert list(ra.keys()) == list(rb.keys())
+    assert all(ra[k].dtype == rb[k].dtype for k in ra)
