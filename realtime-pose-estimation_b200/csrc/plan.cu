@@ -66,7 +66,9 @@ struct brtpe_plan {
   std::vector<Op> ops;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
+  cudaStream_t capture_stream = nullptr;
   ~brtpe_plan() {
+    if (capture_stream) cudaStreamDestroy(capture_stream);
     for (auto& op : ops)
       if (op.umma) umma_conv_release(op.umma);
     if (exec) cudaGraphExecDestroy(exec);
@@ -209,14 +211,19 @@ extern "C" int brtpe_plan_graph_launch(brtpe_plan* pl, void* stream) {
   BRTPE_CHECK_ARG(pl, "brtpe_plan_graph_launch: null plan");
   cudaStream_t st = (cudaStream_t)stream;
   if (!pl->exec) {
-    BRTPE_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    // capture on a private stream: the caller's stream may be the legacy default stream,
+    // which cannot be captured; the instantiated graph is then launched into `st`.
+    if (!pl->capture_stream)
+      BRTPE_CUDA(cudaStreamCreateWithFlags(&pl->capture_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = pl->capture_stream;
+    BRTPE_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
     int rc = BRTPE_OK;
     for (auto& op : pl->ops) {
-      rc = run_op(op, st);
+      rc = run_op(op, cs);
       if (rc) break;
     }
     cudaGraph_t g = nullptr;
-    cudaError_t e = cudaStreamEndCapture(st, &g);
+    cudaError_t e = cudaStreamEndCapture(cs, &g);
     if (rc) {
       if (g) cudaGraphDestroy(g);
       return rc;

@@ -546,6 +546,13 @@ class PoseHigherResolutionNet(nn.Module):
                 out.append(nn.Sequential(*chain))
         return nn.ModuleList(out)
 
+    # compiled plans own native handles and device arenas: never copied / pickled
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_plans"] = {}
+        state["_sig"] = None
+        return state
+
     # ---------------------------------------------------------------- weights bookkeeping
     def invalidate_plans(self):
         """Drop the compiled plans (packed weights are rebuilt at the next forward)."""

@@ -1,0 +1,198 @@
+"""Teacher inference = forward + aggregation + decode, batched and device resident.
+
+Mirrors what the reference's drivers do one image at a time:
+
+* ``aggregate_intree``  -- validate_hhrnet.py:92-101 (bilinear, align_corners=True, to the
+  original image size; heat-maps from the 1/2-resolution head, tags from the 1/4 head);
+* ``aggregate_flip_multiscale`` -- the flip-test / multi-scale protocol of
+  legacy/valid_ae_avg.py:159-205 (upstream get_multi_stage_outputs + aggregate_results,
+  configuration legacy/distillation.py:85-92);
+* ``TeacherPipeline`` -- model -> aggregation -> ``HeatmapParser`` for a whole batch with one
+  host<->device round trip; ``shard``/``gather`` give the one-process-per-GPU data-parallel
+  form (images are independent; the only collective is the final gather of the padded
+  keypoint tensors over NCCL).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+# COCO left/right swap for the joint order of teacher_inference.py:38-40
+FLIP_INDEX = [0, 2, 1, 4, 3, 6, 5, 8, 7, 10, 9, 12, 11, 14, 13, 16, 15]
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+def bilinear_resize(src, out_hw, align_corners, dst=None, dst_inner=1, dst_off=0):
+    """F.interpolate(src, out_hw, mode='bilinear', align_corners=...) on a CUDA NCHW tensor."""
+    lib = L.load()
+    src = _f32c(src)
+    n, c, hi, wi = src.shape
+    ho, wo = int(out_hw[0]), int(out_hw[1])
+    if dst is None:
+        dst = torch.empty((n, c, ho, wo), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        L.check(lib.brtpe_bilinear_resize(L.ptr(src), hi * wi, n * c, hi, wi, L.ptr(dst), ho, wo,
+                                          dst_inner, dst_off, int(bool(align_corners)),
+                                          L.stream_ptr(src.device)), "brtpe_bilinear_resize")
+    return dst
+
+
+def aggregate_intree(y0, y1, out_hw, num_joints=17):
+    """validate_hhrnet.py:94-101 -> det (N,J,h,w), tag (N,A,h,w,1)."""
+    det = bilinear_resize(y1, out_hw, True)
+    tags = _f32c(y0)[:, num_joints:].contiguous()
+    tag = bilinear_resize(tags, out_hw, True)
+    return det, tag.unsqueeze(-1)
+
+
+def aggregate_scale(y0, y1, y0f, y1f, base_hw, num_joints=17, det=None, tag=None,
+                    accumulate=False, final_div=0.0, want_tags=True, flip_index=FLIP_INDEX):
+    """One scale of the flip / multi-scale aggregation (see brtpe_aggregate_scale)."""
+    lib = L.load()
+    y0, y1 = _f32c(y0), _f32c(y1)
+    flip = y0f is not None
+    if flip:
+        y0f, y1f = _f32c(y0f), _f32c(y1f)
+    n, c0, h4, w4 = y0.shape
+    j = num_joints
+    a = c0 - j
+    h2, w2 = y1.shape[2], y1.shape[3]
+    hb, wb = int(base_hw[0]), int(base_hw[1])
+    dev = y0.device
+    if det is None:
+        det = torch.empty((n, j, hb, wb), dtype=torch.float32, device=dev)
+    t = 2 if flip else 1
+    if want_tags and tag is None:
+        tag = torch.empty((n, a, hb, wb, t), dtype=torch.float32, device=dev)
+    fi = (C.c_int32 * j)(*[int(v) for v in flip_index[:j]])
+    with torch.cuda.device(dev):
+        L.check(lib.brtpe_aggregate_scale(
+            L.ptr(y0), L.ptr(y1), L.ptr(y0f) if flip else None, L.ptr(y1f) if flip else None,
+            n, j, a, h4, w4, h2, w2, hb, wb, fi, int(bool(accumulate)), float(final_div),
+            L.ptr(det), L.ptr(tag) if want_tags else None, L.stream_ptr(dev)),
+            "brtpe_aggregate_scale")
+    return det, (tag if want_tags else None)
+
+
+def aggregate_flip_multiscale(per_scale_outputs, base_size, num_joints=17):
+    """``per_scale_outputs``: [(scale, [y0, y1], [y0f, y1f] or None), ...] in visiting order
+    (descending scales, legacy/valid_ae_avg.py:166); ``base_size`` = (W, H).
+    -> det (N,J,H,W), tag (N,A,H,W,T).  Tags come from the scale-1.0 pass only."""
+    hb, wb = int(base_size[1]), int(base_size[0])
+    ns = len(per_scale_outputs)
+    det, tag = None, None
+    for k, (scale, outs, outs_f) in enumerate(per_scale_outputs):
+        want_tags = (scale == 1) or ns == 1
+        last = k == ns - 1
+        det, tg = aggregate_scale(outs[0], outs[1], outs_f[0] if outs_f else None,
+                                  outs_f[1] if outs_f else None, (hb, wb), num_joints, det=det,
+                                  accumulate=k > 0, final_div=float(ns) if last else 0.0,
+                                  want_tags=want_tags)
+        if want_tags:
+            tag = tg
+    return det, tag
+
+
+class TeacherPipeline:
+    """forward (+ flip test) -> aggregation -> decode for a batch of equally sized images.
+
+    ``model``: this package's network (optionally wrapped by ``network_to_half``);
+    ``parser``: this package's ``HeatmapParser``."""
+
+    def __init__(self, model, parser, flip_test=True, project_hw=None, mode="upstream"):
+        if mode not in ("upstream", "intree"):
+            raise ValueError("mode must be 'upstream' (flip/project) or 'intree' (validate_hhrnet.py)")
+        self.model = model
+        self.parser = parser
+        self.flip_test = bool(flip_test)
+        self.project_hw = project_hw
+        self.mode = mode
+        self.num_joints = parser.params.num_joints
+
+    @torch.no_grad()
+    def forward_aggregate(self, x):
+        """x (N,3,H,W) CUDA -> det (N,J,Hb,Wb), tag (N,A,Hb,Wb,T)."""
+        n, _, h, w = x.shape
+        hb, wb = self.project_hw if self.project_hw is not None else (h, w)
+        if self.mode == "intree":
+            y0, y1 = self.model(x)
+            return aggregate_intree(y0, y1, (hb, wb), self.num_joints)
+        if self.flip_test:
+            both = torch.cat((x, torch.flip(x, [3])), 0)
+            y0, y1 = self.model(both)
+            det, tag = aggregate_scale(y0[:n], y1[:n], y0[n:], y1[n:], (hb, wb), self.num_joints)
+        else:
+            y0, y1 = self.model(x)
+            det, tag = aggregate_scale(y0, y1, None, None, (hb, wb), self.num_joints)
+        return det, tag
+
+    @torch.no_grad()
+    def run_device(self, x, adjust=True, refine=True):
+        """-> ans (N,Pmax,J,3+T), count (N), scores (N,Pmax): CUDA tensors, no host sync
+        besides the parser's capacity check."""
+        det, tag = self.forward_aggregate(x)
+        return self.parser.decode_device(det, tag, adjust, refine)
+
+    @torch.no_grad()
+    def run(self, x, adjust=True, refine=True):
+        """Host-facing call: ``x`` may live in (pinned) host memory.  -> list over images of
+        (people (P,J,3+T) float32, scores [np.float32])."""
+        L.load()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        xd = x.to(dev, non_blocking=True)
+        ans, count, scores = self.run_device(xd, adjust, refine)
+        return unpack_results(ans.cpu(), count.cpu(), scores.cpu())
+
+
+def unpack_results(ans, count, scores):
+    ans, count, scores = ans.numpy(), count.numpy(), scores.numpy()
+    out = []
+    for i in range(ans.shape[0]):
+        c = int(count[i])
+        people = np.array(ans[i, :c]) if c else np.array([], dtype=np.float32)
+        out.append((people, [np.float32(s) for s in scores[i, :c]]))
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# data-parallel sharding: one process per GPU, images are independent
+# ---------------------------------------------------------------------------------------
+def shard_range(total, rank, world):
+    """Contiguous split of ``total`` images over ``world`` ranks -> (start, stop)."""
+    base, rem = divmod(int(total), int(world))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def pad_results(ans, count, scores, pcap):
+    """Fixed-shape payload for the gather: people beyond ``pcap`` are flagged, not dropped
+    silently (``overflow`` = count > pcap)."""
+    n, pmax = ans.shape[0], ans.shape[1]
+    if pmax >= pcap:
+        a, s = ans[:, :pcap], scores[:, :pcap]
+    else:
+        a = torch.zeros((n, pcap) + tuple(ans.shape[2:]), dtype=ans.dtype, device=ans.device)
+        a[:, :pmax] = ans
+        s = torch.zeros((n, pcap), dtype=scores.dtype, device=scores.device)
+        s[:, :pmax] = scores
+    return a.contiguous(), count.contiguous(), s.contiguous()
+
+
+def gather_results(ans, count, scores, group=None):
+    """all_gather of equally shaped per-rank results (NCCL on GPUs, gloo in the CPU tests).
+    -> concatenated (ans, count, scores) in rank order on every rank."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    outs = []
+    for t in (ans, count, scores):
+        bufs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(bufs, t.contiguous(), group=group)
+        outs.append(torch.cat(bufs, 0))
+    return tuple(outs)
