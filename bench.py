@@ -1,0 +1,385 @@
+"""Benchmark of the teacher-inference hot path (BASELINE.json): HigherHRNet-W48 640x640
+forward with flip test + heat-map aggregation + HeatmapParser decode.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference            # the CPU implementation of the same path
+
+A step = one batch of 32 synthetic 640x640 images per GPU (configs[1] of BASELINE.json):
+64 forwards (flip test), aggregation to 640x640 (T = 2 tag copies), parse(adjust, refine).
+Prints ONE JSON line (rank 0).  `value` is timed with the inputs already in HBM; `e2e` goes
+through the host-facing call with pinned host input and host results (H2D + D2H inside the
+timed region).  Device timing = CUDA events on the launching stream, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "images/sec W48 640^2 fwd+decode"
+PARSER_KW = dict(num_joints=17, max_num_people=30, detection_threshold=0.1, tag_threshold=1.0,
+                 use_detection_val=True, ignore_too_much=False, tag_per_joint=True, nms_ksize=5,
+                 nms_padding=2)
+FLOP_PER_FORWARD_640 = 298.94e9          # 149.469 GMAC per 640x640 forward
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "tflops": float(p.get("bf16_tflops_sustained",
+                                                                      p["bf16_tflops"])),
+                "source": "MEASURED_PEAKS.json (sustained bf16, copy HBM)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "source": "B200_PROFILING.md fallback"}
+
+
+def make_input(batch, size, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn((batch, 3, size, size), generator=g)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.tmp,
+                stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        try:
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(smax))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# CPU implementation of the path (the oracle port; the reference is pure Python/torch-CPU and
+# /root/reference does not exist on the GPU box)
+# ------------------------------------------------------------------------------------------
+class CpuPath:
+    def __init__(self, size):
+        import rtpe_b200
+        from oracle import group_ref as G
+        from oracle.aggregate_ref import aggregate_flip_multiscale_ref
+        from oracle.hhrnet_ref import hhrnet_forward_ref
+        self.G, self.agg, self.fwd = G, aggregate_flip_multiscale_ref, hhrnet_forward_ref
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        torch.manual_seed(0)
+        self.sd = rtpe_b200.PoseHigherResolutionNet().state_dict()   # default init, seed 0
+        self.params = G.DecodeParams(**PARSER_KW)
+        self.size = size
+
+    @torch.no_grad()
+    def one_image(self, x1):
+        """the reference's per-image loop body: 2 forwards (flip test), aggregation, parse."""
+        y = self.fwd(self.sd, x1)
+        yf = self.fwd(self.sd, torch.flip(x1, [3]))
+        det, tag = self.agg([(1.0, y, yf)], (self.size, self.size))
+        return self.G.parse_image_ref(det.numpy(), tag.numpy(), self.params, True, True)
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    cpu = CpuPath(args.size)
+    x = make_input(max(1, min(args.batch, args.warmup + args.steps)), args.size)
+    for i in range(args.warmup):
+        cpu.one_image(x[i % x.shape[0]:i % x.shape[0] + 1])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        k = (args.warmup + i) % x.shape[0]
+        cpu.one_image(x[k:k + 1])
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    sample = ("each step = 1 image of the %dx%d batch: 2 fp32 CPU forwards (flip test) + "
+              "aggregation + parse(adjust, refine)" % (args.size, args.size))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cpu.cores, "kind": "port",
+                         "torch_threads": torch.get_num_threads(), "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": "HigherHRNet-W48 teacher inference, batch %d synthetic %dx%d per GPU, "
+                        "flip test (2 forwards/image), aggregation to %dx%d (T=2), "
+                        "HeatmapParser.parse(adjust, refine), random-init weights (seed 0)"
+                        % (args.batch, args.size, args.size, args.size, args.size),
+            "batch_per_gpu": args.batch, "image_size": args.size, "flip_test": True,
+            "precision": args.mode, "chunk": args.chunk,
+            "l2": "per-step input (%.0f MB) and activations exceed the 126 MB L2; no flush needed"
+                  % (args.batch * 3 * args.size * args.size * 4 / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    import rtpe_b200
+    from rtpe_b200 import inference
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)
+    if args.mode == "bf16":
+        model = rtpe_b200.get_hrnet_w48_teacher(None).to(dev)
+        net = model[1]
+    else:
+        model = rtpe_b200.get_hrnet_w48_teacher(None, half=False).to(dev)
+        net = model
+    net.chunk_size = args.chunk
+    net.freeze()
+    parser = rtpe_b200.HeatmapParser(**PARSER_KW)
+    pipe = inference.TeacherPipeline(model, parser, flip_test=True)
+
+    # every rank gets its own shard of the (weak-scaled) global batch
+    x_host = make_input(args.batch, args.size, seed=1 + rank).pin_memory()
+    x_dev = x_host.to(dev)
+    pcap = parser.person_capacity
+
+    def step_device():
+        ans, count, scores = pipe.run_device(x_dev, True, True)
+        ans, count, scores = inference.pad_results(ans, count, scores, pcap)
+        if world > 1:
+            ans, count, scores = inference.gather_results(ans, count, scores)
+        return ans, count, scores
+
+    host_out = {}
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        ans, count, scores = pipe.run_device(xd, True, True)
+        ans, count, scores = inference.pad_results(ans, count, scores, pcap)
+        if world > 1:
+            ans, count, scores = inference.gather_results(ans, count, scores)
+        for k, t in (("ans", ans), ("count", count), ("scores", scores)):
+            if k not in host_out:
+                host_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            host_out[k].copy_(t, non_blocking=True)
+        return ans, count, scores
+
+    def timed(fn, steps, warmup, sample_clocks):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), clocks
+
+    ms_dev, clocks = timed(step_device, args.steps, args.warmup, True)
+    ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2), False)
+    ans, count, scores = step_device()
+    torch.cuda.synchronize()
+    people_mean = float(count.float().mean().item())
+
+    total_images = args.batch * world * args.steps
+    value = total_images / (ms_dev * 1e-3)
+    e2e_value = total_images / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), measured live with
+    # CUDA events around every launch of one plan replay, on the launching stream
+    peaks = load_peaks()
+    in_dtype = torch.float16 if args.mode == "bf16" else torch.float32
+    chunk = min(args.chunk, 2 * args.batch)
+    net.plan_profile(chunk, args.size, args.size, in_dtype)
+    ms_ops, kinds, flops = net.plan_profile(chunk, args.size, args.size, in_dtype)
+    conv_ms = sum(m for m, k in zip(ms_ops, kinds) if k in (0, 1))
+    conv_flops = sum(flops)
+    umma_ms = sum(m for m, k in zip(ms_ops, kinds) if k == 0)
+    umma_flops = sum(f for f, k in zip(flops, kinds) if k == 0)
+    umma_launches = sum(1 for k in kinds if k == 0)
+    achieved = (umma_flops if umma_ms > 0 else conv_flops) / max(umma_ms or conv_ms, 1e-9) / 1e9
+    roofline = {"bound": "tensor", "kernel": "conv_umma_kernel (tcgen05 implicit GEMM)",
+                "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["tflops"], "traffic": None,
+                "launches": umma_launches, "avg_launch_ms": umma_ms / max(umma_launches, 1),
+                "flop_per_launch_avg": umma_flops / max(umma_launches, 1),
+                "conv_share_of_forward": conv_ms / max(sum(ms_ops), 1e-9),
+                "peak_source": peaks["source"]}
+
+    # ---- decode kernels against the HBM roofline (secondary)
+    det, tag = pipe.forward_aggregate(x_dev[:min(8, args.batch)])
+    nd, j, h, w = det.shape
+    t = tag.shape[4]
+    for _ in range(2):
+        parser.decode_device(det, tag)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    ev[0].record()
+    val_k, ind_k, _, tag_k = parser.top_k_device(det, tag)
+    ev[1].record()
+    a2, c2, _ = parser.match_device(val_k, ind_k, tag_k, w)
+    ev[2].record()
+    parser.adjust_device(a2, c2, det)
+    ev[3].record()
+    parser.refine_device(det, tag, a2, c2)
+    ev[4].record()
+    torch.cuda.synchronize()
+    b_topk = nd * j * h * w * 4
+    b_refine = nd * j * h * w * 4 * (1 + t)
+    roofline_decode = {
+        "bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"],
+        "top_k": {"achieved": b_topk / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9,
+                  "ms": ev[0].elapsed_time(ev[1])},
+        "refine": {"achieved": b_refine / (ev[3].elapsed_time(ev[4]) * 1e-3) / 1e9,
+                   "ms": ev[3].elapsed_time(ev[4])},
+        "match_ms": ev[1].elapsed_time(ev[2]), "images": nd,
+        "bytes_per_image": 4 * j * h * w * (2 + t)}
+    roofline_decode["top_k"]["frac"] = roofline_decode["top_k"]["achieved"] / peaks["hbm_gbs"]
+    roofline_decode["refine"]["frac"] = roofline_decode["refine"]["achieved"] / peaks["hbm_gbs"]
+
+    plan_ops = len(ms_ops)
+    n_chunks = -(-2 * args.batch // args.chunk)
+    gpu_launches = (n_chunks * plan_ops + 1 + 9) * args.steps
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = CpuPath(args.size)
+        xs = make_input(1, args.size)
+        t0 = time.perf_counter()
+        cpu.one_image(xs)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": 1.0 / dt, "unit": "images/s", "cores": cpu.cores, "kind": "port",
+                        "torch_threads": torch.get_num_threads(), "seconds": dt,
+                        "sample": "1 image of the batch: 2 fp32 CPU forwards (flip test) + "
+                                  "aggregation + parse(adjust, refine), oracle port of the "
+                                  "reference's per-image loop"}
+
+    if rank == 0:
+        h2d = x_host.numel() * x_host.element_size()
+        d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.mode, "data": "synthetic", "config": workload_config(args),
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline,
+            "roofline_decode": roofline_decode, "cpu_baseline": cpu_baseline,
+            "forward_tflops_effective": 2 * args.batch * world * args.steps *
+            FLOP_PER_FORWARD_640 * (args.size / 640.0) ** 2 / (ms_dev * 1e-3) / 1e12,
+            "people_per_image": people_mean,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--size", type=int, default=640)
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--chunk", type=int, default=16, help="forwards per plan replay")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if args.steps is None:
+            args.steps = 2
+        args.warmup = min(args.warmup, 1)
+        run_reference_arm(args, rank)
+        return
+    if args.steps is None:
+        args.steps = 10
+    if world != args.gpus and world > 1:
+        print("warning: WORLD_SIZE %d != --gpus %d" % (world, args.gpus), file=sys.stderr)
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

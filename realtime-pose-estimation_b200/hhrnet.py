@@ -209,7 +209,7 @@ class _Recorder:
 
     def _pack(self, wt, desc, cin_store):
         """wt: (ntaps, Cout, Cin) f32 -> packed weight tensor for the chosen engine."""
-        lib = L.load()
+        lib = L.load(require_cuda=False)
         ntaps, cout, cin = wt.shape
         if cin_store > cin:                                   # zero weights for pad channels
             wt = torch.cat((wt, wt.new_zeros(ntaps, cout, cin_store - cin)), dim=2)
@@ -333,7 +333,7 @@ class _Recorder:
 
     # -- arena + native plan
     def build(self, in_buf):
-        lib = L.load()
+        lib = L.load(require_cuda=False)
         esize = 4 if self.mode == "fp32" else 2
         free = []                                  # (bytes, tensor) of released buffers
         release_at = {}
@@ -403,8 +403,8 @@ class _CompiledPlan:
         self.in_buf = in_buf
         self.outs = outs
         self.recorder = recorder            # keeps arena + packed weights alive
-        self.num_ops = L.load().brtpe_plan_num_ops(handle)
-        self.conv_flops = L.load().brtpe_plan_conv_flops(handle)
+        self.num_ops = L.load(require_cuda=False).brtpe_plan_num_ops(handle)
+        self.conv_flops = L.load(require_cuda=False).brtpe_plan_conv_flops(handle)
 
     def __del__(self):
         try:
