@@ -270,13 +270,13 @@ def run_ours(args, rank, world, local_rank):
     chunk = min(args.chunk, 2 * args.batch)
     net.plan_profile(chunk, args.size, args.size, in_dtype)
     ms_ops, kinds, flops = net.plan_profile(chunk, args.size, args.size, in_dtype)
-    conv_ms = sum(m for m, k in zip(ms_ops, kinds) if k in (0, 1))
+    conv_ms = sum(m for m, k in zip(ms_ops, kinds) if k in (0, 1, 3))
     conv_flops = sum(flops)
-    umma_ms = sum(m for m, k in zip(ms_ops, kinds) if k == 0)
-    umma_flops = sum(f for f, k in zip(flops, kinds) if k == 0)
-    umma_launches = sum(1 for k in kinds if k == 0)
+    umma_ms = sum(m for m, k in zip(ms_ops, kinds) if k in (0, 3))
+    umma_flops = sum(f for f, k in zip(flops, kinds) if k in (0, 3))
+    umma_launches = sum(1 for k in kinds if k in (0, 3))
     achieved = (umma_flops if umma_ms > 0 else conv_flops) / max(umma_ms or conv_ms, 1e-9) / 1e9
-    roofline = {"bound": "tensor", "kernel": "conv_umma_kernel (tcgen05 implicit GEMM)",
+    roofline = {"bound": "tensor", "kernel": "conv_halo_kernel + conv_umma_kernel (tcgen05 implicit GEMM)",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tflops"], "traffic": None,
                 "launches": umma_launches, "avg_launch_ms": umma_ms / max(umma_launches, 1),

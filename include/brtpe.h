@@ -142,7 +142,11 @@ int brtpe_aggregate_scale(const float* y0, const float* y1, const float* y0f, co
  * ---------------------------------------------------------------------------------- */
 
 enum { BRTPE_DT_F32 = 0, BRTPE_DT_BF16 = 1 };
-enum { BRTPE_ENGINE_AUTO = 0, BRTPE_ENGINE_FFMA = 1, BRTPE_ENGINE_UMMA = 2 };
+/* FFMA: CUDA-core fp32-accurate path.  UMMA: tcgen05, one TMA box per tap (any tap table).
+ * UMMA_HALO: tcgen05, 3x3/stride-1 only, one halo tile per channel block + cluster-multicast
+ * weights.  AUTO picks HALO, then UMMA, then FFMA, by what the layer allows. */
+enum { BRTPE_ENGINE_AUTO = 0, BRTPE_ENGINE_FFMA = 1, BRTPE_ENGINE_UMMA = 2,
+       BRTPE_ENGINE_UMMA_HALO = 3 };
 
 /* One fused conv launch: out = act( conv(in, w) + bias [+ residual] ), NHWC activations.
  * Covers nn.Conv2d 3x3/1x1 stride 1/2 (pose_higher_hrnet.py:40-43,:83-89,:163,:202,:218,
@@ -177,7 +181,7 @@ int brtpe_conv_run(const brtpe_conv_desc* d, const void* in, const void* weights
                    const float* bias, const void* residual, void* out, void* stream);
 
 /* Engine brtpe_conv_run / brtpe_plan_add_conv will use for this descriptor
- * (BRTPE_ENGINE_FFMA or BRTPE_ENGINE_UMMA), or a negative error code. */
+ * (BRTPE_ENGINE_FFMA, BRTPE_ENGINE_UMMA or BRTPE_ENGINE_UMMA_HALO), or a negative error code. */
 int brtpe_conv_select_engine(const brtpe_conv_desc* d);
 /* Packed-weight geometry of the tcgen05 path: bf16 [ntaps][*cout_pad][*cin_pad]. */
 int brtpe_umma_weight_dims(int Cin, int Cout_store, int* cin_pad, int* cout_pad);
@@ -222,7 +226,7 @@ int brtpe_plan_run(brtpe_plan*, void* stream);
 /* capture the op list into a CUDA graph (once), then launch it */
 int brtpe_plan_graph_launch(brtpe_plan*, void* stream);
 /* run un-graphed with CUDA events around each op; ms_out[num_ops] (host) gets per-op
- * device milliseconds; kinds_out[num_ops] (host): 0 conv-umma, 1 conv-ffma, 2 other.
+ * device milliseconds; kinds_out[num_ops] (host): 0 conv-umma, 1 conv-ffma, 2 other, 3 conv-umma-halo.
  * Synchronises the stream. */
 int brtpe_plan_profile(brtpe_plan*, void* stream, float* ms_out, int32_t* kinds_out,
                        double* flops_out);

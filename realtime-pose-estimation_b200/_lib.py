@@ -20,7 +20,7 @@ MAX_GROUP_K = 32
 MAX_JOINTS = 32
 
 DT_F32, DT_BF16 = 0, 1
-ENGINE_AUTO, ENGINE_FFMA, ENGINE_UMMA = 0, 1, 2
+ENGINE_AUTO, ENGINE_FFMA, ENGINE_UMMA, ENGINE_UMMA_HALO = 0, 1, 2, 3
 
 
 class BrtpeError(RuntimeError):

@@ -17,6 +17,14 @@ void umma_conv_release(UmmaConvPrepared*);
 int umma_conv_launch(const UmmaConvPrepared* p, const float* bias, const void* residual, void* out,
                      cudaStream_t st);
 
+// ---- tcgen05 halo-tile back end for 3x3 stride-1 convs (conv_halo.cu)
+struct HaloConvPrepared;
+bool halo_conv_supported(const brtpe_conv_desc* d);
+HaloConvPrepared* halo_conv_prepare(const brtpe_conv_desc* d, const void* in, const void* weights);
+void halo_conv_release(HaloConvPrepared*);
+int halo_conv_launch(const HaloConvPrepared* p, const float* bias, const void* residual, void* out,
+                     cudaStream_t st);
+
 int stem_conv1_launch(const void* img, int img_is_half, int N, int H, int W, const float* w,
                       const float* bias, int Cout, void* out, int out_dtype, cudaStream_t st);
 int fuse_sum_launch(int dtype, int nterms, const void* const* terms, const int32_t* shifts,

@@ -21,6 +21,8 @@
 // `stages` A/B slots (full/empty mbarriers) and two TMEM accumulator stages (tmem_full /
 // tmem_empty), so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "conv_common.cuh"
+#include "umma_ptx.cuh"
+#include "conv_epilogue.cuh"
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -44,11 +46,9 @@ struct alignas(64) UmmaParams {
   int tap_c[9], tap_x[9], tap_p[9], tap_y[9];
   int stages, b_stage_bytes, tmem_cols, acc_cols;
   uint32_t idesc;
-  void* out;
-  const void* res;
   const float* bias;
-  int Hout, Wout, out_scale, out_oy, out_ox, out_ld, out_coff, res_ld, res_coff;
-  int Cout, Cout_store, relu;
+  int Hout, Wout, out_scale, out_oy, out_ox;
+  EpiParams epi;
 };
 
 struct UmmaConvPrepared {
@@ -57,109 +57,8 @@ struct UmmaConvPrepared {
   size_t smem;
 };
 
-// ------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > (1u << 22)) __trap();  // a protocol bug becomes an error, not a hung GPU
-  }
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
-               "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
-               : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                         uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32"
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format):
-//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major, 1) |
-//   [32,46) SBO >> 4 (8 rows x 128 B = 1024) | [46,48) version = 1 | [61,64) layout = 2.
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
-  d |= (uint64_t)1u << 16;
-  d |= (uint64_t)(1024u >> 4) << 32;
-  d |= (uint64_t)1u << 46;
-  d |= (uint64_t)2u << 61;
-  return d;
+__device__ __forceinline__ uint32_t um_desc_lo(uint32_t smem_addr) {
+  return ((smem_addr >> 4) & 0x3fffu) | (1u << 16);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -170,8 +69,13 @@ conv_umma_kernel(const __grid_constant__ UmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int stages = p.stages, ntaps = p.ntaps, num_kb = p.num_kb, last_k16 = p.last_k16;
+  const int total_tiles = p.total_tiles, n_tiles = p.n_tiles, BN = p.BN;
+  const int tiles_x = p.tiles_x, tiles_xy = p.tiles_x * p.tiles_y;
+  const int TW = p.TW, TH = p.TH, TN = p.TN;
+  const uint32_t idesc = p.idesc;
   const int stage_bytes = UM_A_BYTES + p.b_stage_bytes;
-  uint8_t* tail = smem + (size_t)p.stages * stage_bytes;
+  uint8_t* tail = smem + (size_t)stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + UM_MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + UM_MAX_STAGES;
@@ -185,7 +89,7 @@ conv_umma_kernel(const __grid_constant__ UmmaParams p) {
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmap_a);
     tma_prefetch_desc(&p.tmap_b);
-    for (int s = 0; s < p.stages; ++s) {
+    for (int s = 0; s < stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
@@ -196,155 +100,112 @@ conv_umma_kernel(const __grid_constant__ UmmaParams p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.n_tiles * p.BN; i += UM_THREADS)
-    bias_s[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.0f;
+  for (int i = threadIdx.x; i < n_tiles * BN; i += UM_THREADS)
+    bias_s[i] = (p.bias && i < p.epi.Cout) ? p.bias[i] : 0.0f;
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  const int tiles_xy = p.tiles_x * p.tiles_y;
-  const uint32_t tx_bytes = (uint32_t)(p.TW * p.TH * p.TN * 128 + p.BN * 128);
+  const uint32_t tx_bytes = (uint32_t)(TW * TH * TN * 128 + BN * 128);
 
   if (warp == 0) {
-    // ===================== TMA producer (one lane) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        const int mt = tile / p.n_tiles;
-        const int x0 = (mt % p.tiles_x) * p.TW;
-        const int y0 = ((mt % tiles_xy) / p.tiles_x) * p.TH;
-        const int n0 = (mt / tiles_xy) * p.TN;
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          for (int kb = 0; kb < p.num_kb; ++kb) {
-            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+    // ===================== TMA producer (warp-uniform, elected lane issues) ================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % n_tiles;
+      const int mt = tile / n_tiles;
+      const int x0 = (mt % tiles_x) * TW;
+      const int y0 = ((mt % tiles_xy) / tiles_x) * TH;
+      const int n0 = (mt / tiles_xy) * TN;
+#pragma unroll 1
+      for (int tap = 0; tap < ntaps; ++tap) {
+        const int tc = p.tap_c[tap], tx = x0 + p.tap_x[tap], tp = p.tap_p[tap], ty = y0 + p.tap_y[tap];
+#pragma unroll 1
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+          if (elect_one()) {
             const uint32_t fb = smem_u32(&full_bar[stage]);
             mbar_expect_tx(fb, tx_bytes);
             const uint32_t a_dst = smem_u32(smem + (size_t)stage * stage_bytes);
-            tma_load_5d(a_dst, &p.tmap_a, fb, p.tap_c[tap] + kb * 64, x0 + p.tap_x[tap],
-                        p.tap_p[tap], y0 + p.tap_y[tap], n0);
-            tma_load_3d(a_dst + UM_A_BYTES, &p.tmap_b, fb, kb * 64, nt * p.BN, tap);
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1u;
-            }
+            tma_load_5d(a_dst, &p.tmap_a, fb, tc + kb * 64, tx, tp, ty, n0);
+            tma_load_3d(a_dst + UM_A_BYTES, &p.tmap_b, fb, kb * 64, nt * BN, tap);
           }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one lane) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_cols);
-        uint32_t accumulate = 0;
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          for (int kb = 0; kb < p.num_kb; ++kb) {
-            mbar_wait(smem_u32(&full_bar[stage]), phase);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-            const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
-            const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + UM_A_BYTES);
-            const int k16 = (kb == p.num_kb - 1) ? p.last_k16 : 4;
-            for (int k = 0; k < k16; ++k) {
-              // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in >>4 units
-              umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                       accumulate);
-              accumulate = 1;
-            }
-            umma_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot when MMAs retire
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1u;
-            }
+    // ===================== MMA issuer (warp-uniform, elected lane issues) ==================
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t ring_lo = um_desc_lo(smem_u32(smem));
+    const uint32_t stage_lo = (uint32_t)(stage_bytes >> 4);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_cols);
+      uint32_t first = 0;
+#pragma unroll 1
+      for (int tap = 0; tap < ntaps; ++tap) {
+#pragma unroll 1
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_lo = ring_lo + (uint32_t)stage * stage_lo;
+          const uint32_t b_lo = a_lo + (uint32_t)(UM_A_BYTES >> 4);
+          const int k16 = (kb == num_kb - 1) ? last_k16 : 4;
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < k16)
+                umma_f16_lohi(d_tmem, a_lo + 2u * k, HI, b_lo + 2u * k, HI, idesc, (first | k) ? 1u : 0u);
+            umma_commit(smem_u32(&empty_bar[stage]));
           }
+          __syncwarp();
+          first = 1;
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(smem_u32(&tfull_bar[as]));  // accumulator ready for the epilogue
       }
+      if (elect_one()) umma_commit(smem_u32(&tfull_bar[as]));
+      __syncwarp();
     }
   } else {
-    // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+    // ===================== epilogue (4 warps, one TMEM lane quarter each) ===================
     const int lg = warp & 3;
     const int m = lg * 32 + lane;
-    const int tw = m % p.TW;
-    const int th = (m / p.TW) % p.TH;
-    const int tn = m / (p.TW * p.TH);
-    __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(p.out);
-    const __nv_bfloat16* __restrict__ res = reinterpret_cast<const __nv_bfloat16*>(p.res);
+    const int tw = m % TW;
+    const int th = (m / TW) % TH;
+    const int tn = m / (TW * TH);
+    const EpiParams e = p.epi;
+    const int nchunks = BN >> 4;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int nt = tile % p.n_tiles;
-      const int mt = tile / p.n_tiles;
-      const int xm = (mt % p.tiles_x) * p.TW + tw;
-      const int ym = ((mt % tiles_xy) / p.tiles_x) * p.TH + th;
-      const int n = (mt / tiles_xy) * p.TN + tn;
-      const bool valid = (tn < p.TN) && xm < p.Wm && ym < p.Hm && n < p.N;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int nt = tile % n_tiles;
+      const int mt = tile / n_tiles;
+      const int xm = (mt % tiles_x) * TW + tw;
+      const int ym = ((mt % tiles_xy) / tiles_x) * TH + th;
+      const int n = (mt / tiles_xy) * TN + tn;
+      const bool valid = (tn < TN) && xm < p.Wm && ym < p.Hm && n < p.N;
       const size_t opix =
           valid ? ((size_t)n * p.Hout + (size_t)(ym * p.out_scale + p.out_oy)) * p.Wout +
                       (size_t)(xm * p.out_scale + p.out_ox)
                 : 0;
+      const int co0 = nt * BN;
+      ResPrefetch rp;
+      epi_prefetch(rp, e, valid, opix, co0, nchunks);
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(smem_u32(&tfull_bar[as]), aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * p.acc_cols);
-      const int co0 = nt * p.BN;
-      for (int c = 0; c < p.BN; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(t_addr + (uint32_t)c, r);
-        tmem_ld_wait();
-        if (c + 16 >= p.BN) {
-          // all TMEM reads of this tile are done: hand the accumulator stage back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
-        }
-        const int co = co0 + c;
-        if (!valid || co >= p.Cout_store) continue;
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + bias_s[co + i];
-        const bool full_chunk = (co + 16 <= p.Cout_store);
-        if (res) {
-          const __nv_bfloat16* rp = res + opix * p.res_ld + p.res_coff + co;
-          if (full_chunk) {
-            uint4 q[2];
-            q[0] = __ldg(reinterpret_cast<const uint4*>(rp));
-            q[1] = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-            const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(q);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += __bfloat162float(rb[i]);
-          } else {
-            for (int i = 0; i < 16 && co + i < p.Cout; ++i) v[i] += __bfloat162float(rp[i]);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (p.relu) v[i] = fmaxf(v[i], 0.0f);
-          if (co + i >= p.Cout) v[i] = 0.0f;
-        }
-        __nv_bfloat16* op = out + opix * p.out_ld + p.out_coff + co;
-        if (full_chunk) {
-          uint4 q[2];
-          __nv_bfloat162* qb = reinterpret_cast<__nv_bfloat162*>(q);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) qb[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-          reinterpret_cast<uint4*>(op)[0] = q[0];
-          reinterpret_cast<uint4*>(op)[1] = q[1];
-        } else {
-          for (int i = 0; i < 16 && co + i < p.Cout_store; ++i) op[i] = __float2bfloat16_rn(v[i]);
-        }
-      }
+      epi_drain(e, bias_s, rp, t_addr, nchunks, co0, valid, opix, smem_u32(&tempty_bar[as]), lane);
     }
   }
 
@@ -469,10 +330,13 @@ UmmaConvPrepared* umma_conv_prepare(const brtpe_conv_desc* d, const void* in, co
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
             ((uint32_t)(128 >> 4) << 24);
 
-  p.out = nullptr; p.res = nullptr; p.bias = nullptr;
+  p.bias = nullptr;
   p.Hout = d->Hout; p.Wout = d->Wout; p.out_scale = d->out_scale; p.out_oy = d->out_oy;
-  p.out_ox = d->out_ox; p.out_ld = d->out_ld; p.out_coff = d->out_coff; p.res_ld = d->res_ld;
-  p.res_coff = d->res_coff; p.Cout = d->Cout; p.Cout_store = d->Cout_store; p.relu = d->relu;
+  p.out_ox = d->out_ox;
+  p.epi.out = nullptr; p.epi.res = nullptr;
+  p.epi.out_ld = d->out_ld; p.epi.out_coff = d->out_coff; p.epi.res_ld = d->res_ld;
+  p.epi.res_coff = d->res_coff; p.epi.Cout = d->Cout; p.epi.Cout_store = d->Cout_store;
+  p.epi.relu = d->relu; p.epi.vec32 = epi_vec32_ok(d);
 
   // ---- tensor maps
   auto encode = get_encode_fn();
@@ -534,8 +398,8 @@ int umma_conv_launch(const UmmaConvPrepared* P, const float* bias, const void* r
                      cudaStream_t st) {
   UmmaParams p = P->p;
   p.bias = bias;
-  p.res = residual;
-  p.out = out;
+  p.epi.res = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.epi.out = reinterpret_cast<__nv_bfloat16*>(out);
   conv_umma_kernel<<<P->grid, UM_THREADS, P->smem, st>>>(p);
   BRTPE_LAUNCH_CHECK();
   return BRTPE_OK;

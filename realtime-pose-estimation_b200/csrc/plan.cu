@@ -18,7 +18,8 @@ struct Op {
   const float* bias;
   const void* res;
   void* out;
-  UmmaConvPrepared* umma;  // non-null: tcgen05 path
+  UmmaConvPrepared* umma;  // non-null: tcgen05 per-tap path
+  HaloConvPrepared* halo;  // non-null: tcgen05 halo-tile path
   // stem / tonchw / fuse
   int i[12];
   const void* terms[4];
@@ -28,6 +29,15 @@ struct Op {
 
 static int choose_engine(const brtpe_conv_desc* d) {
   if (d->engine == BRTPE_ENGINE_FFMA) return BRTPE_ENGINE_FFMA;
+  const bool halo_ok = halo_conv_supported(d);
+  if (d->engine == BRTPE_ENGINE_UMMA_HALO) {
+    if (!halo_ok) {
+      set_error("conv: halo tcgen05 engine requested but the layer is not a 3x3/s1 bf16 conv");
+      return -1;
+    }
+    return BRTPE_ENGINE_UMMA_HALO;
+  }
+  if (d->engine == BRTPE_ENGINE_AUTO && halo_ok) return BRTPE_ENGINE_UMMA_HALO;
   const char* why = nullptr;
   const bool ok = umma_conv_supported(d, &why);
   if (d->engine == BRTPE_ENGINE_UMMA) {
@@ -43,6 +53,7 @@ static int choose_engine(const brtpe_conv_desc* d) {
 static int run_op(const Op& op, cudaStream_t st) {
   switch (op.kind) {
     case OP_CONV:
+      if (op.halo) return halo_conv_launch(op.halo, op.bias, op.res, op.out, st);
       if (op.umma) return umma_conv_launch(op.umma, op.bias, op.res, op.out, st);
       return conv_ffma_launch(&op.d, op.in, op.w, op.bias, op.res, op.out, st);
     case OP_STEM:
@@ -69,8 +80,10 @@ struct brtpe_plan {
   cudaStream_t capture_stream = nullptr;
   ~brtpe_plan() {
     if (capture_stream) cudaStreamDestroy(capture_stream);
-    for (auto& op : ops)
+    for (auto& op : ops) {
       if (op.umma) umma_conv_release(op.umma);
+      if (op.halo) halo_conv_release(op.halo);
+    }
     if (exec) cudaGraphExecDestroy(exec);
     if (graph) cudaGraphDestroy(graph);
   }
@@ -83,6 +96,13 @@ extern "C" int brtpe_conv_run(const brtpe_conv_desc* d, const void* in, const vo
   BRTPE_CHECK_ARG(in && weights && out, "brtpe_conv_run: null tensor");
   const int eng = choose_engine(d);
   if (eng < 0) return BRTPE_EINVAL;
+  if (eng == BRTPE_ENGINE_UMMA_HALO) {
+    HaloConvPrepared* p = halo_conv_prepare(d, in, weights);
+    if (!p) return BRTPE_ECUDA;
+    rc = halo_conv_launch(p, bias, residual, out, (cudaStream_t)stream);
+    halo_conv_release(p);
+    return rc;
+  }
   if (eng == BRTPE_ENGINE_UMMA) {
     UmmaConvPrepared* p = umma_conv_prepare(d, in, weights);
     if (!p) return BRTPE_ECUDA;
@@ -136,7 +156,11 @@ extern "C" int brtpe_plan_add_conv(brtpe_plan* pl, const brtpe_conv_desc* d, con
   op.d = *d;
   op.in = in; op.w = weights; op.bias = bias; op.res = residual; op.out = out;
   op.umma = nullptr;
-  if (eng == BRTPE_ENGINE_UMMA) {
+  op.halo = nullptr;
+  if (eng == BRTPE_ENGINE_UMMA_HALO) {
+    op.halo = halo_conv_prepare(d, in, weights);
+    if (!op.halo) return BRTPE_ECUDA;
+  } else if (eng == BRTPE_ENGINE_UMMA) {
     op.umma = umma_conv_prepare(d, in, weights);
     if (!op.umma) return BRTPE_ECUDA;
   }
@@ -260,7 +284,7 @@ extern "C" int brtpe_plan_profile(brtpe_plan* pl, void* stream, float* ms_out, i
   for (size_t i = 0; i < n && !rc; ++i) {
     cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
     const Op& op = pl->ops[i];
-    if (kinds_out) kinds_out[i] = op.kind == OP_CONV ? (op.umma ? 0 : 1) : 2;
+    if (kinds_out) kinds_out[i] = op.kind == OP_CONV ? (op.halo ? 3 : (op.umma ? 0 : 1)) : 2;
     if (flops_out) flops_out[i] = op.kind == OP_CONV ? conv_flops(&op.d) : 0.0;
   }
   for (auto& evt : ev) cudaEventDestroy(evt);

@@ -216,7 +216,7 @@ class _Recorder:
         eng = lib.brtpe_conv_select_engine(C.byref(desc))
         if eng < 0:
             L.check(eng, "brtpe_conv_select_engine")
-        if eng == L.ENGINE_UMMA:
+        if eng in (L.ENGINE_UMMA, L.ENGINE_UMMA_HALO):
             cin_pad, cout_pad = C.c_int(0), C.c_int(0)
             lib.brtpe_umma_weight_dims(cin_store, desc.Cout_store, C.byref(cin_pad),
                                        C.byref(cout_pad))
@@ -240,7 +240,7 @@ class _Recorder:
         cout_store = cout if cout_store is None else cout_store
         ho, wo = x.h // s, x.w // s
         if out is None:
-            out = self.new(x.n, ho, wo, max(cout_store, (cout_store + 7) // 8 * 8))
+            out = self.new(x.n, ho, wo, (cout_store + 15) // 16 * 16)
         taps = _TAPS3 if k == 3 else [(0, 0)]
         w, b = self._fold(conv, bn)
         wt = torch.stack([w[:, :, dy + (k // 2), dx + (k // 2)] for dy, dx in taps], 0)

@@ -25,7 +25,7 @@ def make_desc(dtype, engine, n, h, w, cin, cout, k, stride, relu, in_ld=None, in
         d.tap_dy[i], d.tap_dx[i] = dy, dx
     d.Hout, d.Wout, d.out_scale, d.out_oy, d.out_ox = ho, wo, 1, 0, 0
     d.Cout = cout
-    d.out_ld = out_ld or ((cout_store + 7) // 8 * 8)
+    d.out_ld = out_ld or ((cout_store + 15) // 16 * 16)
     d.out_coff = out_coff
     d.res_ld, d.res_coff = res_ld, 0
     d.relu = int(relu)
@@ -36,7 +36,7 @@ def make_desc(dtype, engine, n, h, w, cin, cout, k, stride, relu, in_ld=None, in
 def pack_weights(lib, w, taps, k, desc, engine_used, bf16_round):
     """w (Cout,Cin,k,k) f32 -> packed tensor for engine_used."""
     wt = torch.stack([w[:, :, dy + k // 2, dx + k // 2] for dy, dx in taps], 0)  # (T,Cout,Cin)
-    if engine_used == L.ENGINE_UMMA:
+    if engine_used in (L.ENGINE_UMMA, L.ENGINE_UMMA_HALO):
         cp, op = C.c_int(0), C.c_int(0)
         lib.brtpe_umma_weight_dims(desc.Cin, desc.Cout_store, C.byref(cp), C.byref(op))
         packed = torch.zeros((len(taps), op.value, cp.value), dtype=torch.bfloat16, device=w.device)
@@ -61,7 +61,7 @@ def run_conv(engine, mode, n, h, w, cin, cout, k, stride, relu, use_res, seed=0,
     d, taps = make_desc(L.DT_BF16 if bf else L.DT_F32, engine, n, h, w, cin, cout, k, stride,
                         relu, res_ld=(cout if use_res else 0))
     eng = lib.brtpe_conv_select_engine(C.byref(d))
-    assert eng in (L.ENGINE_FFMA, L.ENGINE_UMMA), lib.brtpe_last_error()
+    assert eng in (L.ENGINE_FFMA, L.ENGINE_UMMA, L.ENGINE_UMMA_HALO), lib.brtpe_last_error()
     xin = x.permute(0, 2, 3, 1).contiguous().to(tdt)
     rin = res.permute(0, 2, 3, 1).contiguous().to(tdt) if use_res else None
     packed = pack_weights(lib, wgt, taps, k, d, eng, bf)

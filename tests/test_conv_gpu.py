@@ -48,3 +48,32 @@ def test_umma_bf16(cuda_device, shape):
     assert eng == L.ENGINE_UMMA
     assert torch.isfinite(got).all()
     assert _err(got, ref) <= 6e-3
+
+
+HALO_SHAPES = [
+    # n, h, w, cin, cout, k, stride, relu, res  (3x3 stride 1 only)
+    (2, 32, 48, 48, 48, 3, 1, True, True),
+    (1, 40, 40, 96, 96, 3, 1, True, False),
+    (3, 20, 20, 192, 192, 3, 1, False, True),
+    (1, 20, 20, 384, 384, 3, 1, True, True),
+    (1, 16, 16, 256, 48, 3, 1, True, False),
+    (2, 24, 40, 64, 64, 3, 1, True, False),
+    (1, 17 * 2, 22, 48, 48, 3, 1, True, True),
+    (5, 16, 8, 96, 96, 3, 1, True, True),
+]
+
+
+@pytest.mark.parametrize("shape", HALO_SHAPES)
+def test_umma_halo_bf16(cuda_device, shape):
+    got, ref, eng = run_conv(L.ENGINE_UMMA_HALO, "bf16", *shape)
+    assert eng == L.ENGINE_UMMA_HALO
+    assert torch.isfinite(got).all()
+    assert _err(got, ref) <= 6e-3
+
+
+@pytest.mark.parametrize("cs", ["1", "2", "4"])
+def test_umma_halo_cluster_sizes(cuda_device, cs, monkeypatch):
+    monkeypatch.setenv("BRTPE_HALO_CS", cs)
+    for shape in [(2, 32, 32, 96, 96, 3, 1, True, True), (1, 48, 40, 48, 48, 3, 1, True, True)]:
+        got, ref, eng = run_conv(L.ENGINE_UMMA_HALO, "bf16", *shape)
+        assert _err(got, ref) <= 6e-3

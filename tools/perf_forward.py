@@ -32,15 +32,26 @@ def main():
           (chunk, size, size, dt * 1e3, chunk / dt, flops / dt / 1e12))
     ms, kinds, fl = net.plan_profile(chunk, size, size, torch.float16)
     tot = sum(ms)
-    umma = sum(m for m, k in zip(ms, kinds) if k == 0)
+    umma = sum(m for m, k in zip(ms, kinds) if k in (0, 3))
     ffma = sum(m for m, k in zip(ms, kinds) if k == 1)
     other = sum(m for m, k in zip(ms, kinds) if k == 2)
-    uf = sum(f for f, k in zip(fl, kinds) if k == 0)
+    uf = sum(f for f, k in zip(fl, kinds) if k in (0, 3))
     print("profile: total %.3f ms over %d ops; umma %.3f ms (%.1f TFLOP/s), ffma %.3f ms, other %.3f ms"
           % (tot, len(ms), umma, uf / max(umma, 1e-9) / 1e9, ffma, other))
-    rows = sorted(zip(ms, kinds, fl, range(len(ms))), reverse=True)[:25]
-    for m, k, f, i in rows:
-        print("  op %3d kind %d %.4f ms  %.2f GFLOP  %.1f TFLOP/s" % (i, k, m, f / 1e9, f / max(m, 1e-9) / 1e9))
+    plan = net._get_plan(chunk, size, size, net._mode(), x.device, torch.float16)
+    groups = {}
+    for i, op in enumerate(plan.recorder.ops):
+        if op[0] == "conv":
+            d = op[1]
+            key = ("conv k%d %dx%d s%d %d->%d @%dx%d" % (kinds[i], 3 if d.ntaps == 9 else (2 if d.ntaps == 4 else 1),
+                   3 if d.ntaps == 9 else (2 if d.ntaps == 4 else 1), d.in_stride, d.Cin, d.Cout, d.Hm, d.Wm))
+        else:
+            key = op[0]
+        g = groups.setdefault(key, [0, 0.0, 0.0])
+        g[0] += 1; g[1] += ms[i]; g[2] += fl[i]
+    print("%-44s %5s %9s %7s %9s" % ("op group", "count", "ms", "%time", "TFLOP/s"))
+    for key, (cnt, m, f) in sorted(groups.items(), key=lambda kv: -kv[1][1]):
+        print("%-44s %5d %9.4f %6.1f%% %9.1f" % (key, cnt, m, 100 * m / tot, f / max(m, 1e-9) / 1e9))
 
     # decode stress (config 5 shape, smaller batch)
     nb = int(os.environ.get("DECODE_BATCH", "128"))
