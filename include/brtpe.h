@@ -193,6 +193,13 @@ int brtpe_stem_conv1(const void* img, int img_dtype_is_half, int N, int H, int W
                      const float* w, const float* bias, int Cout, void* out, int out_dtype,
                      void* stream);
 
+/* Stem im2col, the bf16 / tcgen05 form of conv1 (pose_higher_hrnet.py:363-365): NCHW
+ * float32/half image -> NHWC bf16 (N, H/2, W/2, 32); channel k = (ky*3 + kx)*3 + ci is the
+ * 3x3 / stride-2 / pad-1 window of output pixel (oy, ox), channels 27..31 are zero.  conv1
+ * + BN + ReLU is then brtpe_conv_run with a 1x1 tap table and Cin = 32. */
+int brtpe_stem_im2col(const void* img, int img_dtype_is_half, int N, int H, int W, void* out,
+                      void* stream);
+
 /* y_i = relu?( sum_k up_{2^shift_k}(term_k) ) of HighResolutionModule.forward
  * (pose_higher_hrnet.py:245-254); NHWC, nterms <= 4, nearest-neighbour upsample. */
 int brtpe_fuse_sum(int dtype, int nterms, const void* const* terms, const int32_t* shifts,
@@ -218,6 +225,15 @@ int brtpe_plan_add_fuse(brtpe_plan*, int dtype, int nterms, const void* const* t
                         int C, void* out, int out_ld, int relu);
 int brtpe_plan_add_nhwc_to_nchw(brtpe_plan*, int dtype, const void* src, int N, int H, int W,
                                 int C, int ld, int coff, void* dst, int dst_is_half);
+int brtpe_plan_add_stem_im2col(brtpe_plan*, const void* img, int img_is_half, int N, int H, int W,
+                               void* out);
+/* Scheduling annotation of the op added last: `lane` (0..7) is the capture stream the op is
+ * issued on, deps[ndeps] are indices of EARLIER ops that must have completed before it (ops
+ * of the same lane are ordered implicitly).  brtpe_plan_graph_launch turns lanes into
+ * parallel branches of the CUDA graph (the HRNet resolution branches run concurrently);
+ * brtpe_plan_run / brtpe_plan_profile ignore the annotation and run in recording order.
+ * Ops without annotation are lane 0 with no cross-lane dependencies. */
+int brtpe_plan_set_sched(brtpe_plan*, int lane, const int32_t* deps, int ndeps);
 int brtpe_plan_num_ops(const brtpe_plan*);
 /* total algorithmic conv FLOPs (2*MAC) of the plan's conv ops */
 double brtpe_plan_conv_flops(const brtpe_plan*);

@@ -86,6 +86,9 @@ _SIGS = {
     "brtpe_plan_add_fuse": (_I, [_P, _I, _I, C.POINTER(_P), C.POINTER(C.c_int32),
                                  C.POINTER(C.c_int32), _I, _I, _I, _I, _P, _I, _I]),
     "brtpe_plan_add_nhwc_to_nchw": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I]),
+    "brtpe_plan_add_stem_im2col": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "brtpe_plan_set_sched": (_I, [_P, _I, C.POINTER(C.c_int32), _I]),
+    "brtpe_stem_im2col": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "brtpe_plan_num_ops": (_I, [_P]),
     "brtpe_plan_conv_flops": (C.c_double, [_P]),
     "brtpe_plan_run": (_I, [_P, _P]),

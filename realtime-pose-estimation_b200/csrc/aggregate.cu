@@ -98,6 +98,164 @@ __device__ __forceinline__ float cascade_sample(const AggArgs& a, const float* _
   return by.w0 * (bx.w0 * g[0][0] + bx.w1 * g[0][1]) + by.w1 * (bx.w0 * g[1][0] + bx.w1 * g[1][1]);
 }
 
+// ---- tiled version: the stage-average map G (at 1/2 resolution) of the tile's footprint is
+// built once in shared memory (for the image and for the mirrored image), then every output
+// pixel is one 4-tap blend of G.  Same per-element arithmetic as the direct kernel below;
+// ~10x fewer instructions per output, so the kernel is bound by its det/tag writes.
+constexpr int AG_TH = 32, AG_TW = 128, AG_THREADS = 256;
+constexpr int AG_MAXP = 2560;             // floats per G patch (two patches in smem)
+
+__device__ __forceinline__ float g_value(const AggArgs& a, const float* __restrict__ q0,
+                                         const float* __restrict__ q1, int y2, int x2, bool mirror) {
+  if (mirror) x2 = a.W2 - 1 - x2;
+  const Lerp ly = make_lerp(a.s42y, y2, a.H4, false);
+  const Lerp lx = make_lerp(a.s42x, x2, a.W4, false);
+  float v = bilerp(q0, a.W4, ly, lx);
+  if (q1) v = (v + __ldg(q1 + (size_t)y2 * a.W2 + x2)) * 0.5f;
+  return v;
+}
+
+__global__ void __launch_bounds__(AG_THREADS) aggregate_scale_tiled_kernel(AggArgs a) {
+  __shared__ float G[2][AG_MAXP];
+  const int xb0 = blockIdx.x * AG_TW, yb0 = blockIdx.y * AG_TH;
+  const int yb1 = min(yb0 + AG_TH, a.Hb) - 1, xb1 = min(xb0 + AG_TW, a.Wb) - 1;
+  const int y2lo = make_lerp(a.s2by, yb0, a.H2, false).i0, y2hi = make_lerp(a.s2by, yb1, a.H2, false).i1;
+  const int x2lo = make_lerp(a.s2bx, xb0, a.W2, false).i0, x2hi = make_lerp(a.s2bx, xb1, a.W2, false).i1;
+  const int PH = y2hi - y2lo + 1, PW = x2hi - x2lo + 1;
+  const int C0 = a.J + a.A;
+  const size_t p4 = (size_t)a.H4 * a.W4, p2 = (size_t)a.H2 * a.W2, pb = (size_t)a.Hb * a.Wb;
+  const bool flip = a.y0f != nullptr;
+  const int T = flip ? 2 : 1;
+  const int nch = a.J + (a.tag ? a.A : 0);
+  const int tid = threadIdx.x;
+  const int cx = (tid & 31) * 4, ry = tid >> 5;             // 4 columns x rows ry, ry+8, ...
+  // per-thread column interpolation (fixed for the whole kernel)
+  int ci0[4], ci1[4];
+  float cw0[4], cw1[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int xb = min(xb0 + cx + q, a.Wb - 1);
+    const Lerp bx = make_lerp(a.s2bx, xb, a.W2, false);
+    ci0[q] = bx.i0 - x2lo; ci1[q] = bx.i1 - x2lo; cw0[q] = bx.w0; cw1[q] = bx.w1;
+  }
+  const bool col_ok = xb0 + cx < a.Wb;
+  const bool vec4 = ((a.Wb & 3) == 0);
+
+  for (int nc = blockIdx.z; nc < a.N * nch; nc += gridDim.z) {
+    const int n = nc / nch, c = nc - n * nch;
+    const bool is_det = c < a.J;
+    const float *q0, *q1 = nullptr, *q0f = nullptr, *q1f = nullptr;
+    if (is_det) {
+      q0 = a.y0 + ((size_t)n * C0 + c) * p4;
+      q1 = a.y1 + ((size_t)n * a.J + c) * p2;
+      if (flip) {
+        const int cf = a.flip_index[c];
+        q0f = a.y0f + ((size_t)n * C0 + cf) * p4;
+        q1f = a.y1f + ((size_t)n * a.J + cf) * p2;
+      }
+    } else {
+      const int t = c - a.J;
+      q0 = a.y0 + ((size_t)n * C0 + a.J + t) * p4;
+      if (flip) {
+        const int tf = (a.A == a.J) ? a.flip_index[t] : t;
+        q0f = a.y0f + ((size_t)n * C0 + a.J + tf) * p4;
+      }
+    }
+    __syncthreads();                                        // previous channel's readers are done
+    for (int i = tid; i < PH * PW; i += AG_THREADS) {
+      const int r = i / PW, s_ = i - r * PW;
+      G[0][i] = g_value(a, q0, q1, y2lo + r, x2lo + s_, false);
+      if (flip) G[1][i] = g_value(a, q0f, q1f, y2lo + r, x2lo + s_, true);
+    }
+    __syncthreads();
+    if (!col_ok) continue;
+    for (int yb = yb0 + ry; yb <= yb1; yb += AG_THREADS / 32) {
+      const Lerp by = make_lerp(a.s2by, yb, a.H2, false);
+      const float* g0 = &G[0][(by.i0 - y2lo) * PW];
+      const float* g1 = &G[0][(by.i1 - y2lo) * PW];
+      float h[4], hf[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        h[q] = by.w0 * (cw0[q] * g0[ci0[q]] + cw1[q] * g0[ci1[q]]) +
+               by.w1 * (cw0[q] * g1[ci0[q]] + cw1[q] * g1[ci1[q]]);
+        hf[q] = 0.0f;
+      }
+      if (flip) {
+        const float* f0 = g0 + AG_MAXP;
+        const float* f1 = g1 + AG_MAXP;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          hf[q] = by.w0 * (cw0[q] * f0[ci0[q]] + cw1[q] * f0[ci1[q]]) +
+                  by.w1 * (cw0[q] * f1[ci0[q]] + cw1[q] * f1[ci1[q]]);
+      }
+      const int xb = xb0 + cx;
+      if (is_det) {
+        float* d = a.det + ((size_t)n * a.J + c) * pb + (size_t)yb * a.Wb + xb;
+        float o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v = flip ? (h[q] + hf[q]) * 0.5f : h[q];
+          if (a.accumulate && xb + q < a.Wb) v = d[q] + v;
+          if (a.final_div != 0.0f) v = __fdiv_rn(v, a.final_div);
+          o[q] = v;
+        }
+        if (vec4) {
+          *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (xb + q < a.Wb) d[q] = o[q];
+        }
+      } else {
+        const int t = c - a.J;
+        float* o = a.tag + (((size_t)n * a.A + t) * pb + (size_t)yb * a.Wb + xb) * T;
+        if (flip) {
+          if (vec4) {
+            reinterpret_cast<float4*>(o)[0] = make_float4(h[0], hf[0], h[1], hf[1]);
+            reinterpret_cast<float4*>(o)[1] = make_float4(h[2], hf[2], h[3], hf[3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (xb + q < a.Wb) *reinterpret_cast<float2*>(o + 2 * q) = make_float2(h[q], hf[q]);
+          }
+        } else {
+          if (vec4) {
+            *reinterpret_cast<float4*>(o) = make_float4(h[0], h[1], h[2], h[3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (xb + q < a.Wb) o[q] = h[q];
+          }
+        }
+      }
+    }
+  }
+}
+
+// worst-case G patch of a tile, computed with the kernel's own float formulas
+static bool agg_tiled_fits(int H2, int W2, int Hb, int Wb) {
+  auto span = [](int in, int out, int tile) {
+    const float sc = resize_scale(in, out, false);
+    int worst = 0;
+    for (int t0 = 0; t0 < out; t0 += tile) {
+      const int t1 = (t0 + tile < out ? t0 + tile : out) - 1;
+      auto idx0 = [&](int dst) {
+        float s = sc * ((float)dst + 0.5f) - 0.5f;
+        if (s < 0.0f) s = 0.0f;
+        int i0 = (int)s;
+        if (i0 > in - 1) i0 = in - 1;
+        return i0;
+      };
+      const int lo = idx0(t0);
+      int hi = idx0(t1);
+      hi = hi + ((hi < in - 1) ? 1 : 0);
+      if (hi - lo + 1 > worst) worst = hi - lo + 1;
+    }
+    return worst;
+  };
+  return (long)span(H2, Hb, AG_TH) * span(W2, Wb, AG_TW) <= AG_MAXP;
+}
+
 __global__ void __launch_bounds__(256) aggregate_scale_kernel(AggArgs a) {
   const int xb = blockIdx.x * blockDim.x + threadIdx.x;
   const int yb = blockIdx.y;
@@ -194,8 +352,15 @@ extern "C" int brtpe_aggregate_scale(const float* y0, const float* y1, const flo
     BRTPE_CHECK_ARG(a.flip_index[i] >= 0 && a.flip_index[i] < J,
                     "brtpe_aggregate_scale: flip_index[%d] out of range", i);
   const int nch = N * (J + (tag_out ? A : 0));
-  dim3 grid(ceil_div(Wb, 256), Hb, nch < 32 ? nch : 32);
-  aggregate_scale_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(det) & 15) == 0) &&
+                       (!tag_out || (reinterpret_cast<uintptr_t>(tag_out) & 15) == 0);
+  if (aligned && agg_tiled_fits(H2, W2, Hb, Wb) && ceil_div(Hb, AG_TH) <= 65535) {
+    dim3 grid(ceil_div(Wb, AG_TW), ceil_div(Hb, AG_TH), nch < 65535 ? nch : 65535);
+    aggregate_scale_tiled_kernel<<<grid, AG_THREADS, 0, (cudaStream_t)stream>>>(a);
+  } else {
+    dim3 grid(ceil_div(Wb, 256), Hb, nch < 32 ? nch : 32);
+    aggregate_scale_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  }
   BRTPE_LAUNCH_CHECK();
   return BRTPE_OK;
 }

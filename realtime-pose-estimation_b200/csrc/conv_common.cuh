@@ -27,6 +27,8 @@ int halo_conv_launch(const HaloConvPrepared* p, const float* bias, const void* r
 
 int stem_conv1_launch(const void* img, int img_is_half, int N, int H, int W, const float* w,
                       const float* bias, int Cout, void* out, int out_dtype, cudaStream_t st);
+int stem_im2col_launch(const void* img, int img_is_half, int N, int H, int W, void* out,
+                       cudaStream_t st);
 int fuse_sum_launch(int dtype, int nterms, const void* const* terms, const int32_t* shifts,
                     const int32_t* term_ld, int N, int H, int W, int C, void* out, int out_ld,
                     int relu, cudaStream_t st);

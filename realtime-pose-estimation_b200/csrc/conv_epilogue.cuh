@@ -1,16 +1,23 @@
 // Shared epilogue of the tcgen05 convolution kernels: TMEM accumulator -> + folded-BN bias ->
 // + residual -> ReLU -> bf16 -> global (NHWC).  One thread owns one output pixel (one TMEM
-// lane) and walks the Cout tile in chunks of 16 columns = 32 bytes = one DRAM sector, moved
-// with single 256-bit LDG/STG when the tensors allow it.  Everything is statically indexed
-// (no local-memory arrays); the residual of the first EPI_PRE chunks is fetched BEFORE the
-// thread waits for the accumulator so that its latency hides behind the MMAs.
+// lane) and walks the Cout tile in chunks of 16 columns = 32 bytes = one DRAM sector.
+//
+// Two paths:
+//  * epi_fast<RES, RELU>: every chunk is 16 real channels, 32-byte aligned in out and res
+//    (all BasicBlock / Bottleneck / transition / fuse convs of the W48 network).  Two chunks
+//    per tcgen05.ld (x32), 256-bit LDG/STG, packed f32x2 adds, ReLU folded into the bf16x2
+//    conversion; the residual of the NEXT chunk pair is in flight while the current one is
+//    processed, and the first pair is fetched before the thread waits for the accumulator.
+//    ~50 instructions per 16 channels.
+//  * epi_drain: general path (ragged channel counts, unaligned tensors: the 34/17-channel
+//    heads and the concat writer).
 #pragma once
 #include "conv_common.cuh"
 #include "umma_ptx.cuh"
 
 namespace brtpe {
 
-constexpr int EPI_PRE = 6;        // chunks (x16 channels) of residual prefetched per tile
+constexpr int EPI_PRE = 6;        // chunks (x16 channels) of residual prefetched per tile (general path)
 constexpr int EPI_MAX_CHUNKS = 16;
 
 struct EpiParams {
@@ -18,7 +25,22 @@ struct EpiParams {
   const __nv_bfloat16* res;
   int out_ld, out_coff, res_ld, res_coff, Cout, Cout_store, relu;
   int vec32;                      // 1: every 16-channel chunk is 32-byte aligned in out and res
+  int fast;                       // 1: vec32 and Cout == Cout_store is a multiple of 16
 };
+
+// q = x / d for 0 <= x < 2^32 / d  (mul = floor(2^32 / d) + 1; mul == 0 selects plain division)
+struct FastDiv {
+  uint32_t mul, d;
+};
+static inline FastDiv make_fastdiv(uint32_t d, uint64_t max_x) {
+  FastDiv f;
+  f.d = d;
+  f.mul = (d > 1 && max_x * (uint64_t)d < (1ull << 32)) ? (uint32_t)((1ull << 32) / d) + 1u : 0u;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t x, const FastDiv& f) {
+  return f.mul ? __umulhi(x, f.mul) : (f.d == 1 ? x : x / f.d);
+}
 
 struct Chunk32 {
   uint32_t w[8];
@@ -56,6 +78,119 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// (lo, hi) -> bf16x2 with round-to-nearest-even, optionally max(.,0) first (one F2FP)
+template <bool RELU>
+__device__ __forceinline__ uint32_t pack_bf16x2_act(float lo, float hi) {
+  uint32_t r;
+  if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// (x0, x1) += (y0, y1) as one packed fp32 add (sm_100 FADD2): same rounding as two FADDs
+__device__ __forceinline__ void add2(float& x0, float& x1, float y0, float y1) {
+  asm("{\n\t.reg .b64 a, b;\n\t"
+      "mov.b64 a, {%0, %1};\n\t"
+      "mov.b64 b, {%2, %3};\n\t"
+      "add.rn.f32x2 a, a, b;\n\t"
+      "mov.b64 {%0, %1}, a;\n\t}"
+      : "+f"(x0), "+f"(x1)
+      : "f"(y0), "f"(y1));
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_lo(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// one 16-channel chunk: acc (16 raw fp32 words at a[OFF..OFF+15]) + bias + residual -> out
+template <bool RES, bool RELU, int OFF>
+__device__ __forceinline__ void epi_fast_chunk(const uint32_t (&a)[32], uint32_t bias16_smem,
+                                               const Chunk32& rc, __nv_bfloat16* op) {
+  Chunk32 oc;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float4 b;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "r"(bias16_smem + 16u * q));
+    float v0 = __uint_as_float(a[OFF + 4 * q]), v1 = __uint_as_float(a[OFF + 4 * q + 1]);
+    float v2 = __uint_as_float(a[OFF + 4 * q + 2]), v3 = __uint_as_float(a[OFF + 4 * q + 3]);
+    add2(v0, v1, b.x, b.y);
+    add2(v2, v3, b.z, b.w);
+    if (RES) {
+      add2(v0, v1, bf16lo(rc.w[2 * q]), bf16hi(rc.w[2 * q]));
+      add2(v2, v3, bf16lo(rc.w[2 * q + 1]), bf16hi(rc.w[2 * q + 1]));
+    }
+    oc.w[2 * q] = pack_bf16x2_act<RELU>(v0, v1);
+    oc.w[2 * q + 1] = pack_bf16x2_act<RELU>(v2, v3);
+  }
+  st_chunk32(op, oc, true);
+}
+
+// Waits for the accumulator (tfull_bar / parity), drains it and arrives on `arrive_bar`
+// (tmem_empty, one lane per warp) as soon as the last TMEM read of the tile has completed.
+template <bool RES, bool RELU>
+__device__ __forceinline__ void epi_fast(const EpiParams& e, const float* __restrict__ bias_s,
+                                         uint32_t t_addr, int nchunks, int co0, bool valid,
+                                         size_t opix, uint32_t tfull_bar, uint32_t tfull_parity,
+                                         uint32_t arrive_bar, int lane) {
+  const __nv_bfloat16* rp = RES ? e.res + opix * e.res_ld + e.res_coff + co0 : nullptr;
+  __nv_bfloat16* op = e.out + opix * e.out_ld + e.out_coff + co0;
+  const uint32_t bias_u32 = smem_u32(bias_s);
+  Chunk32 r0, r1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r0.w[i] = r1.w[i] = 0u;
+  if (RES && valid) {
+    r0 = ld_chunk32(rp, true);
+    if (nchunks > 1) r1 = ld_chunk32(rp + 16, true);
+  }
+  mbar_wait(tfull_bar, tfull_parity);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < nchunks; c += 2) {
+    const bool two = c + 1 < nchunks;
+    uint32_t a[32];
+    if (two) tmem_ld32(t_addr + (uint32_t)(c * 16), a);
+    else tmem_ld16_lo(t_addr + (uint32_t)(c * 16), a);
+    Chunk32 n0 = r0, n1 = r1;
+    if (RES && valid) {
+      if (c + 2 < nchunks) n0 = ld_chunk32(rp + (c + 2) * 16, true);
+      if (c + 3 < nchunks) n1 = ld_chunk32(rp + (c + 3) * 16, true);
+    }
+    tmem_ld_wait();
+    if (c + 2 >= nchunks) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(arrive_bar);
+    }
+    if (valid) {
+      const uint32_t bs = bias_u32 + (uint32_t)((co0 + c * 16) * 4);
+      epi_fast_chunk<RES, RELU, 0>(a, bs, r0, op + c * 16);
+      if (two) epi_fast_chunk<RES, RELU, 16>(a, bs + 64u, r1, op + c * 16 + 16);
+    }
+    r0 = n0;
+    r1 = n1;
+  }
+}
 
 struct ResPrefetch {
   Chunk32 c[EPI_PRE];
@@ -72,27 +207,25 @@ __device__ __forceinline__ void epi_prefetch(ResPrefetch& rp, const EpiParams& e
   }
 }
 
-// Drains one accumulator tile.  `arrive_bar`: tmem_empty barrier, arrived on (one lane per
-// warp) as soon as the last TMEM read of this tile has completed.
-__device__ __forceinline__ void epi_drain(const EpiParams& e, const float* __restrict__ bias_s,
-                                          const ResPrefetch& rp, uint32_t t_addr, int nchunks,
-                                          int co0, bool valid, size_t opix, uint32_t arrive_bar,
-                                          int lane) {
+// General path.  Drains one accumulator tile.  `arrive_bar`: tmem_empty barrier, arrived on
+// (one lane per warp) as soon as the last TMEM read of this tile has completed.
+static __device__ __noinline__ void epi_drain(const EpiParams& e, const float* __restrict__ bias_s,
+                                       uint32_t t_addr, int nchunks, int co0, bool valid,
+                                       size_t opix, uint32_t tfull_bar, uint32_t tfull_parity,
+                                       uint32_t arrive_bar, int lane) {
   const bool vec32 = e.vec32 != 0;
-#pragma unroll
-  for (int c = 0; c < EPI_MAX_CHUNKS; ++c) {
-    if (c >= nchunks) break;
+  mbar_wait(tfull_bar, tfull_parity);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
     const int co = co0 + c * 16;
     const bool live = valid && co < e.Cout_store;
     const bool whole = co + 16 <= e.Cout;            // chunk entirely made of real channels
     Chunk32 rc;
 #pragma unroll
     for (int i = 0; i < 8; ++i) rc.w[i] = 0u;
-    if (c < EPI_PRE) {
-      rc = rp.c[c < EPI_PRE ? c : 0];
-    } else if (e.res != nullptr && live && whole) {
+    if (e.res != nullptr && live && whole)
       rc = ld_chunk32(e.res + opix * e.res_ld + e.res_coff + co, vec32);
-    }
     uint32_t r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11, r12, r13, r14, r15;
     tmem_ld16s(t_addr + (uint32_t)(c * 16), r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11, r12,
                r13, r14, r15);
@@ -144,10 +277,31 @@ __device__ __forceinline__ void epi_drain(const EpiParams& e, const float* __res
   }
 }
 
+// Dispatch (warp-uniform): waits for the accumulator and drains it.
+__device__ __forceinline__ void epi_tile(const EpiParams& e, const float* __restrict__ bias_s,
+                                         uint32_t t_addr, int nchunks, int co0, bool valid,
+                                         size_t opix, uint32_t tfull_bar, uint32_t tfull_parity,
+                                         uint32_t arrive_bar, int lane) {
+  if (e.fast) {
+    if (e.res != nullptr) {
+      if (e.relu) epi_fast<true, true>(e, bias_s, t_addr, nchunks, co0, valid, opix, tfull_bar, tfull_parity, arrive_bar, lane);
+      else epi_fast<true, false>(e, bias_s, t_addr, nchunks, co0, valid, opix, tfull_bar, tfull_parity, arrive_bar, lane);
+    } else {
+      if (e.relu) epi_fast<false, true>(e, bias_s, t_addr, nchunks, co0, valid, opix, tfull_bar, tfull_parity, arrive_bar, lane);
+      else epi_fast<false, false>(e, bias_s, t_addr, nchunks, co0, valid, opix, tfull_bar, tfull_parity, arrive_bar, lane);
+    }
+  } else {
+    epi_drain(e, bias_s, t_addr, nchunks, co0, valid, opix, tfull_bar, tfull_parity, arrive_bar, lane);
+  }
+}
+
 static inline int epi_vec32_ok(const brtpe_conv_desc* d) {
   const bool out_ok = (d->out_ld % 16 == 0) && (d->out_coff % 16 == 0);
   const bool res_ok = (d->res_ld % 16 == 0) && (d->res_coff % 16 == 0);
   return (out_ok && res_ok) ? 1 : 0;
+}
+static inline int epi_fast_ok(const brtpe_conv_desc* d) {
+  return (epi_vec32_ok(d) && d->Cout % 16 == 0 && d->Cout_store == d->Cout) ? 1 : 0;
 }
 
 }  // namespace brtpe

@@ -9,6 +9,8 @@
 // transposed conv), folded-BN bias, optional residual and ReLU in the epilogue.
 #include "conv_common.cuh"
 
+#include <algorithm>
+
 namespace brtpe {
 
 constexpr int FBM = 64, FBN = 64, FBK = 16, FTHREADS = 256;
@@ -188,6 +190,48 @@ stem_conv1_kernel(const TI* __restrict__ img, int N, int H, int W, const float* 
 }
 
 // ------------------------------------------------------------------------------------------
+// stem im2col (bf16 / tcgen05 path of conv1): NCHW image -> NHWC bf16 (N, H/2, W/2, 32) where
+// channel k = (ky*3 + kx)*3 + ci holds the 3x3 / stride-2 / pad-1 window of output pixel
+// (oy, ox) and channels 27..31 are zero; conv1 then is a 1x1 tcgen05 conv with K = 32.
+// One thread per output pixel: 27 strided reads (L1 keeps the 2x overlap), one 64-byte write.
+// ------------------------------------------------------------------------------------------
+template <typename TI>
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const TI* __restrict__ img, int N, int H, int W, __nv_bfloat16* __restrict__ out) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ox >= Wo) return;
+  const int row = blockIdx.y;                 // n * Ho + oy
+  const int n = row / Ho, oy = row - n * Ho;
+  float v[32];
+#pragma unroll
+  for (int k = 27; k < 32; ++k) v[k] = 0.0f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * 2 + ky - 1;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * 2 + kx - 1;
+      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+        v[(ky * 3 + kx) * 3 + ci] = ok ? to_f32(img[(((size_t)n * 3 + ci) * H + iy) * W + ix]) : 0.0f;
+    }
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + ((size_t)row * Wo + ox) * 32);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat162 pk = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+      w[e] = *reinterpret_cast<uint32_t*>(&pk);
+    }
+    o[q] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // cross-resolution fuse: out = relu?( sum_k nearest_up_{2^s_k}(term_k) ), NHWC
 // ------------------------------------------------------------------------------------------
 struct FuseArgs {
@@ -222,6 +266,45 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(FuseArgs a) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) o[e] = from_f32<T>(a.relu ? fmaxf(s[e], 0.0f) : s[e]);
   }
+}
+
+// bf16 fast path: one thread = 8 channels (16 bytes) of one output pixel, one image row per
+// blockIdx.y; the same left-to-right fp32 summation order as the generic kernel.
+__global__ void __launch_bounds__(256) fuse_sum_bf16x8_kernel(FuseArgs a) {
+  const int cv = a.C >> 3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.W * cv) return;
+  const int x = i / cv, c = (i - x * cv) << 3;
+  const int row = blockIdx.y;               // n * H + y
+  const int n = row / a.H, y = row - n * a.H;
+  float s[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < a.nterms) {
+      const int sh = a.shifts[k];
+      const int hk = a.H >> sh, wk = a.W >> sh;
+      const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(a.terms[k]) +
+                               (((size_t)n * hk + (y >> sh)) * wk + (x >> sh)) * a.ld[k] + c;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+        s[2 * e] = (k == 0) ? lo : s[2 * e] + lo;
+        s[2 * e + 1] = (k == 0) ? hi : s[2 * e + 1] + hi;
+      }
+    }
+  }
+  uint32_t o[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float lo = s[2 * e], hi = s[2 * e + 1];
+    if (a.relu) { lo = fmaxf(lo, 0.0f); hi = fmaxf(hi, 0.0f); }
+    __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+    o[e] = *reinterpret_cast<uint32_t*>(&pk);
+  }
+  __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + ((size_t)row * a.W + x) * a.out_ld + c;
+  *reinterpret_cast<uint4*>(op) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -317,6 +400,38 @@ int stem_conv1_launch(const void* img, int img_is_half, int N, int H, int W, con
   return BRTPE_OK;
 }
 
+int stem_im2col_launch(const void* img, int img_is_half, int N, int H, int W, void* out,
+                       cudaStream_t st) {
+  BRTPE_CHECK_ARG(img && out && N > 0 && H > 0 && W > 0, "stem_im2col: bad arguments");
+  BRTPE_CHECK_ARG((H % 2) == 0 && (W % 2) == 0, "stem_im2col: H and W must be even");
+  BRTPE_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "stem_im2col: out must be 16-byte aligned");
+  const int rows = N * (H / 2);
+  dim3 grid(ceil_div(W / 2, 128), rows);
+  if (rows > 65535) {
+    // blockIdx.y is limited to 65535: split the batch
+    const int per = 65535 / (H / 2);
+    BRTPE_CHECK_ARG(per >= 1, "stem_im2col: image too tall");
+    const size_t isz = img_is_half ? 2 : 4;
+    for (int n0 = 0; n0 < N; n0 += per) {
+      const int nn = std::min(per, N - n0);
+      int rc = stem_im2col_launch(reinterpret_cast<const char*>(img) + (size_t)n0 * 3 * H * W * isz,
+                                  img_is_half, nn, H, W,
+                                  reinterpret_cast<__nv_bfloat16*>(out) + (size_t)n0 * (H / 2) * (W / 2) * 32,
+                                  st);
+      if (rc) return rc;
+    }
+    return BRTPE_OK;
+  }
+  if (img_is_half)
+    stem_im2col_kernel<__half><<<grid, 128, 0, st>>>(reinterpret_cast<const __half*>(img), N, H, W,
+                                                     reinterpret_cast<__nv_bfloat16*>(out));
+  else
+    stem_im2col_kernel<float><<<grid, 128, 0, st>>>(reinterpret_cast<const float*>(img), N, H, W,
+                                                    reinterpret_cast<__nv_bfloat16*>(out));
+  BRTPE_LAUNCH_CHECK();
+  return BRTPE_OK;
+}
+
 int fuse_sum_launch(int dtype, int nterms, const void* const* terms, const int32_t* shifts,
                     const int32_t* term_ld, int N, int H, int W, int C, void* out, int out_ld,
                     int relu, cudaStream_t st) {
@@ -339,8 +454,18 @@ int fuse_sum_launch(int dtype, int nterms, const void* const* terms, const int32
   const size_t total = (size_t)N * H * W * (C / 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
-  if (dtype == BRTPE_DT_F32) fuse_sum_kernel<float><<<blocks, 256, 0, st>>>(a);
-  else fuse_sum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a);
+  bool fast = dtype == BRTPE_DT_BF16 && (C % 8) == 0 && (out_ld % 8) == 0 && (long long)N * H <= 65535 &&
+              (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  for (int k = 0; k < nterms; ++k)
+    fast = fast && (term_ld[k] % 8) == 0 && (reinterpret_cast<uintptr_t>(terms[k]) & 15) == 0;
+  if (fast) {
+    dim3 grid(ceil_div(W * (C / 8), 256), N * H);
+    fuse_sum_bf16x8_kernel<<<grid, 256, 0, st>>>(a);
+  } else if (dtype == BRTPE_DT_F32) {
+    fuse_sum_kernel<float><<<blocks, 256, 0, st>>>(a);
+  } else {
+    fuse_sum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a);
+  }
   BRTPE_LAUNCH_CHECK();
   return BRTPE_OK;
 }

@@ -44,6 +44,7 @@ struct alignas(64) HaloParams {
   int resident;                 // 1: all nine weight taps stay in smem for the whole kernel
   int tmem_cols, acc_cols;
   uint32_t idesc;
+  FastDiv fd_xy, fd_x, fd_nt;
   const float* bias;
   EpiParams epi;
 };
@@ -132,11 +133,14 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
     const int in_coff = p.in_coff;
     bool first = true;
     for (int item = cluster_id; item < num_items; item += num_clusters) {
-      const int nt = item % n_tiles;
-      const int mt = (item / n_tiles) * cs + rank;
-      int n = mt / tiles_xy;
-      const int y0 = ((mt % tiles_xy) / tiles_x) * HL_TH;
-      const int x0 = (mt % tiles_x) * HL_TW;
+      const int mg = (int)fdiv((uint32_t)item, p.fd_nt);
+      const int nt = item - mg * n_tiles;
+      const int mt = mg * cs + rank;
+      int n = (int)fdiv((uint32_t)mt, p.fd_xy);
+      const int rem = mt - n * tiles_xy;
+      const int ty = (int)fdiv((uint32_t)rem, p.fd_x);
+      const int y0 = ty * HL_TH;
+      const int x0 = (rem - ty * tiles_x) * HL_TW;
       if (mt >= m_tiles) n = p.N;                       // fully out of bounds -> zeros
       if (resident && first) {
         // all nine taps of the (single) channel block, once per kernel
@@ -250,24 +254,25 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
     const int th = m >> 3, tw = m & 7;
     const EpiParams e = p.epi;
     const int nchunks = BN >> 4;
+    const int H = p.H, W = p.W, acc_cols = p.acc_cols;
     int it = 0;
     for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
-      const int nt = item % n_tiles;
-      const int mt = (item / n_tiles) * cs + rank;
-      const int n = mt / tiles_xy;
-      const int y = ((mt % tiles_xy) / tiles_x) * HL_TH + th;
-      const int x = (mt % tiles_x) * HL_TW + tw;
-      const bool valid = mt < m_tiles && y < p.H && x < p.W;
-      const size_t opix = valid ? ((size_t)n * p.H + y) * p.W + x : 0;
+      const int mg = (int)fdiv((uint32_t)item, p.fd_nt);
+      const int nt = item - mg * n_tiles;
+      const int mt = mg * cs + rank;
+      const int n = (int)fdiv((uint32_t)mt, p.fd_xy);
+      const int rem = mt - n * tiles_xy;
+      const int ty = (int)fdiv((uint32_t)rem, p.fd_x);
+      const int y = ty * HL_TH + th;
+      const int x = (rem - ty * tiles_x) * HL_TW + tw;
+      const bool valid = mt < m_tiles && y < H && x < W;
+      const size_t opix = valid ? ((size_t)n * H + y) * W + x : 0;
       const int co0 = nt * BN;
-      ResPrefetch rp;
-      epi_prefetch(rp, e, valid, opix, co0, nchunks);
       const int acc = it & 1;
       const uint32_t accph = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(smem_u32(&tfull[acc]), accph);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * p.acc_cols);
-      epi_drain(e, bias_s, rp, t_addr, nchunks, co0, valid, opix, smem_u32(&tempty[acc]), lane);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * acc_cols);
+      epi_tile(e, bias_s, t_addr, nchunks, co0, valid, opix, smem_u32(&tfull[acc]), accph,
+               smem_u32(&tempty[acc]), lane);
     }
   }
 
@@ -384,7 +389,10 @@ HaloConvPrepared* halo_conv_prepare(const brtpe_conv_desc* d, const void* in, co
   p.epi.out = nullptr; p.epi.res = nullptr;
   p.epi.out_ld = d->out_ld; p.epi.out_coff = d->out_coff; p.epi.res_ld = d->res_ld;
   p.epi.res_coff = d->res_coff; p.epi.Cout = d->Cout; p.epi.Cout_store = d->Cout_store;
-  p.epi.relu = d->relu; p.epi.vec32 = epi_vec32_ok(d);
+  p.epi.relu = d->relu; p.epi.vec32 = epi_vec32_ok(d); p.epi.fast = epi_fast_ok(d);
+  p.fd_nt = make_fastdiv((uint32_t)p.n_tiles, (uint64_t)p.num_items + 1);
+  p.fd_xy = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y), (uint64_t)p.m_groups * cs + cs);
+  p.fd_x = make_fastdiv((uint32_t)p.tiles_x, (uint64_t)p.tiles_x * p.tiles_y);
 
   auto encode = halo_encode_fn();
   const cuuint64_t ld_b = (cuuint64_t)d->in_ld * 2;

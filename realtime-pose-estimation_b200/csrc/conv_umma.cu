@@ -46,6 +46,7 @@ struct alignas(64) UmmaParams {
   int tap_c[9], tap_x[9], tap_p[9], tap_y[9];
   int stages, b_stage_bytes, tmem_cols, acc_cols;
   uint32_t idesc;
+  FastDiv fd_nt, fd_xy, fd_x, fd_tw, fd_twh;
   const float* bias;
   int Hout, Wout, out_scale, out_oy, out_ox;
   EpiParams epi;
@@ -114,11 +115,14 @@ conv_umma_kernel(const __grid_constant__ UmmaParams p) {
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile % n_tiles;
-      const int mt = tile / n_tiles;
-      const int x0 = (mt % tiles_x) * TW;
-      const int y0 = ((mt % tiles_xy) / tiles_x) * TH;
-      const int n0 = (mt / tiles_xy) * TN;
+      const int mt = (int)fdiv((uint32_t)tile, p.fd_nt);
+      const int nt = tile - mt * n_tiles;
+      const int tn_ = (int)fdiv((uint32_t)mt, p.fd_xy);
+      const int rem = mt - tn_ * tiles_xy;
+      const int ty_ = (int)fdiv((uint32_t)rem, p.fd_x);
+      const int x0 = (rem - ty_ * tiles_x) * TW;
+      const int y0 = ty_ * TH;
+      const int n0 = tn_ * TN;
 #pragma unroll 1
       for (int tap = 0; tap < ntaps; ++tap) {
         const int tc = p.tap_c[tap], tx = x0 + p.tap_x[tap], tp = p.tap_p[tap], ty = y0 + p.tap_y[tap];
@@ -180,32 +184,34 @@ conv_umma_kernel(const __grid_constant__ UmmaParams p) {
     // ===================== epilogue (4 warps, one TMEM lane quarter each) ===================
     const int lg = warp & 3;
     const int m = lg * 32 + lane;
-    const int tw = m % TW;
-    const int th = (m / TW) % TH;
-    const int tn = m / (TW * TH);
+    const int tn = (int)fdiv((uint32_t)m, p.fd_twh);
+    const int th = (int)fdiv((uint32_t)(m - tn * TW * TH), p.fd_tw);
+    const int tw = m - tn * TW * TH - th * TW;
     const EpiParams e = p.epi;
     const int nchunks = BN >> 4;
+    const int Wm = p.Wm, Hm = p.Hm, N = p.N, Hout = p.Hout, Wout = p.Wout;
+    const int out_scale = p.out_scale, out_oy = p.out_oy, out_ox = p.out_ox, acc_cols = p.acc_cols;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int nt = tile % n_tiles;
-      const int mt = tile / n_tiles;
-      const int xm = (mt % tiles_x) * TW + tw;
-      const int ym = ((mt % tiles_xy) / tiles_x) * TH + th;
-      const int n = (mt / tiles_xy) * TN + tn;
-      const bool valid = (tn < TN) && xm < p.Wm && ym < p.Hm && n < p.N;
+      const int mt = (int)fdiv((uint32_t)tile, p.fd_nt);
+      const int nt = tile - mt * n_tiles;
+      const int tn_ = (int)fdiv((uint32_t)mt, p.fd_xy);
+      const int rem = mt - tn_ * tiles_xy;
+      const int ty_ = (int)fdiv((uint32_t)rem, p.fd_x);
+      const int xm = (rem - ty_ * tiles_x) * TW + tw;
+      const int ym = ty_ * TH + th;
+      const int n = tn_ * TN + tn;
+      const bool valid = (tn < TN) && xm < Wm && ym < Hm && n < N;
       const size_t opix =
-          valid ? ((size_t)n * p.Hout + (size_t)(ym * p.out_scale + p.out_oy)) * p.Wout +
-                      (size_t)(xm * p.out_scale + p.out_ox)
+          valid ? ((size_t)n * Hout + (size_t)(ym * out_scale + out_oy)) * Wout +
+                      (size_t)(xm * out_scale + out_ox)
                 : 0;
       const int co0 = nt * BN;
-      ResPrefetch rp;
-      epi_prefetch(rp, e, valid, opix, co0, nchunks);
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(smem_u32(&tfull_bar[as]), aphase);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * p.acc_cols);
-      epi_drain(e, bias_s, rp, t_addr, nchunks, co0, valid, opix, smem_u32(&tempty_bar[as]), lane);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * acc_cols);
+      epi_tile(e, bias_s, t_addr, nchunks, co0, valid, opix, smem_u32(&tfull_bar[as]), aphase,
+               smem_u32(&tempty_bar[as]), lane);
     }
   }
 
@@ -336,7 +342,12 @@ UmmaConvPrepared* umma_conv_prepare(const brtpe_conv_desc* d, const void* in, co
   p.epi.out = nullptr; p.epi.res = nullptr;
   p.epi.out_ld = d->out_ld; p.epi.out_coff = d->out_coff; p.epi.res_ld = d->res_ld;
   p.epi.res_coff = d->res_coff; p.epi.Cout = d->Cout; p.epi.Cout_store = d->Cout_store;
-  p.epi.relu = d->relu; p.epi.vec32 = epi_vec32_ok(d);
+  p.epi.relu = d->relu; p.epi.vec32 = epi_vec32_ok(d); p.epi.fast = epi_fast_ok(d);
+  p.fd_nt = make_fastdiv((uint32_t)p.n_tiles, (uint64_t)p.total_tiles + 1);
+  p.fd_xy = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y), (uint64_t)p.total_tiles + 1);
+  p.fd_x = make_fastdiv((uint32_t)p.tiles_x, (uint64_t)p.tiles_x * p.tiles_y);
+  p.fd_tw = make_fastdiv((uint32_t)p.TW, 128);
+  p.fd_twh = make_fastdiv((uint32_t)(p.TW * p.TH), 128);
 
   // ---- tensor maps
   auto encode = get_encode_fn();

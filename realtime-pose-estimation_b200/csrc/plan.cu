@@ -3,11 +3,13 @@
 // a fixed (batch chunk, H, W); the host (Python) records it once and replays it per chunk.
 #include "conv_common.cuh"
 
+#include <algorithm>
 #include <vector>
 
 namespace brtpe {
 
-enum OpKind { OP_CONV = 0, OP_STEM = 1, OP_FUSE = 2, OP_TONCHW = 3 };
+enum OpKind { OP_CONV = 0, OP_STEM = 1, OP_FUSE = 2, OP_TONCHW = 3, OP_IM2COL = 4 };
+constexpr int PLAN_MAX_LANES = 8;
 
 struct Op {
   int kind;
@@ -25,6 +27,9 @@ struct Op {
   const void* terms[4];
   int shifts[4], lds[4];
   const float* stem_w;
+  // scheduling: capture stream index + ops (indices) that must have completed before this one
+  int lane;
+  std::vector<int> deps;
 };
 
 static int choose_engine(const brtpe_conv_desc* d) {
@@ -65,6 +70,8 @@ static int run_op(const Op& op, cudaStream_t st) {
     case OP_TONCHW:
       return nhwc_to_nchw_launch(op.i[0], op.in, op.i[1], op.i[2], op.i[3], op.i[4], op.i[5],
                                  op.i[6], op.out, op.i[7], st);
+    case OP_IM2COL:
+      return stem_im2col_launch(op.in, op.i[0], op.i[1], op.i[2], op.i[3], op.out, st);
   }
   return BRTPE_EINVAL;
 }
@@ -77,9 +84,10 @@ struct brtpe_plan {
   std::vector<Op> ops;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
-  cudaStream_t capture_stream = nullptr;
+  cudaStream_t lanes[PLAN_MAX_LANES] = {nullptr};
   ~brtpe_plan() {
-    if (capture_stream) cudaStreamDestroy(capture_stream);
+    for (auto& l : lanes)
+      if (l) cudaStreamDestroy(l);
     for (auto& op : ops) {
       if (op.umma) umma_conv_release(op.umma);
       if (op.halo) halo_conv_release(op.halo);
@@ -212,6 +220,40 @@ extern "C" int brtpe_plan_add_nhwc_to_nchw(brtpe_plan* pl, int dtype, const void
   return BRTPE_OK;
 }
 
+extern "C" int brtpe_plan_add_stem_im2col(brtpe_plan* pl, const void* img, int img_is_half, int N,
+                                          int H, int W, void* out) {
+  BRTPE_CHECK_ARG(pl && img && out, "brtpe_plan_add_stem_im2col: null argument");
+  Op op{};
+  op.kind = OP_IM2COL;
+  op.in = img; op.out = out;
+  op.i[0] = img_is_half; op.i[1] = N; op.i[2] = H; op.i[3] = W;
+  pl->ops.push_back(op);
+  return BRTPE_OK;
+}
+
+extern "C" int brtpe_plan_set_sched(brtpe_plan* pl, int lane, const int32_t* deps, int ndeps) {
+  BRTPE_CHECK_ARG(pl && !pl->ops.empty(), "brtpe_plan_set_sched: no op to annotate");
+  BRTPE_CHECK_ARG(lane >= 0 && lane < PLAN_MAX_LANES, "brtpe_plan_set_sched: lane %d outside [0,%d)",
+                  lane, PLAN_MAX_LANES);
+  BRTPE_CHECK_ARG(ndeps == 0 || deps, "brtpe_plan_set_sched: null deps");
+  BRTPE_CHECK_ARG(!pl->exec, "brtpe_plan_set_sched: plan already captured");
+  Op& op = pl->ops.back();
+  const int self = (int)pl->ops.size() - 1;
+  op.lane = lane;
+  op.deps.clear();
+  for (int k = 0; k < ndeps; ++k) {
+    BRTPE_CHECK_ARG(deps[k] >= 0 && deps[k] < self, "brtpe_plan_set_sched: dependency %d of op %d is not an earlier op",
+                    deps[k], self);
+    op.deps.push_back(deps[k]);
+  }
+  return BRTPE_OK;
+}
+
+extern "C" int brtpe_stem_im2col(const void* img, int img_is_half, int N, int H, int W, void* out,
+                                 void* stream) {
+  return stem_im2col_launch(img, img_is_half, N, H, W, out, (cudaStream_t)stream);
+}
+
 extern "C" int brtpe_plan_num_ops(const brtpe_plan* pl) { return pl ? (int)pl->ops.size() : 0; }
 
 extern "C" double brtpe_plan_conv_flops(const brtpe_plan* pl) {
@@ -231,35 +273,98 @@ extern "C" int brtpe_plan_run(brtpe_plan* pl, void* stream) {
   return BRTPE_OK;
 }
 
+// Captures the op list into a CUDA graph.  Ops are issued in recording order, each on the
+// capture stream of its lane; an op that depends on an op of another lane waits on an event
+// recorded right after that op, so independent lanes (the HRNet branches) become parallel
+// branches of the graph.  Lane 0 is the origin of the capture; every other lane forks from
+// it at its first op and joins it again at the end.
+static int capture_graph(brtpe_plan* pl) {
+  const int n = (int)pl->ops.size();
+  int nl = 1;
+  for (auto& op : pl->ops) nl = std::max(nl, op.lane + 1);
+  for (int l = 0; l < nl; ++l)
+    if (!pl->lanes[l]) BRTPE_CUDA(cudaStreamCreateWithFlags(&pl->lanes[l], cudaStreamNonBlocking));
+  std::vector<char> need_event(n, 0);
+  for (int i = 0; i < n; ++i)
+    for (int d : pl->ops[i].deps)
+      if (d >= 0 && d < i && pl->ops[d].lane != pl->ops[i].lane) need_event[d] = 1;
+  std::vector<cudaEvent_t> ev(n, nullptr);
+  std::vector<cudaEvent_t> extra;
+  auto new_event = [&](cudaEvent_t* e) {
+    cudaError_t r = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+    if (r == cudaSuccess) extra.push_back(*e);
+    return r;
+  };
+  int rc = BRTPE_OK;
+  cudaError_t ce = cudaStreamBeginCapture(pl->lanes[0], cudaStreamCaptureModeThreadLocal);
+  if (ce != cudaSuccess) {
+    set_error("cudaStreamBeginCapture failed: %s", cudaGetErrorString(ce));
+    return BRTPE_ECUDA;
+  }
+  std::vector<char> joined(nl, 0);
+  joined[0] = 1;
+  cudaEvent_t fork = nullptr;
+  for (int i = 0; i < n && !rc; ++i) {
+    const Op& op = pl->ops[i];
+    cudaStream_t st = pl->lanes[op.lane];
+    bool waited = false;
+    for (int d : op.deps) {
+      if (d < 0 || d >= i || pl->ops[d].lane == op.lane) continue;
+      if (cudaStreamWaitEvent(st, ev[d], 0) != cudaSuccess) rc = BRTPE_ECUDA;
+      waited = true;
+    }
+    if (!joined[op.lane]) {
+      if (!waited) {   // no cross-lane dependency yet: fork from the start of the capture
+        if (!fork) {
+          // an event recorded on lane 0 before anything else would be ideal; recording it
+          // now (after earlier lane-0 ops) is still correct, only less parallel
+          if (new_event(&fork) != cudaSuccess || cudaEventRecord(fork, pl->lanes[0]) != cudaSuccess)
+            rc = BRTPE_ECUDA;
+        }
+        if (!rc && cudaStreamWaitEvent(st, fork, 0) != cudaSuccess) rc = BRTPE_ECUDA;
+      }
+      joined[op.lane] = 1;
+    }
+    if (rc) break;
+    rc = run_op(op, st);
+    if (!rc && need_event[i]) {
+      if (new_event(&ev[i]) != cudaSuccess || cudaEventRecord(ev[i], st) != cudaSuccess) rc = BRTPE_ECUDA;
+    }
+  }
+  for (int l = 1; l < nl && !rc; ++l) {
+    if (!joined[l]) continue;
+    cudaEvent_t e;
+    if (new_event(&e) != cudaSuccess || cudaEventRecord(e, pl->lanes[l]) != cudaSuccess ||
+        cudaStreamWaitEvent(pl->lanes[0], e, 0) != cudaSuccess)
+      rc = BRTPE_ECUDA;
+  }
+  cudaGraph_t g = nullptr;
+  ce = cudaStreamEndCapture(pl->lanes[0], &g);
+  for (auto e : extra) cudaEventDestroy(e);
+  if (rc) {
+    if (g) cudaGraphDestroy(g);
+    if (rc == BRTPE_ECUDA) set_error("plan capture: a CUDA stream/event call failed: %s",
+                                     cudaGetErrorString(cudaGetLastError()));
+    return rc;
+  }
+  if (ce != cudaSuccess) {
+    set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+    return BRTPE_ECUDA;
+  }
+  pl->graph = g;
+  BRTPE_CUDA(cudaGraphInstantiate(&pl->exec, g, 0));
+  return BRTPE_OK;
+}
+
 extern "C" int brtpe_plan_graph_launch(brtpe_plan* pl, void* stream) {
   BRTPE_CHECK_ARG(pl, "brtpe_plan_graph_launch: null plan");
-  cudaStream_t st = (cudaStream_t)stream;
   if (!pl->exec) {
-    // capture on a private stream: the caller's stream may be the legacy default stream,
-    // which cannot be captured; the instantiated graph is then launched into `st`.
-    if (!pl->capture_stream)
-      BRTPE_CUDA(cudaStreamCreateWithFlags(&pl->capture_stream, cudaStreamNonBlocking));
-    cudaStream_t cs = pl->capture_stream;
-    BRTPE_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-    int rc = BRTPE_OK;
-    for (auto& op : pl->ops) {
-      rc = run_op(op, cs);
-      if (rc) break;
-    }
-    cudaGraph_t g = nullptr;
-    cudaError_t e = cudaStreamEndCapture(cs, &g);
-    if (rc) {
-      if (g) cudaGraphDestroy(g);
-      return rc;
-    }
-    if (e != cudaSuccess) {
-      set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
-      return BRTPE_ECUDA;
-    }
-    pl->graph = g;
-    BRTPE_CUDA(cudaGraphInstantiate(&pl->exec, g, 0));
+    // captured on private streams: the caller's stream may be the legacy default stream,
+    // which cannot be captured; the instantiated graph is then launched into `stream`.
+    int rc = capture_graph(pl);
+    if (rc) return rc;
   }
-  BRTPE_CUDA(cudaGraphLaunch(pl->exec, st));
+  BRTPE_CUDA(cudaGraphLaunch(pl->exec, (cudaStream_t)stream));
   return BRTPE_OK;
 }
 

@@ -150,7 +150,7 @@ class HighResolutionModule(nn.Module):
 # ---------------------------------------------------------------------------------------
 class _T:
     """virtual NHWC tensor"""
-    __slots__ = ("n", "h", "w", "ld", "first", "last", "buf", "keep")
+    __slots__ = ("n", "h", "w", "ld", "first", "last", "buf", "keep", "lane", "touch", "inherit")
 
     def __init__(self, n, h, w, ld):
         self.n, self.h, self.w, self.ld = n, h, w, ld
@@ -158,6 +158,9 @@ class _T:
         self.last = None
         self.buf = None
         self.keep = False
+        self.lane = 0          # lane of the op that creates it (arena pools are per lane)
+        self.touch = []        # (op index, is_write, phase group) of every op using it
+        self.inherit = []      # ops that used the previous tenants of its arena buffer
 
     def numel(self):
         return self.n * self.h * self.w * self.ld
@@ -176,6 +179,9 @@ class _Recorder:
         self.tensors = []
         self.keepalive = []                       # packed weights / biases
         self.in_is_half = in_is_half
+        self.lane = 0                             # lane of the ops being recorded
+        self.op_lane = []                         # per op: lane
+        self.op_rw = []                           # per op: (reads, writes, phase group)
 
     # -- tensors
     def new(self, n, h, w, ld):
@@ -186,7 +192,13 @@ class _Recorder:
     def _touch(self, t, idx):
         if t.first is None:
             t.first = idx
+            t.lane = self.lane
         t.last = idx
+
+    def _sched(self, reads, writes, group=None):
+        """Register the op being appended: lane + the tensors it reads / writes."""
+        self.op_lane.append(self.lane)
+        self.op_rw.append(([t for t in reads if t is not None], list(writes), group))
 
     # -- weights
     def _fold(self, conv, bn):
@@ -249,8 +261,9 @@ class _Recorder:
         self._emit_conv(d, x, wt, b, residual, out, cin_store)
         return out
 
-    def deconv4x4s2(self, x, deconv, bn, cin_store):
-        """ConvTranspose2d(k4,s2,p1)+BN+ReLU as four output-parity 2x2 convs."""
+    def deconv4x4s2(self, x, deconv, bn, cin_store, lanes=(0, 1, 2, 3)):
+        """ConvTranspose2d(k4,s2,p1)+BN+ReLU as four output-parity 2x2 convs (independent:
+        they write disjoint pixels of the output, one lane each)."""
         cin, cout = deconv.in_channels, deconv.out_channels
         out = self.new(x.n, 2 * x.h, 2 * x.w, cout)
         w = deconv.weight.detach().to(self.device, torch.float32)          # (Cin,Cout,4,4)
@@ -271,7 +284,10 @@ class _Recorder:
                 wt = torch.stack(mats, 0)
                 d = self._desc(x, 0, cin_store, taps, 1, x.h, x.w, out, 2, a, bb, cout, cout, 0,
                                None, True)
-                self._emit_conv(d, x, wt, b, None, out, cin_store)
+                keep = self.lane
+                self.lane = lanes[(2 * a + bb) % len(lanes)]
+                self._emit_conv(d, x, wt, b, None, out, cin_store, group=("deconv", id(out)))
+                self.lane = keep
         return out
 
     def _desc(self, x, in_coff, cin, taps, stride, hm, wm, out, out_scale, oy, ox, cout,
@@ -294,12 +310,13 @@ class _Recorder:
         d.Cout_store = cout_store
         return d
 
-    def _emit_conv(self, d, x, wt, bias, residual, out, cin_store):
+    def _emit_conv(self, d, x, wt, bias, residual, out, cin_store, group=None):
         packed = self._pack(wt, d, cin_store)
         bias = bias.contiguous()
         self.keepalive += [packed, bias]
         idx = len(self.ops)
         self.ops.append(("conv", d, x, packed, bias, residual, out))
+        self._sched([x, residual], [out], group)
         self._touch(x, idx)
         if residual is not None:
             self._touch(residual, idx)
@@ -312,7 +329,26 @@ class _Recorder:
         self.keepalive += [wp, b]
         idx = len(self.ops)
         self.ops.append(("stem", wp, b.contiguous(), out))
+        self._sched([], [out])
         self._touch(out, idx)
+        return out
+
+    def stem_tc(self, conv, bn):
+        """conv1 + BN + ReLU on the tensor cores: im2col (27 -> 32 channels per output pixel)
+        followed by a 1x1 tcgen05 conv with K = 32."""
+        w, b = self._fold(conv, bn)                                        # (64,3,3,3)
+        cout = w.shape[0]
+        cols = self.new(self.n, self.h // 2, self.w // 2, 32)
+        idx = len(self.ops)
+        self.ops.append(("im2col", cols))
+        self._sched([], [cols])
+        self._touch(cols, idx)
+        wt = w.new_zeros((1, cout, 32))
+        wt[0, :, :27] = w.permute(0, 2, 3, 1).reshape(cout, 27)            # k = (ky, kx, ci)
+        out = self.new(self.n, self.h // 2, self.w // 2, cout)
+        d = self._desc(cols, 0, 32, [(0, 0)], 1, cols.h, cols.w, out, 1, 0, 0, cout, cout, 0,
+                       None, True)
+        self._emit_conv(d, cols, wt, b, None, out, 32)
         return out
 
     def fuse(self, terms, shifts, c, relu, out=None):
@@ -321,6 +357,7 @@ class _Recorder:
             out = self.new(t0.n, t0.h << shifts[0], t0.w << shifts[0], c)
         idx = len(self.ops)
         self.ops.append(("fuse", list(terms), list(shifts), c, relu, out))
+        self._sched(list(terms), [out])
         for t in terms:
             self._touch(t, idx)
         self._touch(out, idx)
@@ -329,36 +366,72 @@ class _Recorder:
     def to_nchw(self, x, c, coff, dst):
         idx = len(self.ops)
         self.ops.append(("nchw", x, c, coff, dst))
+        self._sched([x], [])
         self._touch(x, idx)
 
     # -- arena + native plan
     def build(self, in_buf):
         lib = L.load(require_cuda=False)
         esize = 4 if self.mode == "fp32" else 2
-        free = []                                  # (bytes, tensor) of released buffers
+        # Liveness-packed arena.  Released buffers go back to the pool of the lane that
+        # created them and are only re-used by that lane, so arena re-use does not serialise
+        # independent lanes; the ops that used the previous tenants are still recorded as
+        # dependencies of the new tenant's first writer (`inherit`).
+        free = {}                                  # lane -> [(bytes, storage, users)]
         release_at = {}
         for t in self.tensors:
             if t.first is not None and not t.keep:
                 release_at.setdefault(t.last, []).append(t)
+        first_at = {}
+        for t in self.tensors:
+            if t.first is not None:
+                first_at.setdefault(t.first, []).append(t)
         total = 0
         for idx, op in enumerate(self.ops):
-            for t in self.tensors:
-                if t.first == idx and t.buf is None:
-                    need = t.numel() * esize
-                    best = None
-                    for k, (nb, buf) in enumerate(free):
-                        if nb >= need and (best is None or nb < free[best][0]):
-                            best = k
-                    if best is not None:
-                        nb, buf = free.pop(best)
-                    else:
-                        nb = (need + 255) // 256 * 256
-                        buf = torch.zeros(nb, dtype=torch.uint8, device=self.device)
-                        total += nb
-                    t.buf = (nb, buf)
+            for t in first_at.get(idx, []):
+                if t.buf is not None:
+                    continue
+                need = t.numel() * esize
+                pool = free.setdefault(t.lane, [])
+                best = None
+                for k, (nb, buf, users) in enumerate(pool):
+                    if nb >= need and (best is None or nb < pool[best][0]):
+                        best = k
+                if best is not None:
+                    nb, buf, users = pool.pop(best)
+                    t.inherit = list(users)
+                else:
+                    nb = (need + 255) // 256 * 256
+                    buf = torch.zeros(nb, dtype=torch.uint8, device=self.device)
+                    total += nb
+                    t.inherit = []
+                t.buf = (nb, buf)
+            reads, writes, group = self.op_rw[idx]
+            for t in reads:
+                t.touch.append((idx, False, group))
+            for t in writes:
+                t.touch.append((idx, True, group))
             for t in release_at.get(idx, []):
-                free.append(t.buf)
+                users = sorted(set(t.inherit) | set(i for i, _, _ in t.touch))
+                free.setdefault(t.lane, []).append((t.buf[0], t.buf[1], users))
         self.arena_bytes = total
+
+        # dependencies: RAW on every earlier writer, WAR/WAW on every earlier user (ops of one
+        # phase group write disjoint parts of a tensor and do not order each other), plus the
+        # users of the arena buffer's previous tenants
+        self.deps = []
+        for idx in range(len(self.ops)):
+            reads, writes, group = self.op_rw[idx]
+            dep = set()
+            for t in reads:
+                dep.update(i for i, wr, _ in t.touch if wr and i < idx)
+                dep.update(i for i in t.inherit if i < idx)
+            for t in writes:
+                dep.update(i for i, _, g in t.touch
+                           if i < idx and not (group is not None and g == group))
+                dep.update(i for i in t.inherit if i < idx)
+            lane = self.op_lane[idx]
+            self.deps.append(sorted(i for i in dep if self.op_lane[i] != lane))
 
         plan = lib.brtpe_plan_create()
         try:
@@ -391,6 +464,16 @@ class _Recorder:
                         plan, self.dt, L.ptr(x.buf[1]), x.n, x.h, x.w, c, x.ld, coff,
                         L.ptr(dst), int(dst.dtype == torch.float16)),
                         "brtpe_plan_add_nhwc_to_nchw")
+                elif kind == "im2col":
+                    _, cols = op
+                    L.check(lib.brtpe_plan_add_stem_im2col(
+                        plan, L.ptr(in_buf), int(self.in_is_half), self.n, self.h, self.w,
+                        L.ptr(cols.buf[1])), "brtpe_plan_add_stem_im2col")
+                k = lib.brtpe_plan_num_ops(plan) - 1
+                deps = self.deps[k]
+                arr = (C.c_int32 * max(len(deps), 1))(*deps)
+                L.check(lib.brtpe_plan_set_sched(plan, self.op_lane[k], arr, len(deps)),
+                        "brtpe_plan_set_sched")
         except Exception:
             lib.brtpe_plan_destroy(plan)
             raise
@@ -511,6 +594,7 @@ class PoseHigherResolutionNet(nn.Module):
         self.chunk_size = 8            # images per plan replay (keeps a layer's in+out in L2)
         self.conv_engine = L.ENGINE_AUTO
         self.use_cuda_graph = True
+        self.parallel_branches = True  # resolution branches = parallel branches of the CUDA graph
         self._plans = {}
         self._sig = None
         self._frozen = False
@@ -595,7 +679,11 @@ class PoseHigherResolutionNet(nn.Module):
     # ---------------------------------------------------------------- plan
     def _record(self, n, h, w, mode, device, in_is_half, out_half):
         R = _Recorder(self, n, h, w, mode, self.conv_engine, device, in_is_half)
-        x = R.stem(self.conv1, self.bn1)
+        par = self.parallel_branches
+        if mode == "bf16" and self.conv_engine != L.ENGINE_FFMA:
+            x = R.stem_tc(self.conv1, self.bn1)
+        else:
+            x = R.stem(self.conv1, self.bn1)
         x = R.conv(x, self.conv2, self.bn2, True)
         for blk in self.layer1:
             res = x
@@ -615,6 +703,7 @@ class PoseHigherResolutionNet(nn.Module):
             stage = getattr(self, "stage%d" % (si + 1))
             xs = []
             for i, tr in enumerate(trans):
+                R.lane = i if par else 0              # lane = resolution branch
                 if isinstance(tr, NoOpModule):
                     xs.append(ys[i])
                 elif i < len(ys) and not isinstance(tr[0], nn.Sequential):
@@ -625,34 +714,48 @@ class PoseHigherResolutionNet(nn.Module):
                         t = R.conv(t, sub[0], sub[1], True)
                     xs.append(t)
             for mi, mod in enumerate(stage):
-                for i in range(mod.num_branches):
-                    for blk in mod.branches[i]:
+                # interleave the branches block by block: the recording order is also the
+                # issue order of the capture, so independent launches sit next to each other
+                nblk = max(len(b) for b in mod.branches)
+                for bi in range(nblk):
+                    for i in range(mod.num_branches):
+                        if bi >= len(mod.branches[i]):
+                            continue
+                        R.lane = i if par else 0
+                        blk = mod.branches[i][bi]
                         t = R.conv(xs[i], blk.conv1, blk.bn1, True)
                         xs[i] = R.conv(t, blk.conv2, blk.bn2, True, residual=xs[i])
                 outs = []
                 final_module = si == 3 and mi == len(stage) - 1
-                for i in range(len(mod.fuse_layers)):
-                    terms, shifts = [], []
-                    for j in range(mod.num_branches):
+                nout = len(mod.fuse_layers)
+                terms_of = [[None] * mod.num_branches for _ in range(nout)]
+                shifts_of = [[0] * mod.num_branches for _ in range(nout)]
+                for j in range(mod.num_branches):     # fuse convs run on their source lane
+                    R.lane = j if par else 0
+                    for i in range(nout):
                         f = mod.fuse_layers[i][j]
                         if j == i:
-                            terms.append(xs[j]); shifts.append(0)
+                            terms_of[i][j] = xs[j]
                         elif j > i:
-                            terms.append(R.conv(xs[j], f[0], f[1], False)); shifts.append(j - i)
+                            terms_of[i][j] = R.conv(xs[j], f[0], f[1], False)
+                            shifts_of[i][j] = j - i
                         else:
                             t = xs[j]
                             for k, sub in enumerate(f):
                                 t = R.conv(t, sub[0], sub[1], k != len(f) - 1)
-                            terms.append(t); shifts.append(0)
+                            terms_of[i][j] = t
+                for i in range(nout):
+                    R.lane = i if par else 0
                     c = mod.num_inchannels[i]
                     dst = None
                     if final_module and i == 0 and cat:
                         # stage-4 output lands in channels [0, c) of the concat buffer
                         cat_ld = (c + head0.out_channels + 15) // 16 * 16
                         dst = R.new(n, xs[0].h, xs[0].w, cat_ld)
-                    outs.append(R.fuse(terms, shifts, c, True, out=dst))
+                    outs.append(R.fuse(terms_of[i], shifts_of[i], c, True, out=dst))
                 xs = outs
             ys = xs
+        R.lane = 0
 
         x = ys[0]
         c0 = head0.in_channels
@@ -663,13 +766,16 @@ class PoseHigherResolutionNet(nn.Module):
             pad_store = cat_ld - c0
             R.conv(x, head0, None, False, out=x, out_coff=c0, in_coff=0, cin_store=c0,
                    cout_store=pad_store)
+            R.lane = 1 if par else 0
             R.to_nchw(x, head0.out_channels, c0, y0_out)
+            R.lane = 0
         else:
             y = R.conv(x, head0, None, False)
             R.to_nchw(y, head0.out_channels, 0, y0_out)
         for i in range(self.num_deconvs):
             dl = self.deconv_layers[i]
-            x = R.deconv4x4s2(x, dl[0][0], dl[0][1], x.ld if cat else dl[0][0].in_channels)
+            x = R.deconv4x4s2(x, dl[0][0], dl[0][1], x.ld if cat else dl[0][0].in_channels,
+                              lanes=(0, 1, 2, 3) if par else (0,))
             for k in range(1, len(dl)):
                 blk = dl[k][0]
                 t = R.conv(x, blk.conv1, blk.bn1, True)
@@ -682,7 +788,7 @@ class PoseHigherResolutionNet(nn.Module):
         return R, outs
 
     def _get_plan(self, n, h, w, mode, device, in_dtype):
-        key = (n, h, w, mode, str(device), in_dtype, self.conv_engine)
+        key = (n, h, w, mode, str(device), in_dtype, self.conv_engine, self.parallel_branches)
         plan = self._plans.get(key)
         if plan is None:
             in_is_half = in_dtype == torch.float16
