@@ -247,6 +247,13 @@ int brtpe_plan_graph_launch(brtpe_plan*, void* stream);
 int brtpe_plan_profile(brtpe_plan*, void* stream, float* ms_out, int32_t* kinds_out,
                        double* flops_out);
 
+/* ---- debug instrumentation (not part of the reference surface)
+ * While `buf` is non-NULL every conv_halo_kernel launch with <= max_ctas CTAs runs its
+ * instrumented instantiation and writes 16 int64 cycle counters per CTA to
+ * buf[cta*16 + slot] (device memory, caller owned; slots documented in csrc/conv_halo.cu).
+ * Pass NULL to switch it off. */
+int brtpe_debug_halo_prof(void* buf, int max_ctas);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,7 @@ _SIGS = {
     "brtpe_plan_conv_flops": (C.c_double, [_P]),
     "brtpe_plan_run": (_I, [_P, _P]),
     "brtpe_plan_graph_launch": (_I, [_P, _P]),
+    "brtpe_debug_halo_prof": (_I, [_P, _I]),
     "brtpe_plan_profile": (_I, [_P, _P, C.POINTER(C.c_float), C.POINTER(C.c_int32),
                                 C.POINTER(C.c_double)]),
 }

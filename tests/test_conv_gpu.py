@@ -71,9 +71,26 @@ def test_umma_halo_bf16(cuda_device, shape):
     assert _err(got, ref) <= 6e-3
 
 
-@pytest.mark.parametrize("cs", ["1", "2", "4"])
-def test_umma_halo_cluster_sizes(cuda_device, cs, monkeypatch):
-    monkeypatch.setenv("BRTPE_HALO_CS", cs)
-    for shape in [(2, 32, 32, 96, 96, 3, 1, True, True), (1, 48, 40, 48, 48, 3, 1, True, True)]:
+@pytest.mark.parametrize("knob,value", [("BRTPE_HALO_TPS", "1"), ("BRTPE_HALO_TPS", "3"),
+                                        ("BRTPE_HALO_NT", "2"), ("BRTPE_HALO_NT", "3"),
+                                        ("BRTPE_HALO_NO_RESIDENT", "1")])
+def test_umma_halo_tilings(cuda_device, knob, value, monkeypatch):
+    """weight-stage size (taps per stage), Cout tiling and resident/streamed weights are
+    tuning choices: every setting must give the same result"""
+    monkeypatch.setenv(knob, value)
+    for shape in [(2, 32, 32, 96, 96, 3, 1, True, True), (1, 48, 40, 48, 48, 3, 1, True, True),
+                  (3, 20, 20, 192, 192, 3, 1, True, True), (1, 16, 24, 64, 64, 3, 1, True, False)]:
         got, ref, eng = run_conv(L.ENGINE_UMMA_HALO, "bf16", *shape)
+        assert eng == L.ENGINE_UMMA_HALO
+        assert _err(got, ref) <= 6e-3
+
+
+def test_umma_halo_many_items(cuda_device):
+    """more work items than SMs: every CTA walks several tile pairs (ring wrap-around,
+    accumulator double buffering, cross-tile residual prefetch), odd tile count at the end"""
+    for shape in [(7, 80, 72, 48, 48, 3, 1, True, True), (3, 80, 80, 96, 96, 3, 1, True, True),
+                  (9, 40, 40, 192, 192, 3, 1, True, True), (5, 36, 20, 384, 384, 3, 1, True, True)]:
+        got, ref, eng = run_conv(L.ENGINE_UMMA_HALO, "bf16", *shape)
+        assert eng == L.ENGINE_UMMA_HALO
+        assert torch.isfinite(got).all()
         assert _err(got, ref) <= 6e-3

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(128) exp_kernel(const __grid_constant__ Params
     umma_commit(smem_u32(&bars[1]));
     mbar_wait(smem_u32(&bars[1]), 0);
     long long t1 = clock64();
-    if (p.cycles) *p.cycles = t1 - t0;
+    if (p.cycles && blockIdx.x == 0) *p.cycles = t1 - t0;
   }
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -175,18 +175,24 @@ int main() {
       }
     }
   }
-  // ---- MMA issue-rate timing
-  for (int N : {48, 64, 96, 128, 192, 256}) {
-    Params p;
-    make_map(&p.tmap_a, drow, ROWS, ROWS);
-    make_map(&p.tmap_b, db, 256, 256);
-    p.out = nullptr; p.shift_rows = 0; p.sbo_bytes = 1024; p.base_off = 0; p.N = N; p.reps = 512; p.cycles = dcyc;
-    exp_kernel<<<1, 128, smem>>>(p);
-    CK(cudaDeviceSynchronize());
-    long long cyc = 0;
-    CK(cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost));
-    printf("N=%3d: %lld cycles for %d MMAs (M=128,K=16) -> %.1f cycles/MMA (ideal %d), %.0f%% of peak\n", N, cyc, 512 * 4,
-           (double)cyc / (512 * 4), N / 2, 100.0 * (N / 2) / ((double)cyc / (512 * 4)));
+  // ---- MMA issue-rate timing: aligned vs halo-style (shifted start, SBO = 1280) A operand,
+  // one CTA per SM (grid 1) and two co-resident CTAs per SM (grid 296)
+  struct R { int shift, sbo; } rv[] = {{0, 1024}, {1, 1024}, {0, 1280}, {11, 1280}, {21, 1280}};
+  for (int grid : {1, 296}) {
+    for (int N : {48, 96, 192, 256}) {
+      for (auto r : rv) {
+        Params p;
+        make_map(&p.tmap_a, drow, ROWS, ROWS);
+        make_map(&p.tmap_b, db, 256, 256);
+        p.out = nullptr; p.shift_rows = r.shift; p.sbo_bytes = r.sbo; p.base_off = 0; p.N = N; p.reps = 512; p.cycles = dcyc;
+        exp_kernel<<<grid, 128, smem>>>(p);
+        CK(cudaDeviceSynchronize());
+        long long cyc = 0;
+        CK(cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost));
+        printf("grid=%3d N=%3d shift=%2d sbo=%4d: %.1f cycles/MMA (ideal %d)\n", grid, N, r.shift, r.sbo,
+               (double)cyc / (512 * 4), N / 2);
+      }
+    }
   }
   return 0;
 }
