@@ -29,6 +29,18 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+# banner to stdout at communicator creation), so the process's fd 1 is pointed at stderr and
+# the JSON line goes to a private duplicate of the original stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 METRIC = "images/sec W48 640^2 fwd+decode"
 PARSER_KW = dict(num_joints=17, max_num_people=30, detection_threshold=0.1, tag_threshold=1.0,
                  use_detection_val=True, ignore_too_much=False, tag_per_joint=True, nms_ksize=5,
@@ -165,7 +177,7 @@ def run_reference_arm(args, rank):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args):
@@ -218,9 +230,7 @@ def run_ours(args, rank, world, local_rank):
 
     host_out = {}
 
-    def step_e2e():
-        xd = x_host.to(dev, non_blocking=True)
-        ans, count, scores = pipe.run_device(xd, True, True)
+    def finish_e2e(ans, count, scores):
         ans, count, scores = inference.pad_results(ans, count, scores, pcap)
         if world > 1:
             ans, count, scores = inference.gather_results(ans, count, scores)
@@ -228,7 +238,13 @@ def run_ours(args, rank, world, local_rank):
             if k not in host_out:
                 host_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
             host_out[k].copy_(t, non_blocking=True)
-        return ans, count, scores
+
+    def run_e2e(nsteps):
+        """nsteps batches through the host-facing pipelined call: every step copies its input
+        from pinned host memory (overlapped with the previous step's kernels) and copies its
+        results back to pinned host memory."""
+        for ans, count, scores in pipe.run_stream((x_host for _ in range(nsteps)), True, True):
+            finish_e2e(ans, count, scores)
 
     def timed(fn, steps, warmup, sample_clocks):
         for _ in range(warmup):
@@ -254,7 +270,21 @@ def run_ours(args, rank, world, local_rank):
         return float(ms.item()), clocks
 
     ms_dev, clocks = timed(step_device, args.steps, args.warmup, True)
-    ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2), False)
+    run_e2e(max(2, args.warmup))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_e2e(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms_t.item())
     ans, count, scores = step_device()
     torch.cuda.synchronize()
     people_mean = float(count.float().mean().item())
@@ -271,18 +301,29 @@ def run_ours(args, rank, world, local_rank):
     net.plan_profile(chunk, args.size, args.size, in_dtype)
     ms_ops, kinds, flops = net.plan_profile(chunk, args.size, args.size, in_dtype)
     conv_ms = sum(m for m, k in zip(ms_ops, kinds) if k in (0, 1, 3))
-    conv_flops = sum(flops)
-    umma_ms = sum(m for m, k in zip(ms_ops, kinds) if k in (0, 3))
-    umma_flops = sum(f for f, k in zip(flops, kinds) if k in (0, 3))
-    umma_launches = sum(1 for k in kinds if k in (0, 3))
-    achieved = (umma_flops if umma_ms > 0 else conv_flops) / max(umma_ms or conv_ms, 1e-9) / 1e9
-    roofline = {"bound": "tensor", "kernel": "conv_halo_kernel + conv_umma_kernel (tcgen05 implicit GEMM)",
-                "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tflops"], "traffic": None,
-                "launches": umma_launches, "avg_launch_ms": umma_ms / max(umma_launches, 1),
-                "flop_per_launch_avg": umma_flops / max(umma_launches, 1),
-                "conv_share_of_forward": conv_ms / max(sum(ms_ops), 1e-9),
-                "peak_source": peaks["source"]}
+
+    def conv_roofline(kset, name):
+        ms = sum(m for m, k in zip(ms_ops, kinds) if k in kset)
+        fl = sum(f for f, k in zip(flops, kinds) if k in kset)
+        nl = sum(1 for k in kinds if k in kset)
+        ach = fl / max(ms, 1e-9) / 1e9
+        return {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peaks["tflops"],
+                "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": None, "launches": nl,
+                "avg_launch_ms": ms / max(nl, 1), "flop_per_launch_avg": fl / max(nl, 1),
+                "share_of_forward": ms / max(sum(ms_ops), 1e-9), "peak_source": peaks["source"],
+                "chunk": chunk}
+
+    # dominant kernel: the 3x3/s1 tcgen05 halo kernel (kind 3); the per-tap tcgen05 kernel (1x1,
+    # stride 2, deconv phases, stem) is reported beside it
+    roofline = conv_roofline((3,), "conv_halo_kernel (tcgen05 implicit GEMM, 3x3 s1)")
+    roofline_other = conv_roofline((0,), "conv_umma_kernel (tcgen05 implicit GEMM, 1x1 / s2 / deconv)")
+    roofline["conv_share_of_forward"] = conv_ms / max(sum(ms_ops), 1e-9)
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(tpath):
+        with open(tpath) as f:
+            t = json.load(f)
+        roofline["traffic"] = t.get("dram_bytes_per_launch")
+        roofline["traffic_note"] = t.get("note")
 
     # ---- decode kernels against the HBM roofline (secondary)
     det, tag = pipe.forward_aggregate(x_dev[:min(8, args.batch)])
@@ -343,12 +384,13 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline,
+            "roofline_other_convs": roofline_other,
             "roofline_decode": roofline_decode, "cpu_baseline": cpu_baseline,
             "forward_tflops_effective": 2 * args.batch * world * args.steps *
             FLOP_PER_FORWARD_640 * (args.size / 640.0) ** 2 / (ms_dev * 1e-3) / 1e12,
             "people_per_image": people_mean,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -362,7 +404,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=640)
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--chunk", type=int, default=16, help="forwards per plan replay")
+    ap.add_argument("--chunk", type=int, default=64,
+                    help="forwards per plan replay (64 = the whole flip-test batch in one CUDA graph)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

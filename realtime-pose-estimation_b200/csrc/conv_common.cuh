@@ -20,7 +20,8 @@ int umma_conv_launch(const UmmaConvPrepared* p, const float* bias, const void* r
 // ---- tcgen05 halo-tile back end for 3x3 stride-1 convs (conv_halo.cu)
 struct HaloConvPrepared;
 bool halo_conv_supported(const brtpe_conv_desc* d);
-HaloConvPrepared* halo_conv_prepare(const brtpe_conv_desc* d, const void* in, const void* weights);
+HaloConvPrepared* halo_conv_prepare(const brtpe_conv_desc* d, const void* in, const void* weights,
+                                    void* out);
 void halo_conv_release(HaloConvPrepared*);
 int halo_conv_launch(const HaloConvPrepared* p, const float* bias, const void* residual, void* out,
                      cudaStream_t st);

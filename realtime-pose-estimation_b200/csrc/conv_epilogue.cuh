@@ -129,9 +129,9 @@ __device__ __forceinline__ void epi_fast_chunk(const uint32_t (&a)[32], uint32_t
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     float4 b;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-                 : "r"(bias16_smem + 16u * q));
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"      // bias_s is written once, before the
+        : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)   // first CTA-wide sync: safe to hoist
+        : "r"(bias16_smem + 16u * q));
     float v0 = __uint_as_float(a[OFF + 4 * q]), v1 = __uint_as_float(a[OFF + 4 * q + 1]);
     float v2 = __uint_as_float(a[OFF + 4 * q + 2]), v3 = __uint_as_float(a[OFF + 4 * q + 3]);
     add2(v0, v1, b.x, b.y);
@@ -144,6 +144,29 @@ __device__ __forceinline__ void epi_fast_chunk(const uint32_t (&a)[32], uint32_t
     oc.w[2 * q + 1] = pack_bf16x2_act<RELU>(v2, v3);
   }
   st_chunk32(op, oc, true);
+}
+
+// same arithmetic, result kept in registers (staged through shared memory + TMA store by the caller)
+template <bool RES, bool RELU, int OFF>
+__device__ __forceinline__ void epi_pack_chunk(const uint32_t (&a)[32], uint32_t bias16_smem,
+                                               const Chunk32& rc, Chunk32& oc) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float4 b;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"      // bias_s is written once, before the
+        : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)   // first CTA-wide sync: safe to hoist
+        : "r"(bias16_smem + 16u * q));
+    float v0 = __uint_as_float(a[OFF + 4 * q]), v1 = __uint_as_float(a[OFF + 4 * q + 1]);
+    float v2 = __uint_as_float(a[OFF + 4 * q + 2]), v3 = __uint_as_float(a[OFF + 4 * q + 3]);
+    add2(v0, v1, b.x, b.y);
+    add2(v2, v3, b.z, b.w);
+    if (RES) {
+      add2(v0, v1, bf16lo(rc.w[2 * q]), bf16hi(rc.w[2 * q]));
+      add2(v2, v3, bf16lo(rc.w[2 * q + 1]), bf16hi(rc.w[2 * q + 1]));
+    }
+    oc.w[2 * q] = pack_bf16x2_act<RELU>(v0, v1);
+    oc.w[2 * q + 1] = pack_bf16x2_act<RELU>(v2, v3);
+  }
 }
 
 // Waits for the accumulator (tfull_bar / parity), drains it and arrives on `arrive_bar`

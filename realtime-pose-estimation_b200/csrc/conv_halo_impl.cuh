@@ -1,0 +1,879 @@
+// tcgen05 implicit-GEMM kernel for the 3x3 / stride-1 / pad-1 convolutions of HigherHRNet
+// (BasicBlock conv1/conv2, Bottleneck conv2, transition1[0]: 87 % of the network's FLOPs,
+// rtpe/third_party/pose_higher_hrnet.py:40-43, :46-75, :85-87, :558-563).
+//
+// A operand: the 8x16-pixel output tile reads ONE (16+2)x(8+2)-pixel halo tile per 64-channel
+// block, loaded once by TMA (zero fill = padding) as 180 rows of 128 B with SWIZZLE_128B.
+// tcgen05 swizzles on absolute shared-memory address bits (profiles/r01_exp_umma_shift.md),
+// so tap (kh, kw) is the same tile read through a descriptor whose start address is advanced
+// by (kh*10 + kw)*128 B and whose 8-row-group pitch (SBO) is 10*128 B: the nine taps cost no
+// extra global/L2 traffic.
+//
+// Work decomposition (version 2; measurements in profiles/r01d_halo_anatomy.md):
+//  * persistent, ONE CTA per SM, 10 warps: warp 0 TMA producer, warp 1 MMA issuer, warps 2-9
+//    two epilogue groups;
+//  * one work item = a PAIR of pixel tiles (2 x 128 output pixels) x one Cout tile.  Every
+//    weight stage that reaches shared memory feeds both tiles (two TMEM accumulators), which
+//    halves the L2->SMEM weight traffic and the number of barrier hand-offs per MMA -- the two
+//    things that bounded version 1 (one hand-off costs ~115 cycles, a 12 KB TMA stage ~228);
+//  * weights stay resident for the whole kernel when they fit (Cin <= 64: 48/64-channel
+//    layers), otherwise they stream in stages of 9, 3 or 1 taps;
+//  * accumulators are double-buffered in TMEM when 4*BN <= 512 columns, so the epilogue of
+//    item i overlaps the MMAs of item i+1; epilogue group g drains tile g of the pair;
+//  * the epilogue runs one 64-channel round ahead with its residual loads, across tile
+//    boundaries, so their L2/HBM latency is off the critical path.
+#include "conv_common.cuh"
+#include "umma_ptx.cuh"
+#include "conv_epilogue.cuh"
+
+#include <cudaTypedefs.h>
+#include <string.h>
+#include <stdlib.h>
+#include <algorithm>
+
+namespace brtpe {
+
+constexpr int HL_THREADS = 320;
+constexpr int HL_TW = 8, HL_TH = 16;
+constexpr int HL_PITCH = HL_TW + 2;                       // halo row pitch in pixels
+constexpr int HL_HROWS = (HL_TH + 2) * HL_PITCH;          // 180 pixel rows of 128 B
+constexpr int HL_A_BYTES = HL_HROWS * 128;                // 23040
+constexpr int HL_A_TILE = 23552;                          // rounded to 1024
+constexpr int HL_A_STAGE = 2 * HL_A_TILE;                 // two tiles per stage
+constexpr int HL_MAX_A = 4, HL_MAX_B = 8;
+constexpr int HL_MAX_BN = 256;
+constexpr int HL_SMEM_MAX = 227 * 1024;
+constexpr int HL_TAIL = 4096;                             // barriers + TMEM slot + bias
+constexpr int HL_STAGE_OUT = 2048;                        // per epilogue warp: 32 px x 32 ch bf16
+constexpr int HL_STAGE_BYTES = 8 * HL_STAGE_OUT;          // x out_slabs (1 or 2 slabs per warp)
+
+struct alignas(64) HaloParams {
+  CUtensorMap tmap_a;
+  CUtensorMap tmap_b;
+  CUtensorMap tmap_o;           // output (C, W, H, N), box 32 ch x 8 px x 4 rows, SWIZZLE_64B
+  int N, H, W;
+  int tiles_x, tiles_y, m_tiles, n_tiles, BN, num_items;
+  int num_kb, last_k16, in_coff;
+  int a_stages, b_stages, b_stage_bytes;
+  int tps, b_groups;            // taps per weight stage, stages per channel block (tps*b_groups = 9)
+  int resident;                 // 1: all weights stay in smem for the whole kernel
+  int cg;                       // 1: one CTA per MMA; 2: CTA pair (tcgen05 cta_group::2): M = 256 over
+                                // two SMs, each CTA holds its 2 pixel tiles and HALF of the weight rows
+  int num_units;                // groups of 2*cg pixel tiles
+  int acc_stages, tmem_cols;
+  int out_slabs;                // staging slabs per epilogue warp (2 when shared memory allows)
+  uint32_t idesc;
+  FastDiv fd_xy, fd_x, fd_nt;
+  const float* bias;
+  EpiParams epi;
+  long long* prof;              // debug: per-CTA role/wait cycle counters
+  int dbg;                      // debug (BRTPE_HALO_DBG): 1 no MMA issue, 2 no epilogue work,
+                                // 4 no weight loads, 8 no activation loads (results are garbage)
+};
+
+// Debug instrumentation (brtpe_debug_halo_prof): 16 counters per CTA, in SM clock cycles.
+//  0 kernel total (thread 0)   1 prologue (until the first CTA-wide sync)
+//  2 producer loop total       3 producer waiting for a free A stage   4 ... free B stage
+//  5 MMA loop total            6 MMA waiting for A data   7 ... B data   8 ... a free accumulator
+//  9 epilogue warp 2 loop total  10 epilogue waiting for the accumulator  11 items of this CTA
+constexpr int HL_PROF_SLOTS = 16;
+extern long long* g_halo_prof;       // defined in conv_halo.cu
+extern int g_halo_prof_ctas;
+
+#define HL_TIMED(slot, stmt)                   \
+  do {                                         \
+    if (PROF) {                                \
+      const long long t0__ = clock64();        \
+      stmt;                                    \
+      pc[slot] += clock64() - t0__;            \
+    } else {                                   \
+      stmt;                                    \
+    }                                          \
+  } while (0)
+
+struct HaloConvPrepared {
+  HaloParams p;
+  int grid;
+  size_t smem;
+  brtpe_conv_desc d;            // to (re-)encode the output tensor map
+  const void* out_encoded;      // output pointer tmap_o was encoded for
+};
+
+// descriptor halves (see make_kmajor_sw128_desc): lo = start>>4 | LBO(1)<<16, hi = SBO>>4 |
+// version(1)<<14 | SWIZZLE_128B(2)<<29
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) {
+  return ((smem_addr >> 4) & 0x3fffu) | (1u << 16);
+}
+__device__ __forceinline__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) {
+  return (sbo_bytes >> 4) | (1u << 14) | (2u << 29);
+}
+
+// tile index -> image / origin of the 8x16 output tile (n == p.N for tiles past the end:
+// their TMA box is fully out of bounds and reads zeros, their outputs are never stored)
+struct TileOrg {
+  int n, y0, x0;
+};
+__device__ __forceinline__ TileOrg tile_origin(const HaloParams& p, int mt) {
+  TileOrg o;
+  const int tiles_xy = p.tiles_x * p.tiles_y;
+  o.n = (int)fdiv((uint32_t)mt, p.fd_xy);
+  const int rem = mt - o.n * tiles_xy;
+  const int ty = (int)fdiv((uint32_t)rem, p.fd_x);
+  o.y0 = ty * HL_TH;
+  o.x0 = (rem - ty * p.tiles_x) * HL_TW;
+  if (mt >= p.m_tiles) o.n = p.N;
+  return o;
+}
+
+// ---- epilogue, fast path: one 64-channel round of residual in flight ahead of the math
+struct EpiPix {
+  bool valid;
+  size_t opix;
+};
+__device__ __forceinline__ EpiPix epi_pixel(const HaloParams& p, int item, int tile, int m,
+                                            int rank) {
+  EpiPix e;
+  e.valid = false;
+  e.opix = 0;
+  if (item >= p.num_items) return e;
+  const int unit = (int)fdiv((uint32_t)item, p.fd_nt);
+  const int mt = unit * (2 * p.cg) + rank * 2 + tile;
+  const TileOrg o = tile_origin(p, mt);
+  const int y = o.y0 + (m >> 3), x = o.x0 + (m & 7);
+  e.valid = mt < p.m_tiles && y < p.H && x < p.W;
+  e.opix = e.valid ? ((size_t)o.n * p.H + y) * p.W + x : 0;
+  return e;
+}
+
+template <bool RES>
+__device__ __forceinline__ void epi_fetch_round(Chunk32 (&r)[4], const __nv_bfloat16* rp,
+                                                bool valid, int c0, int nchunks) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (RES && valid && c0 + j < nchunks) r[j] = ld_chunk32(rp + (c0 + j) * 16, true);
+  }
+}
+
+template <bool RES, bool RELU>
+__device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const float* bias_s,
+                                                   uint32_t tmem_base, uint64_t* tfull,
+                                                   uint32_t tempty_addr, int group, int lg,
+                                                   int lane, int rank, int item0, int istep,
+                                                   uint32_t stage_buf, bool PROF, long long* pc) {
+  const EpiParams& e = p.epi;
+  const int m = lg * 32 + lane;
+  const int BN = p.BN, n_tiles = p.n_tiles, num_items = p.num_items;
+  const int nchunks = BN >> 4;
+  const int acc_stages = p.acc_stages;
+  const uint32_t bias_u32 = smem_u32(bias_s);
+  Chunk32 nxt[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) nxt[j].w[i] = 0u;
+
+  constexpr bool remote = (HL_CG == 2);
+  const bool two_slabs = p.out_slabs == 2;
+  int slab_sel = 0;   // the accumulator-free barrier lives in the leader CTA
+  int item = item0;
+  EpiPix px = epi_pixel(p, item, group, m, rank);
+  int nt = item - (int)fdiv((uint32_t)item, p.fd_nt) * n_tiles;
+  epi_fetch_round<RES>(nxt, RES ? e.res + px.opix * e.res_ld + e.res_coff + nt * BN : nullptr,
+                       px.valid, 0, nchunks);
+  int it = 0;
+  for (; item < num_items; item += istep, ++it) {
+    const int next_item = item + istep;
+    const EpiPix npx = epi_pixel(p, next_item, group, m, rank);
+    const int nnt = next_item - (int)fdiv((uint32_t)next_item, p.fd_nt) * n_tiles;
+    const int co0 = nt * BN;
+    const __nv_bfloat16* rp = RES ? e.res + px.opix * e.res_ld + e.res_coff + co0 : nullptr;
+    const __nv_bfloat16* nrp = RES ? e.res + npx.opix * e.res_ld + e.res_coff + nnt * BN : nullptr;
+    // origin of this warp's 8 x 4 pixel slab (TMA clips what lies outside the image / batch)
+    const TileOrg org = tile_origin(
+        p, (int)fdiv((uint32_t)item, p.fd_nt) * (2 * p.cg) + rank * 2 + group);
+    const int oy = org.y0 + 4 * lg;
+    const int acc = (acc_stages == 2) ? (it & 1) : 0;
+    const uint32_t accph = (acc_stages == 2) ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
+    const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) +
+                            (uint32_t)(acc * 2 * BN + group * BN);
+    HL_TIMED(10, mbar_wait(smem_u32(&tfull[acc]), accph));
+    if (PROF) pc[11] += 1;
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < nchunks; c0 += 4) {
+      Chunk32 cur[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+      if (c0 + 4 < nchunks) epi_fetch_round<RES>(nxt, rp, px.valid, c0 + 4, nchunks);
+      else epi_fetch_round<RES>(nxt, nrp, npx.valid, 0, nchunks);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = c0 + 2 * h;
+        if (c < nchunks) {
+          const bool two = c + 1 < nchunks;
+          uint32_t a[32];
+          if (two) tmem_ld32(t_addr + (uint32_t)(c * 16), a);
+          else tmem_ld16_lo(t_addr + (uint32_t)(c * 16), a);
+          tmem_ld_wait();
+          if (c + 2 >= nchunks) {                  // last TMEM read of this tile
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (remote) mbar_arrive_cluster(tempty_addr + 8u * acc);
+              else mbar_arrive(tempty_addr + 8u * acc);
+            }
+          }
+          if (!two && n_tiles > 1) {
+            // 16-channel tail of a Cout tile that has a neighbour: the 32-channel store box
+            // would spill into the neighbour's channels, so this chunk is stored directly
+            if (px.valid) {
+              const uint32_t bs = bias_u32 + (uint32_t)((co0 + c * 16) * 4);
+              epi_fast_chunk<RES, RELU, 0>(a, bs, cur[2 * h],
+                                           e.out + px.opix * e.out_ld + e.out_coff + co0 + c * 16);
+            }
+          } else {
+            // 32 (or 16) channels of 32 pixels -> bf16 in registers -> this warp's staging
+            // slab (64-byte rows, SWIZZLE_64B so the 16-byte stores are conflict free) -> one
+            // TMA store.  One line request per lane and access was the limit of the direct
+            // 32-byte global stores (profiles/r01e_halo_pair.md).
+            const uint32_t bs = bias_u32 + (uint32_t)((co0 + c * 16) * 4);
+            Chunk32 o0, o1;
+            epi_pack_chunk<RES, RELU, 0>(a, bs, cur[2 * h], o0);
+            if (two) epi_pack_chunk<RES, RELU, 16>(a, bs + 64u, cur[2 * h + 1], o1);
+            // slab (re-)use: with two slabs per warp only the store before the previous one
+            // must have finished reading
+            if (lane == 0) {
+              if (two_slabs) bulk_wait_read1();
+              else bulk_wait_read0();
+            }
+            __syncwarp();
+            const uint32_t slab = stage_buf + (two_slabs ? (uint32_t)(slab_sel * HL_STAGE_OUT) : 0u);
+            slab_sel ^= 1;
+            const uint32_t row = slab + (uint32_t)lane * 64u;
+            const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+            st_shared_v4(row + ((0u ^ sw) << 4), o0.w[0], o0.w[1], o0.w[2], o0.w[3]);
+            st_shared_v4(row + ((1u ^ sw) << 4), o0.w[4], o0.w[5], o0.w[6], o0.w[7]);
+            if (two) {
+              st_shared_v4(row + ((2u ^ sw) << 4), o1.w[0], o1.w[1], o1.w[2], o1.w[3]);
+              st_shared_v4(row + ((3u ^ sw) << 4), o1.w[4], o1.w[5], o1.w[6], o1.w[7]);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&p.tmap_o, slab, e.out_coff + co0 + c * 16, org.x0, oy, org.n);
+              bulk_commit();
+            }
+          }
+        }
+      }
+    }
+    px = npx;
+    nt = nnt;
+  }
+  if (lane == 0) bulk_wait0();                      // every TMA store of this warp has landed
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(HL_THREADS, 1)
+HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
+  const bool PROF = p.prof != nullptr;   // debug counters (brtpe_debug_halo_prof), warp-uniform
+  extern __shared__ uint8_t smem_raw[];
+  long long pc[HL_PROF_SLOTS];
+#pragma unroll
+  for (int i = 0; i < HL_PROF_SLOTS; ++i) pc[i] = 0;
+  const long long t_start = PROF ? clock64() : 0;
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // hoist everything the hot loops need out of the constant bank
+  const int a_stages = p.a_stages, b_stages = p.b_stages, b_stage_bytes = p.b_stage_bytes;
+  const int num_kb = p.num_kb, last_k16 = p.last_k16, num_items = p.num_items;
+  const int n_tiles = p.n_tiles, BN = p.BN;
+  const int tps = p.tps, b_groups = p.b_groups, acc_stages = p.acc_stages;
+  const bool resident = p.resident != 0;
+  const uint32_t idesc = p.idesc;
+  const int dbg = p.dbg;
+  // CTA pair (cta_group::2): rank 0 is the leader (issues the MMAs, owns the pair's barriers)
+  constexpr bool cg2 = (HL_CG == 2);
+  const int rank = cg2 ? (int)cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  const int item0 = cg2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int istep = cg2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tpi = 2 * p.cg;                         // pixel tiles per work item
+  const int BNh = cg2 ? (BN >> 1) : BN;             // weight rows this CTA holds
+
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + (size_t)a_stages * HL_A_STAGE;
+  uint8_t* stage_out = b_ring + (size_t)b_stages * b_stage_bytes;     // 8 epilogue-warp slabs
+  uint8_t* tail = stage_out + (size_t)p.out_slabs * HL_STAGE_BYTES;
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_a = full_a + HL_MAX_A;
+  uint64_t* full_b = empty_a + HL_MAX_A;
+  uint64_t* empty_b = full_b + HL_MAX_B;
+  uint64_t* tfull = empty_b + HL_MAX_B;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmap_a);
+    tma_prefetch_desc(&p.tmap_b);
+    tma_prefetch_desc(&p.tmap_o);
+    for (int s = 0; s < HL_MAX_A; ++s) {
+      mbar_init(smem_u32(&full_a[s]), 1);
+      mbar_init(smem_u32(&empty_a[s]), 1);
+    }
+    for (int s = 0; s < HL_MAX_B; ++s) {
+      mbar_init(smem_u32(&full_b[s]), 1);
+      mbar_init(smem_u32(&empty_b[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tfull[s]), 1);
+      mbar_init(smem_u32(&tempty[s]), (uint32_t)(8 * p.cg));   // 8 epilogue warps per CTA
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < n_tiles * BN; i += HL_THREADS)
+    bias_s[i] = (p.bias && i < p.epi.Cout) ? p.bias[i] : 0.0f;
+  if (warp == 1) {
+    if (cg2) tmem_alloc_cg2(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    else tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (cg2) cluster_sync_all();      // the peer's barriers exist before anything is signalled on them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long t_loop = PROF ? clock64() : 0;
+
+  if (warp == 0) {
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) ========
+    // Pair mode: both CTAs load their own activation tiles and their half of the weight rows;
+    // completion is counted on the LEADER's full barrier, which alone expects the bytes of both.
+    int as_ = 0, bs_ = 0;
+    uint32_t aph = 0, bph = 0;
+    const uint32_t stage_b_bytes = (uint32_t)(tps * BN * 128);          // both CTAs together
+    const int in_coff = p.in_coff;
+    const int brow0 = rank * BNh;
+    auto sig = [&](const uint64_t* bar) -> uint32_t {                   // barrier the TMA signals
+      const uint32_t a = smem_u32(bar);
+      return cg2 ? mapa_u32(a, 0u) : a;
+    };
+    if (resident) {
+      // every tap of every channel block, once per kernel
+      if (elect_one()) {
+        const uint32_t fb = smem_u32(&full_b[0]);
+        if (leader) mbar_expect_tx(fb, (uint32_t)(num_kb * 9 * BN * 128));
+        const uint32_t fbs = sig(&full_b[0]);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const uint32_t dst = smem_u32(b_ring) + (uint32_t)(kb * 9 * BNh * 128);
+          if (cg2) tma_load_3d_cg2(dst, &p.tmap_b, fbs, kb * 64, brow0, 0);
+          else tma_load_3d(dst, &p.tmap_b, fb, kb * 64, 0, 0);
+        }
+      }
+      __syncwarp();
+    }
+    // The activation tiles of step s+1 (a step = one channel block of one item) are requested as
+    // soon as their stage is free, in between the weight stages of step s: the weight loads
+    // block on the MMA's progress, and the activation load must neither queue behind all of
+    // them nor hold them up.
+    int nx_item = item0, nx_kb = 0;                 // next activation load to issue
+    auto load_a = [&](bool block) -> bool {
+      if (nx_item >= num_items) return true;
+      const uint32_t eb = smem_u32(&empty_a[as_]);
+      if (block) {
+        HL_TIMED(3, mbar_wait(eb, aph ^ 1u));
+      } else if (!mbar_test(eb, aph ^ 1u)) {
+        return false;
+      }
+      const int unit = (int)fdiv((uint32_t)nx_item, p.fd_nt);
+      const TileOrg o0 = tile_origin(p, unit * tpi + rank * 2);
+      const TileOrg o1 = tile_origin(p, unit * tpi + rank * 2 + 1);
+      if (elect_one()) {
+        const uint32_t fa = smem_u32(&full_a[as_]);
+        if (dbg & 8) {
+          if (leader) mbar_arrive(fa);
+        } else {
+          const uint32_t dst = smem_u32(a_ring + (size_t)as_ * HL_A_STAGE);
+          if (leader) mbar_expect_tx(fa, (uint32_t)(tpi * HL_A_BYTES));
+          if (cg2) {
+            const uint32_t fas = sig(&full_a[as_]);
+            tma_load_5d_cg2(dst, &p.tmap_a, fas, in_coff + nx_kb * 64, o0.x0 - 1, 0, o0.y0 - 1, o0.n);
+            tma_load_5d_cg2(dst + HL_A_TILE, &p.tmap_a, fas, in_coff + nx_kb * 64, o1.x0 - 1, 0,
+                            o1.y0 - 1, o1.n);
+          } else {
+            tma_load_5d(dst, &p.tmap_a, fa, in_coff + nx_kb * 64, o0.x0 - 1, 0, o0.y0 - 1, o0.n);
+            tma_load_5d(dst + HL_A_TILE, &p.tmap_a, fa, in_coff + nx_kb * 64, o1.x0 - 1, 0,
+                        o1.y0 - 1, o1.n);
+          }
+        }
+      }
+      __syncwarp();
+      if (++as_ == a_stages) { as_ = 0; aph ^= 1u; }
+      if (++nx_kb == num_kb) { nx_kb = 0; nx_item += istep; }
+      return true;
+    };
+    load_a(true);                                   // step 0
+    for (int item = item0; item < num_items; item += istep) {
+      const int nt = item - (int)fdiv((uint32_t)item, p.fd_nt) * n_tiles;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        // invariant: the activation load of this step has been issued
+        bool next_done = load_a(false);
+        if (!resident) {
+#pragma unroll 1
+          for (int g = 0; g < b_groups; ++g) {
+            HL_TIMED(4, mbar_wait(smem_u32(&empty_b[bs_]), bph ^ 1u));
+            if (elect_one()) {
+              const uint32_t fb = smem_u32(&full_b[bs_]);
+              if (dbg & 4) {
+                if (leader) mbar_arrive(fb);
+              } else {
+                const uint32_t dst = smem_u32(b_ring + (size_t)bs_ * b_stage_bytes);
+                if (leader) mbar_expect_tx(fb, stage_b_bytes);
+                if (cg2) tma_load_3d_cg2(dst, &p.tmap_b, sig(&full_b[bs_]), kb * 64,
+                                         nt * BN + brow0, g * tps);
+                else tma_load_3d(dst, &p.tmap_b, fb, kb * 64, nt * BN, g * tps);
+              }
+            }
+            __syncwarp();
+            if (++bs_ == b_stages) { bs_ = 0; bph ^= 1u; }
+            if (!next_done) next_done = load_a(false);
+          }
+        }
+        if (!next_done) load_a(true);
+      }
+    }
+    if (PROF && lane == 0) {
+      long long* o = p.prof + (size_t)blockIdx.x * HL_PROF_SLOTS;
+      o[2] = clock64() - t_loop; o[3] = pc[3]; o[4] = pc[4];
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only; one elected lane issues) ============
+    if (leader) {
+      int as_ = 0, bs_ = 0;
+      uint32_t aph = 0, bph = 0;
+      int it = 0;
+      constexpr uint32_t A_HI = desc_hi(HL_PITCH * 128);
+      constexpr uint32_t B_HI = desc_hi(1024);
+      const uint32_t a_ring_lo = desc_lo(smem_u32(a_ring));
+      const uint32_t b_ring_lo = desc_lo(smem_u32(b_ring));
+      const uint32_t a_stage_lo = (uint32_t)(HL_A_STAGE >> 4);
+      const uint32_t a_tile_lo = (uint32_t)(HL_A_TILE >> 4);
+      const uint32_t b_stage_lo = (uint32_t)(b_stage_bytes >> 4);
+      const uint32_t b_tap_lo = (uint32_t)((BNh * 128) >> 4);
+      const bool no_mma = (dbg & 1) != 0;
+      constexpr uint16_t PAIR = 0x3;
+      if (resident) {
+        HL_TIMED(7, mbar_wait(smem_u32(&full_b[0]), 0));
+      }
+      for (int item = item0; item < num_items; item += istep, ++it) {
+        const int acc = (acc_stages == 2) ? (it & 1) : 0;
+        const uint32_t accph = (acc_stages == 2) ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
+        if (cg2) {
+          HL_TIMED(8, mbar_wait_cluster(smem_u32(&tempty[acc]), accph ^ 1u));
+        } else {
+          HL_TIMED(8, mbar_wait(smem_u32(&tempty[acc]), accph ^ 1u));
+        }
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * BN);
+        const uint32_t d1 = d0 + (uint32_t)BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          HL_TIMED(6, mbar_wait(smem_u32(&full_a[as_]), aph));
+          const uint32_t a0 = a_ring_lo + (uint32_t)as_ * a_stage_lo;
+          const uint32_t a1 = a0 + a_tile_lo;
+          const int k16 = (kb == num_kb - 1) ? last_k16 : 4;
+#pragma unroll 1
+          for (int g = 0; g < b_groups; ++g) {
+            uint32_t b_lo;
+            if (resident) {
+              b_lo = b_ring_lo + (uint32_t)(kb * 9) * b_tap_lo;
+            } else {
+              HL_TIMED(7, mbar_wait(smem_u32(&full_b[bs_]), bph));
+              b_lo = b_ring_lo + (uint32_t)bs_ * b_stage_lo;
+            }
+            if (elect_one()) {
+              int kh = (g * tps) / 3, kw = (g * tps) - kh * 3;
+#pragma unroll 1
+              for (int t = 0; t < tps; ++t) {
+                // tap (kh, kw): same halo tile, start advanced by (kh*PITCH + kw) rows of 128 B
+                const uint32_t a_off = (uint32_t)(((kh * HL_PITCH + kw) * 128) >> 4);
+                const uint32_t bt = b_lo + (uint32_t)t * b_tap_lo;
+                const uint32_t first = (uint32_t)(kb | g | t);
+                if (!no_mma) {
+                  if (cg2) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      if (k < k16)
+                        umma_f16_lohi_cg2(d0, a0 + a_off + 2u * k, A_HI, bt + 2u * k, B_HI, idesc,
+                                          (first | (uint32_t)k) ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      if (k < k16)
+                        umma_f16_lohi_cg2(d1, a1 + a_off + 2u * k, A_HI, bt + 2u * k, B_HI, idesc,
+                                          (first | (uint32_t)k) ? 1u : 0u);
+                  } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      if (k < k16)
+                        umma_f16_lohi(d0, a0 + a_off + 2u * k, A_HI, bt + 2u * k, B_HI, idesc,
+                                      (first | (uint32_t)k) ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      if (k < k16)
+                        umma_f16_lohi(d1, a1 + a_off + 2u * k, A_HI, bt + 2u * k, B_HI, idesc,
+                                      (first | (uint32_t)k) ? 1u : 0u);
+                  }
+                }
+                if (++kw == 3) { kw = 0; ++kh; }
+              }
+              if (!resident) {
+                if (cg2) umma_commit_cg2(smem_u32(&empty_b[bs_]), PAIR);
+                else umma_commit(smem_u32(&empty_b[bs_]));
+              }
+            }
+            __syncwarp();
+            if (!resident) {
+              if (++bs_ == b_stages) { bs_ = 0; bph ^= 1u; }
+            }
+          }
+          if (elect_one()) {
+            if (cg2) umma_commit_cg2(smem_u32(&empty_a[as_]), PAIR);
+            else umma_commit(smem_u32(&empty_a[as_]));
+          }
+          __syncwarp();
+          if (++as_ == a_stages) { as_ = 0; aph ^= 1u; }
+        }
+        if (elect_one()) {
+          if (cg2) umma_commit_cg2(smem_u32(&tfull[acc]), PAIR);
+          else umma_commit(smem_u32(&tfull[acc]));
+        }
+        __syncwarp();
+      }
+      if (PROF && lane == 0) {
+        long long* o = p.prof + (size_t)blockIdx.x * HL_PROF_SLOTS;
+        o[5] = clock64() - t_loop; o[6] = pc[6]; o[7] = pc[7]; o[8] = pc[8];
+      }
+    }
+  } else {
+    // ===================== epilogue: group g drains tile g of this CTA =======================
+    const int group = (warp - 2) >> 2;
+    const int lg = warp & 3;                       // TMEM lane quarter this warp may read
+    const EpiParams& e = p.epi;
+    // the accumulator-free barrier of the pair lives in the leader CTA
+    const uint32_t tempty_addr = cg2 ? mapa_u32(smem_u32(&tempty[0]), 0u) : smem_u32(&tempty[0]);
+    const uint32_t stage_slab = smem_u32(stage_out) + (uint32_t)((warp - 2) * p.out_slabs * HL_STAGE_OUT);
+    if (dbg & 2) {
+      int it = 0;
+      for (int item = item0; item < num_items; item += istep, ++it) {
+        const int acc = (acc_stages == 2) ? (it & 1) : 0;
+        const uint32_t accph = (acc_stages == 2) ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
+        mbar_wait(smem_u32(&tfull[acc]), accph);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (cg2) mbar_arrive_cluster(tempty_addr + 8u * acc);
+          else mbar_arrive(tempty_addr + 8u * acc);
+        }
+      }
+    } else if (e.fast) {
+      if (e.res != nullptr) {
+        if (e.relu) halo_epilogue_fast<true, true>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
+        else halo_epilogue_fast<true, false>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
+      } else {
+        if (e.relu) halo_epilogue_fast<false, true>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
+        else halo_epilogue_fast<false, false>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
+      }
+    } else {
+      // general epilogue (ragged channel counts): single-CTA mode only (host guarantees cg == 1)
+      const int m = lg * 32 + lane;
+      const int nchunks = BN >> 4;
+      int it = 0;
+      for (int item = item0; item < num_items; item += istep, ++it) {
+        const int unit = (int)fdiv((uint32_t)item, p.fd_nt);
+        const int nt = item - unit * n_tiles;
+        const EpiPix px = epi_pixel(p, item, group, m, rank);
+        const int acc = (acc_stages == 2) ? (it & 1) : 0;
+        const uint32_t accph = (acc_stages == 2) ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
+        const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) +
+                                (uint32_t)(acc * 2 * BN + group * BN);
+        epi_drain(e, bias_s, t_addr, nchunks, nt * BN, px.valid, px.opix, smem_u32(&tfull[acc]),
+                  accph, smem_u32(&tempty[acc]), lane);
+      }
+    }
+    if (PROF && warp == 2 && lane == 0) {
+      long long* o = p.prof + (size_t)blockIdx.x * HL_PROF_SLOTS;
+      o[9] = clock64() - t_loop; o[10] = pc[10]; o[11] = pc[11];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (cg2) cluster_sync_all();      // nobody leaves while the pair's MMAs / commits may still touch it
+  if (warp == 1) {
+    tc_fence_after();
+    if (cg2) tmem_dealloc_cg2(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+  if (PROF && threadIdx.x == 0) {
+    long long* o = p.prof + (size_t)blockIdx.x * HL_PROF_SLOTS;
+    o[0] = clock64() - t_start;
+    o[1] = t_loop - t_start;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 halo_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// cycles of one M=128, K=16 MMA with both operands in shared memory (measured:
+// profiles/r01_exp_umma_shift.md): max(N/2, 32 + N/4)
+static inline double mma_cycles(int bn) { return std::max(bn / 2.0, 32.0 + bn / 4.0); }
+
+// Cout tiling: the fewest tiles that fit (BN <= 256), unless a finer split fills the SMs
+// better (small maps: few pixel-tile pairs) -- estimated as rounds * per-item MMA time.
+static void halo_n_tiling(int cout_store, int pairs, int workers, int* n_tiles, int* bn) {
+  const int cp = (cout_store + 15) / 16 * 16;
+  const int sms = workers;
+  int best_nt = 0, best_bn = 0;
+  double best = 0;
+  const int nt0 = (cp + HL_MAX_BN - 1) / HL_MAX_BN;
+  for (int nt = nt0; nt <= nt0 + 3; ++nt) {
+    const int b = ((cp + nt - 1) / nt + 15) / 16 * 16;
+    if (nt > nt0 && b < 96) break;
+    const long long items = (long long)pairs * nt;
+    const double rounds = (double)((items + sms - 1) / sms);
+    const double cost = rounds * mma_cycles(b) + 0.05 * nt;   // tie -> fewer tiles
+    if (best_nt == 0 || cost < best) {
+      best = cost; best_nt = nt; best_bn = b;
+    }
+  }
+  *n_tiles = best_nt;
+  *bn = best_bn;
+}
+
+static bool HL_NAME(g_halo_attr_set) = false;
+
+// Output tensor map of the epilogue's TMA stores: (C = out_coff + Cout, W, H, N) with the pixel
+// stride of the output buffer; box = 32 channels x 8 px x 4 rows (one epilogue warp's slab),
+// SWIZZLE_64B.  Stores beyond C / W / H / N are clipped by the hardware: that is how ragged
+// tiles, the 16-channel tail of odd channel counts and tiles past the end of the batch are
+// handled.
+static bool halo_encode_out(const brtpe_conv_desc* d, void* out, CUtensorMap* map) {
+  auto encode = halo_encode_fn();
+  const cuuint64_t ld_b = (cuuint64_t)d->out_ld * 2;
+  cuuint64_t gdim[4] = {(cuuint64_t)(d->out_coff + d->Cout), (cuuint64_t)d->Wout,
+                        (cuuint64_t)d->Hout, (cuuint64_t)d->N};
+  cuuint64_t gstr[3] = {ld_b, ld_b * d->Wout, ld_b * d->Wout * d->Hout};
+  cuuint32_t box[4] = {32, (cuuint32_t)HL_TW, 4, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("halo conv: cuTensorMapEncodeTiled(out) failed with %d", (int)r);
+    return false;
+  }
+  return true;
+}
+
+HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const void* in,
+                                             const void* weights, void* out) {
+  HaloConvPrepared* P = new HaloConvPrepared();
+  P->d = *d;
+  P->out_encoded = nullptr;
+  HaloParams& p = P->p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->N; p.H = d->Hin; p.W = d->Win;
+  p.tiles_x = ceil_div(p.W, HL_TW);
+  p.tiles_y = ceil_div(p.H, HL_TH);
+  p.m_tiles = p.tiles_x * p.tiles_y * p.N;
+  // CTA-pair mode (tcgen05 cta_group::2): needs the chunk-aligned fast epilogue and an even
+  // number of SMs; BRTPE_HALO_CG=1 forces the single-CTA kernel
+  p.cg = HL_CG;
+  if (p.cg == 2 && (!epi_fast_ok(d) || (num_sms() & 1) || p.m_tiles < 4)) {
+    delete P;
+    return nullptr;
+  }
+  const int tpi = 2 * p.cg;
+  const int workers = num_sms() / p.cg;               // CTAs (cg 1) or CTA pairs (cg 2)
+  const int pairs = ceil_div(p.m_tiles, tpi);         // work units of 2*cg pixel tiles
+  p.num_units = pairs;
+  halo_n_tiling(d->Cout_store, pairs, workers, &p.n_tiles, &p.BN);
+  if (getenv("BRTPE_HALO_NT")) {
+    const int nt = atoi(getenv("BRTPE_HALO_NT"));
+    const int cp = (d->Cout_store + 15) / 16 * 16;
+    const int b = ((cp + nt - 1) / std::max(nt, 1) + 15) / 16 * 16;
+    if (nt >= 1 && b <= HL_MAX_BN && b >= 16) { p.n_tiles = nt; p.BN = b; }
+  }
+  p.num_items = pairs * p.n_tiles;
+
+  p.num_kb = ceil_div(d->Cin, 64);
+  p.last_k16 = (d->Cin - (p.num_kb - 1) * 64) / 16;
+  p.in_coff = d->in_coff;
+  p.dbg = getenv("BRTPE_HALO_DBG") ? atoi(getenv("BRTPE_HALO_DBG")) : 0;
+  p.acc_stages = (4 * p.BN <= 512) ? 2 : 1;
+  int cols = 32;
+  while (cols < p.acc_stages * 2 * p.BN) cols *= 2;
+  p.tmem_cols = cols;
+
+  // shared-memory plan: [A ring][B ring or resident weights][tail]; in pair mode every CTA
+  // holds half of the weight rows
+  const int tap_bytes = (p.BN / p.cg) * 128;
+  // two output slabs per epilogue warp unless that would push resident weights out / leave the
+  // weight ring with fewer than two stages
+  p.out_slabs = 2;
+  {
+    const int b2 = HL_SMEM_MAX - HL_TAIL - 1024 - 2 * HL_STAGE_BYTES;
+    const int tb = (p.BN / p.cg) * 128;
+    const bool res1 = p.n_tiles == 1 && p.num_kb * 9 * tb + 2 * HL_A_STAGE <= b2 + HL_STAGE_BYTES;
+    const bool res2 = p.n_tiles == 1 && p.num_kb * 9 * tb + 2 * HL_A_STAGE <= b2;
+    if ((res1 && !res2) || (!res2 && 2 * tb > b2 - 2 * HL_A_STAGE)) p.out_slabs = 1;
+  }
+  const int budget = HL_SMEM_MAX - HL_TAIL - 1024 - p.out_slabs * HL_STAGE_BYTES;
+  const int resident_bytes = p.num_kb * 9 * tap_bytes;
+  p.resident = (p.n_tiles == 1 && resident_bytes + 2 * HL_A_STAGE <= budget) ? 1 : 0;
+  if (getenv("BRTPE_HALO_NO_RESIDENT")) p.resident = 0;
+  if (p.resident) {
+    p.tps = 9; p.b_groups = 1; p.b_stages = 1;
+    p.b_stage_bytes = (int)align_up((size_t)resident_bytes, 1024);
+    p.a_stages = std::min(HL_MAX_A, (budget - p.b_stage_bytes) / HL_A_STAGE);
+  } else {
+    p.a_stages = 2;
+    const int bbudget = budget - p.a_stages * HL_A_STAGE;
+    // the largest tap group that still leaves >= 2 stages
+    int tps = 9;
+    if (2 * 9 * tap_bytes > bbudget) tps = 3;
+    if (tps == 3 && 2 * 3 * tap_bytes > bbudget) tps = 1;
+    if (getenv("BRTPE_HALO_TPS")) {
+      const int t = atoi(getenv("BRTPE_HALO_TPS"));
+      if ((t == 1 || t == 3 || t == 9) && 2 * t * tap_bytes <= bbudget) tps = t;
+    }
+    p.tps = tps;
+    p.b_groups = 9 / tps;
+    p.b_stage_bytes = (int)align_up((size_t)tps * tap_bytes, 1024);
+    p.b_stages = std::min(HL_MAX_B, bbudget / p.b_stage_bytes);
+    if (p.b_stages < 2) {
+      set_error("halo conv: weight stage of %d bytes does not fit twice", p.b_stage_bytes);
+      delete P;
+      return nullptr;
+    }
+  }
+  P->smem = (size_t)p.a_stages * HL_A_STAGE + (size_t)p.b_stages * p.b_stage_bytes +
+            (size_t)p.out_slabs * HL_STAGE_BYTES + HL_TAIL + 1024;
+  P->grid = p.cg * std::max(1, std::min(p.num_items, workers));
+
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
+            ((uint32_t)((128 * p.cg) >> 4) << 24);
+  p.epi.out = nullptr; p.epi.res = nullptr;
+  p.epi.out_ld = d->out_ld; p.epi.out_coff = d->out_coff; p.epi.res_ld = d->res_ld;
+  p.epi.res_coff = d->res_coff; p.epi.Cout = d->Cout; p.epi.Cout_store = d->Cout_store;
+  p.epi.relu = d->relu; p.epi.vec32 = epi_vec32_ok(d);
+  // the fast epilogue walks whole 16-channel chunks of real channels
+  p.epi.fast = (epi_fast_ok(d) && p.n_tiles * p.BN == d->Cout) ? 1 : 0;
+  if (p.cg == 2 && !p.epi.fast) {
+    set_error("halo conv: pair mode needs Cout = n_tiles * BN (Cout %d, %d x %d)", d->Cout, p.n_tiles, p.BN);
+    delete P;
+    return nullptr;
+  }
+  p.fd_nt = make_fastdiv((uint32_t)p.n_tiles, (uint64_t)p.num_items + 2ull * num_sms() + 2);
+  p.fd_xy = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y), (uint64_t)p.m_tiles + 8ull * num_sms() + 8);
+  p.fd_x = make_fastdiv((uint32_t)p.tiles_x, (uint64_t)p.tiles_x * p.tiles_y);
+
+  auto encode = halo_encode_fn();
+  const cuuint64_t ld_b = (cuuint64_t)d->in_ld * 2;
+  cuuint64_t gdim[5] = {(cuuint64_t)(d->in_coff + d->Cin), (cuuint64_t)d->Win, 1,
+                        (cuuint64_t)d->Hin, (cuuint64_t)d->N};
+  cuuint64_t gstr[4] = {ld_b, ld_b * d->Win, ld_b * d->Win, ld_b * d->Win * d->Hin};
+  cuuint32_t box[5] = {64, (cuuint32_t)HL_PITCH, 1, (cuuint32_t)(HL_TH + 2), 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(&p.tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), gdim,
+                      gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("halo conv: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+    delete P;
+    return nullptr;
+  }
+  // packed weights: bf16 [9][cout_pad][cin_pad] (brtpe_umma_weight_dims); rows beyond cout_pad
+  // (when n_tiles*BN rounds up past it) are out of bounds and read as zeros
+  int cin_pad = 0, cout_pad = 0;
+  brtpe_umma_weight_dims(d->Cin, d->Cout_store, &cin_pad, &cout_pad);
+  cuuint64_t wdim[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, 9};
+  cuuint64_t wstr[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)cin_pad * 2 * cout_pad};
+  cuuint32_t wbox[3] = {64, (cuuint32_t)(p.BN / p.cg), (cuuint32_t)p.tps};
+  cuuint32_t westr[3] = {1, 1, 1};
+  r = encode(&p.tmap_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(weights), wdim, wstr,
+             wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("halo conv: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+    delete P;
+    return nullptr;
+  }
+  if (out != nullptr && p.epi.fast) {
+    if (!halo_encode_out(d, out, &p.tmap_o)) {
+      delete P;
+      return nullptr;
+    }
+    P->out_encoded = out;
+  }
+  if (!HL_NAME(g_halo_attr_set)) {
+    if (cudaFuncSetAttribute(HL_NAME(conv_halo_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             HL_SMEM_MAX) != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(HL_NAME(conv_halo_kernel)) failed");
+      delete P;
+      return nullptr;
+    }
+    HL_NAME(g_halo_attr_set) = true;
+  }
+  return P;
+}
+
+int HL_NAME(halo_conv_launch)(const HaloConvPrepared* P, const float* bias, const void* residual, void* out,
+                     cudaStream_t st) {
+  HaloParams p = P->p;
+  p.bias = bias;
+  p.epi.res = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.epi.out = reinterpret_cast<__nv_bfloat16*>(out);
+  if (p.epi.fast && out != P->out_encoded) {       // output buffer changed since prepare
+    if (!halo_encode_out(&P->d, out, &p.tmap_o)) return BRTPE_ECUDA;
+  }
+  const bool prof = g_halo_prof != nullptr && P->grid <= g_halo_prof_ctas;
+  p.prof = prof ? g_halo_prof : nullptr;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(P->grid);
+  cfg.blockDim = dim3(HL_THREADS);
+  cfg.dynamicSmemBytes = P->smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.cg;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, HL_NAME(conv_halo_kernel), p);
+  if (e != cudaSuccess) {
+    set_error("HL_NAME(conv_halo_kernel) launch failed: %s", cudaGetErrorString(e));
+    return BRTPE_ECUDA;
+  }
+  return BRTPE_OK;
+}
+
+}  // namespace brtpe

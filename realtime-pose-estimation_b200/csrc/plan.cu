@@ -105,7 +105,7 @@ extern "C" int brtpe_conv_run(const brtpe_conv_desc* d, const void* in, const vo
   const int eng = choose_engine(d);
   if (eng < 0) return BRTPE_EINVAL;
   if (eng == BRTPE_ENGINE_UMMA_HALO) {
-    HaloConvPrepared* p = halo_conv_prepare(d, in, weights);
+    HaloConvPrepared* p = halo_conv_prepare(d, in, weights, out);
     if (!p) return BRTPE_ECUDA;
     rc = halo_conv_launch(p, bias, residual, out, (cudaStream_t)stream);
     halo_conv_release(p);
@@ -166,7 +166,7 @@ extern "C" int brtpe_plan_add_conv(brtpe_plan* pl, const brtpe_conv_desc* d, con
   op.umma = nullptr;
   op.halo = nullptr;
   if (eng == BRTPE_ENGINE_UMMA_HALO) {
-    op.halo = halo_conv_prepare(d, in, weights);
+    op.halo = halo_conv_prepare(d, in, weights, out);
     if (!op.halo) return BRTPE_ECUDA;
   } else if (eng == BRTPE_ENGINE_UMMA) {
     op.umma = umma_conv_prepare(d, in, weights);

@@ -141,6 +141,54 @@ class TeacherPipeline:
         return self.parser.decode_device(det, tag, adjust, refine)
 
     @torch.no_grad()
+    def run_stream(self, host_batches, adjust=True, refine=True):
+        """Pipelined host-facing loop over an iterable of (pinned) host batches: while batch i
+        is being computed, batch i+1 is copied host->device on a side stream into the other of
+        two persistent device buffers.  Yields the device results ``(ans, count, scores)`` of
+        every batch in order (see ``run_device``); the caller copies what it needs back."""
+        L.load()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        bufs = [None, None]                    # device input buffers (allocated on first use)
+        consumed = [None, None]                # event: compute that read bufs[k] has finished
+        state = {"k": 0}
+
+        def stage(xh):
+            k = state["k"]
+            state["k"] = k ^ 1
+            if bufs[k] is None or bufs[k].shape != xh.shape or bufs[k].dtype != xh.dtype:
+                bufs[k] = torch.empty(xh.shape, dtype=xh.dtype, device=dev)
+                consumed[k] = None
+            if consumed[k] is not None:
+                copy_stream.wait_event(consumed[k])
+            with torch.cuda.stream(copy_stream):
+                bufs[k].copy_(xh, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return k, ev
+
+        it = iter(host_batches)
+        try:
+            nxt = stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            k, ev = nxt
+            main.wait_event(ev)
+            # forward + aggregation of this batch are enqueued first, then the next copy is
+            # staged so that it overlaps them
+            det, tag = self.forward_aggregate(bufs[k])
+            done = torch.cuda.Event()
+            done.record(main)
+            consumed[k] = done
+            try:
+                nxt = stage(next(it))
+            except StopIteration:
+                nxt = None
+            yield self.parser.decode_device(det, tag, adjust, refine)
+
+    @torch.no_grad()
     def run(self, x, adjust=True, refine=True):
         """Host-facing call: ``x`` may live in (pinned) host memory.  -> list over images of
         (people (P,J,3+T) float32, scores [np.float32])."""

@@ -16,7 +16,8 @@ NAMES = ["kernel", "prologue", "prod.loop", "prod.wait_freeA", "prod.wait_freeB"
 
 
 def run(lib, n, h, w, c, reps=5):
-    d, taps = make_desc(L.DT_BF16, 0, n, h, w, c, c, 3, 1, True, res_ld=c)
+    use_res = os.environ.get("RES", "1") != "0"
+    d, taps = make_desc(L.DT_BF16, 0, n, h, w, c, c, 3, 1, True, res_ld=c if use_res else 0)
     used = lib.brtpe_conv_select_engine(C.byref(d))
     g = torch.Generator().manual_seed(0)
     x = torch.randn((n, h, w, c), generator=g).cuda().to(torch.bfloat16)
@@ -26,8 +27,8 @@ def run(lib, n, h, w, c, reps=5):
     out = torch.empty((n, h, w, d.out_ld), dtype=torch.bfloat16, device="cuda")
     packed = pack_weights(lib, wgt, taps, 3, d, used, True)
     plan = lib.brtpe_plan_create()
-    L.check(lib.brtpe_plan_add_conv(plan, C.byref(d), L.ptr(x), L.ptr(packed), L.ptr(bias), L.ptr(res),
-                                    L.ptr(out)), "add")
+    L.check(lib.brtpe_plan_add_conv(plan, C.byref(d), L.ptr(x), L.ptr(packed), L.ptr(bias),
+                                    L.ptr(res) if use_res else None, L.ptr(out)), "add")
     st = L.stream_ptr()
     for _ in range(3):
         lib.brtpe_plan_run(plan, st)
