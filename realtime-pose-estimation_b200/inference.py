@@ -117,19 +117,26 @@ class TeacherPipeline:
         self.num_joints = parser.params.num_joints
 
     @torch.no_grad()
-    def forward_aggregate(self, x):
-        """x (N,3,H,W) CUDA -> det (N,J,Hb,Wb), tag (N,A,Hb,Wb,T)."""
+    def forward_aggregate(self, x, after_forward=None):
+        """x (N,3,H,W) CUDA -> det (N,J,Hb,Wb), tag (N,A,Hb,Wb,T).  ``after_forward`` (optional
+        callable) runs on the host right after the network launches have been enqueued."""
         n, _, h, w = x.shape
         hb, wb = self.project_hw if self.project_hw is not None else (h, w)
         if self.mode == "intree":
             y0, y1 = self.model(x)
+            if after_forward is not None:
+                after_forward()
             return aggregate_intree(y0, y1, (hb, wb), self.num_joints)
         if self.flip_test:
             both = torch.cat((x, torch.flip(x, [3])), 0)
             y0, y1 = self.model(both)
+            if after_forward is not None:
+                after_forward()
             det, tag = aggregate_scale(y0[:n], y1[:n], y0[n:], y1[n:], (hb, wb), self.num_joints)
         else:
             y0, y1 = self.model(x)
+            if after_forward is not None:
+                after_forward()
             det, tag = aggregate_scale(y0, y1, None, None, (hb, wb), self.num_joints)
         return det, tag
 
@@ -142,26 +149,27 @@ class TeacherPipeline:
 
     @torch.no_grad()
     def run_stream(self, host_batches, adjust=True, refine=True):
-        """Pipelined host-facing loop over an iterable of (pinned) host batches: while batch i
-        is being computed, batch i+1 is copied host->device on a side stream into the other of
-        two persistent device buffers.  Yields the device results ``(ans, count, scores)`` of
-        every batch in order (see ``run_device``); the caller copies what it needs back."""
+        """Pipelined host-facing loop over an iterable of (pinned) host batches.  The copy of
+        batch i+1 into the other of two persistent device buffers runs on a side stream while
+        batch i is aggregated and decoded -- it is released when the network of batch i has
+        finished, because a copy that runs concurrently with the network's CUDA graph slows the
+        graph down by more than the copy takes (measured: profiles/r01e_halo_pair.md).
+        Yields the device results ``(ans, count, scores)`` of every batch in order (see
+        ``run_device``); the caller copies what it needs back."""
         L.load()
         dev = torch.device("cuda", torch.cuda.current_device())
         copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
         bufs = [None, None]                    # device input buffers (allocated on first use)
-        consumed = [None, None]                # event: compute that read bufs[k] has finished
         state = {"k": 0}
 
-        def stage(xh):
+        def stage(xh, after=None):
             k = state["k"]
             state["k"] = k ^ 1
             if bufs[k] is None or bufs[k].shape != xh.shape or bufs[k].dtype != xh.dtype:
                 bufs[k] = torch.empty(xh.shape, dtype=xh.dtype, device=dev)
-                consumed[k] = None
-            if consumed[k] is not None:
-                copy_stream.wait_event(consumed[k])
+            if after is not None:
+                copy_stream.wait_event(after)  # also orders the copy after the last reader of bufs[k]
             with torch.cuda.stream(copy_stream):
                 bufs[k].copy_(xh, non_blocking=True)
                 ev = torch.cuda.Event()
@@ -170,22 +178,22 @@ class TeacherPipeline:
 
         it = iter(host_batches)
         try:
-            nxt = stage(next(it))
+            nxt = [stage(next(it))]
         except StopIteration:
             return
-        while nxt is not None:
-            k, ev = nxt
+        while nxt[0] is not None:
+            k, ev = nxt[0]
             main.wait_event(ev)
-            # forward + aggregation of this batch are enqueued first, then the next copy is
-            # staged so that it overlaps them
-            det, tag = self.forward_aggregate(bufs[k])
-            done = torch.cuda.Event()
-            done.record(main)
-            consumed[k] = done
-            try:
-                nxt = stage(next(it))
-            except StopIteration:
-                nxt = None
+
+            def stage_next():
+                fwd_done = torch.cuda.Event()
+                fwd_done.record(main)
+                try:
+                    nxt[0] = stage(next(it), fwd_done)
+                except StopIteration:
+                    nxt[0] = None
+
+            det, tag = self.forward_aggregate(bufs[k], after_forward=stage_next)
             yield self.parser.decode_device(det, tag, adjust, refine)
 
     @torch.no_grad()
