@@ -316,6 +316,11 @@ def run_ours(args, rank, world, local_rank):
     # dominant kernel: the 3x3/s1 tcgen05 halo kernel (kind 3); the per-tap tcgen05 kernel (1x1,
     # stride 2, deconv phases, stem) is reported beside it
     roofline = conv_roofline((3,), "conv_halo_kernel (tcgen05 implicit GEMM, 3x3 s1)")
+    if args.mode == "fp32":
+        # fp32 mode has no tensor-core kernel (<= 1e-4 rules out single-pass TF32/bf16): the
+        # CUDA-core FFMA kernel is the dominant one; the tensor peak is kept as denominator
+        roofline = conv_roofline((1,), "conv_ffma_kernel (fp32 FFMA implicit GEMM)")
+        roofline["note"] = "fp32 CUDA-core path; frac is against the bf16 tensor peak"
     roofline_other = conv_roofline((0,), "conv_umma_kernel (tcgen05 implicit GEMM, 1x1 / s2 / deconv)")
     roofline["conv_share_of_forward"] = conv_ms / max(sum(ms_ops), 1e-9)
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")

@@ -141,6 +141,34 @@ class TeacherPipeline:
         return det, tag
 
     @torch.no_grad()
+    def forward_aggregate_multiscale(self, inputs_by_scale, base_hw):
+        """Multi-scale test protocol of legacy/valid_ae_avg.py:159-205: ``inputs_by_scale`` is a
+        list of ``(scale, x_scale)`` with x_scale (N,3,Hs,Ws) CUDA -- the image batch already
+        resized for that scale (the reference does it with resize_align_multi_scale) --
+        visited in the order given (the reference visits descending scales).  Every scale runs
+        the network on the image and, with ``flip_test``, on its mirror; heat-maps are
+        projected to ``base_hw`` = (H, W), summed over scales and divided by their number,
+        tags come from the scale-1.0 pass.  -> det (N,J,H,W), tag (N,A,H,W,T)."""
+        hb, wb = int(base_hw[0]), int(base_hw[1])
+        ns = len(inputs_by_scale)
+        det, tag = None, None
+        for k, (scale, x) in enumerate(inputs_by_scale):
+            n = x.shape[0]
+            if self.flip_test:
+                y0, y1 = self.model(torch.cat((x, torch.flip(x, [3])), 0))
+                outs, outs_f = (y0[:n], y1[:n]), (y0[n:], y1[n:])
+            else:
+                outs, outs_f = tuple(self.model(x)), (None, None)
+            want_tags = (scale == 1) or ns == 1
+            det, tg = aggregate_scale(outs[0], outs[1], outs_f[0], outs_f[1], (hb, wb),
+                                      self.num_joints, det=det, accumulate=k > 0,
+                                      final_div=float(ns) if k == ns - 1 else 0.0,
+                                      want_tags=want_tags)
+            if want_tags:
+                tag = tg
+        return det, tag
+
+    @torch.no_grad()
     def run_device(self, x, adjust=True, refine=True):
         """-> ans (N,Pmax,J,3+T), count (N), scores (N,Pmax): CUDA tensors, no host sync
         besides the parser's capacity check."""
