@@ -247,6 +247,26 @@ int brtpe_plan_graph_launch(brtpe_plan*, void* stream);
 int brtpe_plan_profile(brtpe_plan*, void* stream, float* ms_out, int32_t* kinds_out,
                        double* flops_out);
 
+/* ---- context-aware-module student (rtpe/students.py:118-201, :595-771; BASELINE config 4)
+ * Small NHWC streaming ops, dtype = BRTPE_DT_* of the activations.  iparams[0] is always the
+ * dtype; `kind` and the remaining parameters:
+ *  1 AvgPool2d(3,2,1,count_include_pad=False) (students.py:657): in0 (N,H,W,in_ld) -> out
+ *    (N,H/2,W/2,out_ld);                       iparams = {dtype, N, H, W, C, in_ld, out_ld}
+ *  2 SELayer pooling, stage 1 (students.py:137-139): in0 (N,HW,ld) -> out float
+ *    partial[N][chunks][C];                    iparams = {dtype, N, HW, C, ld, chunks}
+ *  3 SELayer gate (students.py:129-141): in0 = partial, in1 = float [W1 (hid x C), b1 (hid),
+ *    W2 (C x hid), b2 (C)] -> out float gate[N][C] = sigmoid(W2 relu(W1 mean + b1) + b2);
+ *                                              iparams = {dtype, N, C, hid, chunks, HW}
+ *  4 ContextAwareModule tail (students.py:199-200): out = relu(in0 + in1 * gate), in2 = gate;
+ *                                              iparams = {dtype, N, HW, C, ld0, ld1, ld_out}
+ *  5 attention injection (students.py:752-753): a = sigmoid(in0[...,0] / 20); out = in1 + a;
+ *    in2 = float att_out (N,H,W) written with a; iparams = {dtype, N, HW, C, ld_att, ld_in1, ld_out}
+ */
+int brtpe_aux_run(int kind, const void* in0, const void* in1, const void* in2, void* out,
+                  const int32_t* iparams, int nparams, void* stream);
+int brtpe_plan_add_aux(brtpe_plan*, int kind, const void* in0, const void* in1, const void* in2,
+                       void* out, const int32_t* iparams, int nparams);
+
 /* ---- debug instrumentation (not part of the reference surface)
  * While `buf` is non-NULL every conv_halo_kernel launch with <= max_ctas CTAs runs its
  * instrumented instantiation and writes 16 int64 cycle counters per CTA to

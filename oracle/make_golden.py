@@ -19,7 +19,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from oracle.ref_loader import load_reference  # noqa: E402
+from oracle.ref_loader import load_reference, load_reference_students  # noqa: E402
 from oracle.weights import fill_params_deterministic  # noqa: E402
 import rtpe_b200  # noqa: E402  (only its torch-side synthetic generator is used)
 
@@ -76,6 +76,21 @@ def model_fixture(ref_model, name, h, w, seed):
     print(name, tuple(y0.shape), tuple(y1.shape), float(y0.abs().max()), float(y1.abs().max()))
 
 
+def student_fixture(ref_students, name, h, w, seed):
+    """AttentionStudent (rtpe/students.py:595-771), BASELINE config 4 hyper-parameters."""
+    torch.manual_seed(0)
+    net = ref_students.AttentionStudent(None, "cpu", inplanes=48, num_heatmaps=17, ae_dims=1,
+                                        half_precision=False).eval()
+    fill_params_deterministic(net, seed)
+    x = torch.randn(2, 3, h, w, generator=torch.Generator().manual_seed(seed + 1))
+    with torch.no_grad():
+        att, det = net(x)
+    np.savez_compressed(os.path.join(OUT, name), x=x.numpy(), att=att.numpy(), det=det.numpy(),
+                        seed=np.int64(seed), entries=np.int64(len(net.state_dict())))
+    print(name, tuple(att.shape), tuple(det.shape), float(att.min()), float(att.max()),
+          float(det.abs().max()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref_group, ref_model = load_reference()
@@ -85,6 +100,7 @@ def main():
                    tag_scale=0.25)
     decode_fixture(ref_group, "decode_shared_tag.npz", 2, 48, 56, 1, 4, seed=24, tag_per_joint=False)
     model_fixture(ref_model, "hhrnet_64x96.npz", 64, 96, seed=7)
+    student_fixture(load_reference_students(), "student_64x96.npz", 64, 96, seed=9)
 
 
 if __name__ == "__main__":

@@ -37,3 +37,13 @@ def load_reference():
         import rtpe.third_party.group as ref_group
         import rtpe.third_party.pose_higher_hrnet as ref_model
     return ref_group, ref_model
+
+
+def load_reference_students():
+    """-> rtpe.students of the unmodified reference (students.py:595 AttentionStudent)."""
+    load_reference()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import rtpe.students as ref_students
+    return ref_students

@@ -1,0 +1,100 @@
+"""ORACLE (test infrastructure only) -- functional CPU restatement of
+``AttentionStudent.forward`` (rtpe/students.py:733-768) and the blocks it calls:
+``StemHRNet.forward`` (:252-264; Bottleneck = pose_higher_hrnet.py:78-116), ``mid_stem``
+(:617-629), ``ContextAwareModule.forward`` (:181-201), ``SELayer.forward`` (:137-142), the
+attention / detection pyramids (:653-713).
+
+It consumes a plain ``state_dict`` with the reference's key names and evaluates the student with
+torch CPU operators in a chosen dtype, eval-mode BatchNorm.  Quirks of the reference that are
+kept on purpose: ``mid`` and ``lo`` of both pyramids are the SAME upsampled ``lo`` map (so the sum
+is hi + 2*up(lo)), ``det_hi`` is applied twice to the same input and ``det_mid`` is never used
+(:756-761), the returned attention map is ``sigmoid(att / 20)`` (:752).
+
+Pinned against the reference class itself (same weights, same input) in
+tests/test_oracle_vs_reference.py and through tests/golden/student_64x96.npz.
+Only tests/, smoke() and bench.py's CPU-baseline legs may import this.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+EPS = 1e-5
+
+
+def _bn(x, sd, p):
+    return F.batch_norm(x, sd[p + ".running_mean"].to(x.dtype), sd[p + ".running_var"].to(x.dtype),
+                        sd[p + ".weight"].to(x.dtype), sd[p + ".bias"].to(x.dtype), False, 0.0, EPS)
+
+
+def _conv(x, sd, p, stride=1, padding=0, dilation=1):
+    b = sd.get(p + ".bias")
+    return F.conv2d(x, sd[p + ".weight"].to(x.dtype), None if b is None else b.to(x.dtype),
+                    stride=stride, padding=padding, dilation=dilation)
+
+
+def _bottleneck(x, sd, p):
+    """pose_higher_hrnet.py:96-116."""
+    out = F.relu(_bn(_conv(x, sd, p + ".conv1"), sd, p + ".bn1"))
+    out = F.relu(_bn(_conv(out, sd, p + ".conv2", padding=1), sd, p + ".bn2"))
+    out = _bn(_conv(out, sd, p + ".conv3"), sd, p + ".bn3")
+    res = x
+    if (p + ".downsample.0.weight") in sd:
+        res = _bn(_conv(x, sd, p + ".downsample.0"), sd, p + ".downsample.1")
+    return F.relu(out + res)
+
+
+def stem_ref(sd, x, p="stem.1"):
+    """students.py:252-264."""
+    x = F.relu(_bn(_conv(x, sd, p + ".conv1", stride=2, padding=1), sd, p + ".bn1"))
+    x = F.relu(_bn(_conv(x, sd, p + ".conv2", stride=2, padding=1), sd, p + ".bn2"))
+    for i in range(4):
+        x = _bottleneck(x, sd, "%s.layer1.%d" % (p, i))
+    return x
+
+
+def cam_ref(sd, x, p):
+    """students.py:181-201 (no HDC upsampling: the dilated convs keep the size)."""
+    residual = F.relu(_bn(_conv(x, sd, p + ".residual.0"), sd, p + ".residual.1"))
+    y = x.mean(dim=(2, 3))                                                    # AdaptiveAvgPool2d(1)
+    y = F.relu(F.linear(y, sd[p + ".se.fc.0.weight"].to(x.dtype), sd[p + ".se.fc.0.bias"].to(x.dtype)))
+    y = torch.sigmoid(F.linear(y, sd[p + ".se.fc.2.weight"].to(x.dtype), sd[p + ".se.fc.2.bias"].to(x.dtype)))
+    outs = []
+    i = 0
+    while (p + ".hdcs.%d.0.weight" % i) in sd:
+        d = i + 1                                                             # dilations 1..n (:659,:688)
+        outs.append(F.relu(_bn(_conv(x, sd, p + ".hdcs.%d.0" % i, padding=d, dilation=d), sd,
+                               p + ".hdcs.%d.1" % i)))
+        i += 1
+    out = F.relu(_bn(_conv(torch.cat(outs, dim=1), sd, p + ".hdc_top.0"), sd, p + ".hdc_top.1"))
+    return F.relu(residual + out * y[:, :, None, None])
+
+
+def _pool(x):
+    return F.avg_pool2d(x, kernel_size=3, stride=2, padding=1, count_include_pad=False)
+
+
+@torch.no_grad()
+def attention_student_forward_ref(state_dict, x, dtype=torch.float32):
+    """-> (att (N,1,H/4,W/4), det (N,C,H/4,W/4)) like AttentionStudent.forward."""
+    sd = state_dict
+    x = x.to(dtype)
+    s = stem_ref(sd, x)
+    s = F.relu(_bn(_conv(s, sd, "mid_stem.0", padding=1), sd, "mid_stem.1"))
+    s = F.relu(_bn(_conv(s, sd, "mid_stem.3", padding=1), sd, "mid_stem.4"))
+    hw = s.shape[-2:]
+    hi = cam_ref(sd, s, "att_hi.0")
+    mid = cam_ref(sd, _pool(s), "att_mid.1")
+    lo = cam_ref(sd, _pool(mid), "att_lo.1")
+    lo_up = F.interpolate(lo, hw, mode="nearest")
+    att = hi + lo_up + lo_up
+    att = _conv(att, sd, "att_top.0", padding=1)
+    att = torch.sigmoid(att / 20)
+    s = s + att.expand(s.shape)
+    hi = cam_ref(sd, s, "det_hi.0")
+    mid = hi                                            # det_hi applied twice to the same input
+    lo = cam_ref(sd, _pool(mid), "det_lo.1")
+    lo_up = F.interpolate(lo, hw, mode="nearest")
+    det = hi + lo_up + lo_up
+    det = _conv(det, sd, "det_top.0", padding=1)
+    return att, det

@@ -22,6 +22,8 @@ def fill_params_deterministic(module: torch.nn.Module, seed: int = 0):
         if t.dim() == 4:                                     # conv / deconv weight
             fan_in = t.shape[1] * t.shape[2] * t.shape[3]
             v = torch.randn(t.shape, generator=g) * (0.3 / fan_in) ** 0.5
+        elif t.dim() == 2:                                   # Linear weight (SE layers)
+            v = torch.randn(t.shape, generator=g) * (1.0 / t.shape[1]) ** 0.5
         elif leaf == "running_var":
             v = torch.rand(t.shape, generator=g) * 0.5 + 0.75
         elif leaf == "running_mean":

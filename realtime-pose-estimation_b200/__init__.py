@@ -11,4 +11,5 @@ from .hhrnet import PoseHigherResolutionNet, BasicBlock, Bottleneck, HighResolut
     NoOpModule  # noqa: F401
 from .precision import network_to_half, tofp16, tofp32, BN_convert_float, \
     get_hrnet_w48_teacher, W48_KWARGS  # noqa: F401
+from .students import AttentionStudent, ContextAwareModule, SELayer, StemHRNet  # noqa: F401
 from ._lib import BrtpeError, LIB_PATH  # noqa: F401

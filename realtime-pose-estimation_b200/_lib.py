@@ -94,6 +94,8 @@ _SIGS = {
     "brtpe_plan_run": (_I, [_P, _P]),
     "brtpe_plan_graph_launch": (_I, [_P, _P]),
     "brtpe_debug_halo_prof": (_I, [_P, _I]),
+    "brtpe_aux_run": (_I, [_I, _P, _P, _P, _P, C.POINTER(C.c_int32), _I, _P]),
+    "brtpe_plan_add_aux": (_I, [_P, _I, _P, _P, _P, _P, C.POINTER(C.c_int32), _I]),
     "brtpe_plan_profile": (_I, [_P, _P, C.POINTER(C.c_float), C.POINTER(C.c_int32),
                                 C.POINTER(C.c_double)]),
 }

@@ -8,7 +8,9 @@
 
 namespace brtpe {
 
-enum OpKind { OP_CONV = 0, OP_STEM = 1, OP_FUSE = 2, OP_TONCHW = 3, OP_IM2COL = 4 };
+enum OpKind { OP_CONV = 0, OP_STEM = 1, OP_FUSE = 2, OP_TONCHW = 3, OP_IM2COL = 4, OP_AUX = 5 };
+int aux_launch(int kind, const void* in0, const void* in1, const void* in2, void* out,
+               const int32_t* ip, cudaStream_t st);   // student_ops.cu
 constexpr int PLAN_MAX_LANES = 8;
 
 struct Op {
@@ -72,6 +74,8 @@ static int run_op(const Op& op, cudaStream_t st) {
                                  op.i[6], op.out, op.i[7], st);
     case OP_IM2COL:
       return stem_im2col_launch(op.in, op.i[0], op.i[1], op.i[2], op.i[3], op.out, st);
+    case OP_AUX:
+      return aux_launch(op.i[8], op.terms[0], op.terms[1], op.terms[2], op.out, op.i, st);
   }
   return BRTPE_EINVAL;
 }
@@ -227,6 +231,20 @@ extern "C" int brtpe_plan_add_stem_im2col(brtpe_plan* pl, const void* img, int i
   op.kind = OP_IM2COL;
   op.in = img; op.out = out;
   op.i[0] = img_is_half; op.i[1] = N; op.i[2] = H; op.i[3] = W;
+  pl->ops.push_back(op);
+  return BRTPE_OK;
+}
+
+extern "C" int brtpe_plan_add_aux(brtpe_plan* pl, int kind, const void* in0, const void* in1,
+                                  const void* in2, void* out, const int32_t* iparams, int nparams) {
+  BRTPE_CHECK_ARG(pl && in0 && out && iparams && nparams >= 4 && nparams <= 8,
+                  "brtpe_plan_add_aux: bad arguments");
+  Op op{};
+  op.kind = OP_AUX;
+  op.terms[0] = in0; op.terms[1] = in1; op.terms[2] = in2;
+  op.out = out;
+  for (int i = 0; i < nparams; ++i) op.i[i] = iparams[i];
+  op.i[8] = kind;
   pl->ops.push_back(op);
   return BRTPE_OK;
 }

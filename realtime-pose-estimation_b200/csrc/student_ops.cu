@@ -1,0 +1,196 @@
+// Small NHWC kernels of the context-aware-module student (rtpe/students.py, config 4):
+//   * AvgPool2d(3, stride 2, padding 1, count_include_pad=False)   (students.py:657-658)
+//   * SELayer: global average pool -> Linear -> ReLU -> Linear -> Sigmoid, returned as a gate
+//     per (image, channel)                                          (students.py:118-142)
+//   * ContextAwareModule tail: relu(residual + hdc * gate)          (students.py:197-201)
+//   * attention injection: stem_out + sigmoid(att / 20)             (students.py:752-753)
+// All are bandwidth-bound streaming kernels over NHWC activations (fp32 or bf16, the precision
+// mode of the plan); reductions are two-stage and deterministic (no atomics).
+#include "conv_common.cuh"
+
+namespace brtpe {
+
+enum AuxKind { AUX_AVGPOOL = 1, AUX_SE_PARTIAL = 2, AUX_SE_GATE = 3, AUX_CAM_MIX = 4, AUX_ATT_ADD = 5 };
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+avgpool3s2_kernel(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C,
+                  int in_ld, int out_ld) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = (size_t)N * Ho * Wo * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    size_t p = i / C;
+    const int xo = (int)(p % Wo);
+    p /= Wo;
+    const int yo = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    float s = 0.0f;
+    int cnt = 0;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int y = 2 * yo + dy;
+      if (y < 0 || y >= H) continue;
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int x = 2 * xo + dx;
+        if (x < 0 || x >= W) continue;
+        s += to_f32(in[(((size_t)n * H + y) * W + x) * in_ld + c]);
+        ++cnt;
+      }
+    }
+    out[(((size_t)n * Ho + yo) * Wo + xo) * out_ld + c] = from_f32<T>(s / (float)cnt);
+  }
+}
+
+// partial[n][chunk][c] = sum over the chunk's pixels of in[n][p][c]
+template <typename T>
+__global__ void __launch_bounds__(256)
+se_partial_kernel(const T* __restrict__ in, float* __restrict__ partial, int HW, int C, int ld,
+                  int chunks) {
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int per = (HW + chunks - 1) / chunks;
+  const int p0 = chunk * per, p1 = min(HW, p0 + per);
+  __shared__ float red[256];
+  // thread t owns channel t % C of pixel rows t / C, t / C + rows, ...
+  const int rows = max(1, 256 / C);
+  const int c = threadIdx.x % C, r = threadIdx.x / C;
+  float s = 0.0f;
+  if (r < rows)
+    for (int p = p0 + r; p < p1; p += rows) s += to_f32(in[((size_t)n * HW + p) * ld + c]);
+  red[threadIdx.x] = (r < rows) ? s : 0.0f;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float t = 0.0f;
+    for (int k = 0; k < rows; ++k) t += red[k * C + threadIdx.x];   // fixed order
+    partial[((size_t)n * chunks + chunk) * C + threadIdx.x] = t;
+  }
+}
+
+// gate[n][c] = sigmoid(W2 relu(W1 mean + b1) + b2); fc = [W1 (hid x C), b1 (hid), W2 (C x hid), b2 (C)]
+__global__ void __launch_bounds__(128)
+se_gate_kernel(const float* __restrict__ partial, const float* __restrict__ fc,
+               float* __restrict__ gate, int C, int hid, int chunks, int HW) {
+  const int n = blockIdx.x;
+  __shared__ float mean[128], h[128];
+  const int t = threadIdx.x;
+  if (t < C) {
+    float s = 0.0f;
+    for (int k = 0; k < chunks; ++k) s += partial[((size_t)n * chunks + k) * C + t];
+    mean[t] = s / (float)HW;
+  }
+  __syncthreads();
+  const float* w1 = fc;
+  const float* b1 = w1 + (size_t)hid * C;
+  const float* w2 = b1 + hid;
+  const float* b2 = w2 + (size_t)C * hid;
+  if (t < hid) {
+    float s = b1[t];
+    for (int k = 0; k < C; ++k) s += w1[t * C + k] * mean[k];
+    h[t] = fmaxf(s, 0.0f);
+  }
+  __syncthreads();
+  if (t < C) {
+    float s = b2[t];
+    for (int k = 0; k < hid; ++k) s += w2[t * hid + k] * h[k];
+    gate[(size_t)n * C + t] = 1.0f / (1.0f + expf(-s));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+cam_mix_kernel(const T* __restrict__ res, const T* __restrict__ hdc, const float* __restrict__ gate,
+               T* __restrict__ out, int N, int HW, int C, int ld_res, int ld_hdc, int ld_out) {
+  const size_t total = (size_t)N * HW * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const size_t p = i / C;
+    const int n = (int)(p / HW);
+    const float v = to_f32(res[p * ld_res + c]) + to_f32(hdc[p * ld_hdc + c]) * gate[(size_t)n * C + c];
+    out[p * ld_out + c] = from_f32<T>(fmaxf(v, 0.0f));
+  }
+}
+
+// att_out[p] = sigmoid(att[p][0] / 20)  (float, = NCHW with one channel);
+// out[p][c] = stem[p][c] + att_out[p]
+template <typename T>
+__global__ void __launch_bounds__(256)
+att_add_kernel(const T* __restrict__ att, const T* __restrict__ stem, T* __restrict__ out,
+               float* __restrict__ att_out, size_t P, int C, int ld_att, int ld_stem, int ld_out) {
+  const size_t total = P * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const size_t p = i / C;
+    const float a = 1.0f / (1.0f + expf(-to_f32(att[p * ld_att]) / 20.0f));
+    if (c == 0) att_out[p] = a;
+    out[p * ld_out + c] = from_f32<T>(to_f32(stem[p * ld_stem + c]) + a);
+  }
+}
+
+static int grid_for(size_t total) {
+  size_t b = (total + 255) / 256;
+  const size_t cap = (size_t)num_sms() * 16;
+  return (int)(b < cap ? (b ? b : 1) : cap);
+}
+
+// ip: kind-specific integer parameters (see the brtpe_aux_run documentation in brtpe.h)
+int aux_launch(int kind, const void* in0, const void* in1, const void* in2, void* out,
+               const int32_t* ip, cudaStream_t st) {
+  const bool bf = ip[0] == BRTPE_DT_BF16;
+  switch (kind) {
+    case AUX_AVGPOOL: {
+      const int N = ip[1], H = ip[2], W = ip[3], C = ip[4], ild = ip[5], old = ip[6];
+      BRTPE_CHECK_ARG(N > 0 && H >= 2 && W >= 2 && !(H & 1) && !(W & 1) && C > 0, "avgpool: bad shape");
+      const int g = grid_for((size_t)N * (H / 2) * (W / 2) * C);
+      if (bf) avgpool3s2_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in0, (__nv_bfloat16*)out, N, H, W, C, ild, old);
+      else avgpool3s2_kernel<float><<<g, 256, 0, st>>>((const float*)in0, (float*)out, N, H, W, C, ild, old);
+      break;
+    }
+    case AUX_SE_PARTIAL: {
+      const int N = ip[1], HW = ip[2], C = ip[3], ld = ip[4], chunks = ip[5];
+      BRTPE_CHECK_ARG(N > 0 && HW > 0 && C > 0 && C <= 128 && chunks > 0, "se_partial: bad shape");
+      dim3 grid(chunks, N);
+      if (bf) se_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in0, (float*)out, HW, C, ld, chunks);
+      else se_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)in0, (float*)out, HW, C, ld, chunks);
+      break;
+    }
+    case AUX_SE_GATE: {
+      const int N = ip[1], C = ip[2], hid = ip[3], chunks = ip[4], HW = ip[5];
+      BRTPE_CHECK_ARG(N > 0 && C > 0 && C <= 128 && hid > 0 && hid <= 128, "se_gate: bad shape");
+      se_gate_kernel<<<N, 128, 0, st>>>((const float*)in0, (const float*)in1, (float*)out, C, hid, chunks, HW);
+      break;
+    }
+    case AUX_CAM_MIX: {
+      const int N = ip[1], HW = ip[2], C = ip[3];
+      const int g = grid_for((size_t)N * HW * C);
+      if (bf) cam_mix_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in0, (const __nv_bfloat16*)in1, (const float*)in2, (__nv_bfloat16*)out, N, HW, C, ip[4], ip[5], ip[6]);
+      else cam_mix_kernel<float><<<g, 256, 0, st>>>((const float*)in0, (const float*)in1, (const float*)in2, (float*)out, N, HW, C, ip[4], ip[5], ip[6]);
+      break;
+    }
+    case AUX_ATT_ADD: {
+      const size_t P = (size_t)ip[1] * ip[2];
+      const int C = ip[3];
+      const int g = grid_for(P * C);
+      float* att_out = (float*)const_cast<void*>(in2);
+      if (bf) att_add_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in0, (const __nv_bfloat16*)in1, (__nv_bfloat16*)out, att_out, P, C, ip[4], ip[5], ip[6]);
+      else att_add_kernel<float><<<g, 256, 0, st>>>((const float*)in0, (const float*)in1, (float*)out, att_out, P, C, ip[4], ip[5], ip[6]);
+      break;
+    }
+    default:
+      set_error("brtpe_aux_run: unknown kind %d", kind);
+      return BRTPE_EINVAL;
+  }
+  BRTPE_LAUNCH_CHECK();
+  return BRTPE_OK;
+}
+
+}  // namespace brtpe
+
+extern "C" int brtpe_aux_run(int kind, const void* in0, const void* in1, const void* in2, void* out,
+                             const int32_t* iparams, int nparams, void* stream) {
+  BRTPE_CHECK_ARG(in0 && out && iparams && nparams >= 4 && nparams <= 8, "brtpe_aux_run: bad arguments");
+  int32_t ip[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < nparams; ++i) ip[i] = iparams[i];
+  return brtpe::aux_launch(kind, in0, in1, in2, out, ip, (cudaStream_t)stream);
+}

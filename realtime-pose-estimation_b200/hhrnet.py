@@ -247,15 +247,17 @@ class _Recorder:
         """conv (+BN) (+residual) (+ReLU) over virtual tensor x -> virtual tensor."""
         k = conv.kernel_size[0]
         s = conv.stride[0]
+        dil = conv.dilation[0]                       # dilated 3x3 = the same taps, spread out
         cin, cout = conv.in_channels, conv.out_channels
         cin_store = cin if cin_store is None else cin_store
         cout_store = cout if cout_store is None else cout_store
         ho, wo = x.h // s, x.w // s
         if out is None:
             out = self.new(x.n, ho, wo, (cout_store + 15) // 16 * 16)
-        taps = _TAPS3 if k == 3 else [(0, 0)]
+        taps = [(dy * dil, dx * dil) for dy, dx in _TAPS3] if k == 3 else [(0, 0)]
         w, b = self._fold(conv, bn)
-        wt = torch.stack([w[:, :, dy + (k // 2), dx + (k // 2)] for dy, dx in taps], 0)
+        ktaps = _TAPS3 if k == 3 else [(0, 0)]
+        wt = torch.stack([w[:, :, dy + (k // 2), dx + (k // 2)] for dy, dx in ktaps], 0)
         d = self._desc(x, in_coff, cin_store, taps, s, ho, wo, out, 1, 0, 0, cout, cout_store,
                        out_coff, residual, relu)
         self._emit_conv(d, x, wt, b, residual, out, cin_store)
@@ -363,6 +365,15 @@ class _Recorder:
         self._touch(out, idx)
         return out
 
+    def aux(self, kind, reads, writes, in0, in1, in2, out, iparams):
+        """Student-only NHWC op (brtpe_plan_add_aux).  in*/out: virtual tensors or raw torch
+        tensors (weights, float side buffers)."""
+        idx = len(self.ops)
+        self.ops.append(("aux", kind, in0, in1, in2, out, [int(v) for v in iparams]))
+        self._sched(list(reads), list(writes))
+        for t in list(reads) + list(writes):
+            self._touch(t, idx)
+
     def to_nchw(self, x, c, coff, dst):
         idx = len(self.ops)
         self.ops.append(("nchw", x, c, coff, dst))
@@ -464,6 +475,16 @@ class _Recorder:
                         plan, self.dt, L.ptr(x.buf[1]), x.n, x.h, x.w, c, x.ld, coff,
                         L.ptr(dst), int(dst.dtype == torch.float16)),
                         "brtpe_plan_add_nhwc_to_nchw")
+                elif kind == "aux":
+                    _, akind, in0, in1, in2, out, ip = op
+
+                    def _p(t):
+                        if t is None:
+                            return None
+                        return L.ptr(t.buf[1]) if isinstance(t, _T) else L.ptr(t)
+                    arr = (C.c_int32 * len(ip))(*ip)
+                    L.check(lib.brtpe_plan_add_aux(plan, akind, _p(in0), _p(in1), _p(in2), _p(out),
+                                                   arr, len(ip)), "brtpe_plan_add_aux")
                 elif kind == "im2col":
                     _, cols = op
                     L.check(lib.brtpe_plan_add_stem_im2col(
@@ -498,7 +519,124 @@ class _CompiledPlan:
             pass
 
 
-class PoseHigherResolutionNet(nn.Module):
+class _PlanRunner:
+    """Shared execution machinery of the drop-in modules: a module records itself once per
+    (chunk, H, W, precision) as a native launch plan (``_record``) and ``forward`` replays the
+    plan (CUDA graph) per chunk of images.  Sub-classes provide ``_record`` and ``_ref_param``
+    (any parameter: its dtype selects the precision mode, its device the GPU)."""
+
+    def _init_runner(self):
+        # execution options (not part of the reference API)
+        self.chunk_size = 8            # images per plan replay
+        self.conv_engine = L.ENGINE_AUTO
+        self.use_cuda_graph = True
+        self.parallel_branches = True  # resolution branches = parallel branches of the CUDA graph
+        self._plans = {}
+        self._sig = None
+        self._frozen = False
+
+    # compiled plans own native handles and device arenas: never copied / pickled
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_plans"] = {}
+        state["_sig"] = None
+        return state
+
+    def invalidate_plans(self):
+        """Drop the compiled plans (packed weights are rebuilt at the next forward)."""
+        self._plans = {}
+        self._sig = None
+
+    def _signature(self):
+        """Cheap fingerprint of every parameter / buffer (storage address + in-place version
+        counter): load_state_dict, .half(), .to() and optimizer steps all change it."""
+        acc = 0
+        for t in list(self.parameters()) + list(self.buffers()):
+            acc = (acc * 1000003 + t.data_ptr() * 31 + t._version) & 0xFFFFFFFFFFFFFFFF
+        return acc
+
+    def freeze(self, frozen=True):
+        """Skip the per-forward parameter fingerprint (weights promised not to change)."""
+        self._frozen = bool(frozen)
+        return self
+
+    def _mode(self):
+        return "fp32" if self._ref_param().dtype == torch.float32 else "bf16"
+
+    def _get_plan(self, n, h, w, mode, device, in_dtype):
+        key = (n, h, w, mode, str(device), in_dtype, self.conv_engine, self.parallel_branches)
+        plan = self._plans.get(key)
+        if plan is None:
+            in_is_half = in_dtype == torch.float16
+            in_buf = torch.empty((n, 3, h, w), dtype=in_dtype, device=device)
+            with torch.cuda.device(device):
+                R, outs = self._record(n, h, w, mode, device, in_is_half, in_is_half)
+                handle = R.build(in_buf)
+            plan = _CompiledPlan(handle, in_buf, outs, R)
+            self._plans[key] = plan
+        return plan
+
+    def _run_plans(self, x, size_multiple):
+        lib = L.load()
+        if not isinstance(x, torch.Tensor) or not x.is_cuda:
+            raise L.BrtpeError("%s.forward needs a CUDA tensor (no CPU fallback); got %r"
+                               % (type(self).__name__, getattr(x, "device", type(x)),))
+        if self.training:
+            raise L.BrtpeError("this implementation is inference-only: call .eval() "
+                               "(BatchNorm is folded with its running statistics)")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError("expected input (N, 3, H, W), got %s" % (tuple(x.shape),))
+        n, _, h, w = x.shape
+        if h % size_multiple or w % size_multiple:
+            raise ValueError("H and W must be multiples of %d (got %dx%d)" % (size_multiple, h, w))
+        if x.dtype == torch.bfloat16:
+            x = x.to(torch.float32)
+        if x.dtype not in (torch.float32, torch.float16):
+            raise ValueError("input dtype must be float32 or float16")
+        mode = self._mode()
+        dev = x.device
+        x = x.contiguous()
+        if not self._frozen or self._sig is None:
+            sig = self._signature()
+            if sig != self._sig:
+                self._plans = {}
+                self._sig = sig
+        nb = min(self.chunk_size, n)
+        odt = torch.float16 if x.dtype == torch.float16 else torch.float32
+        results = None
+        with torch.cuda.device(dev):
+            st = L.stream_ptr(dev)
+            for s0 in range(0, n, nb):
+                cn = min(nb, n - s0)
+                plan = self._get_plan(cn, h, w, mode, dev, x.dtype)
+                plan.in_buf.copy_(x[s0:s0 + cn])
+                if self.use_cuda_graph:
+                    L.check(lib.brtpe_plan_graph_launch(plan.handle, st), "brtpe_plan_graph_launch")
+                else:
+                    L.check(lib.brtpe_plan_run(plan.handle, st), "brtpe_plan_run")
+                if results is None:
+                    results = [torch.empty((n,) + tuple(o.shape[1:]), dtype=o.dtype, device=dev)
+                               for o in plan.outs]
+                for r, o in zip(results, plan.outs):
+                    r[s0:s0 + cn].copy_(o)
+        return results
+
+    def plan_profile(self, n, h, w, in_dtype=torch.float32):
+        """Per-launch device times of one plan replay: (ms[], kind[], flops[])."""
+        lib = L.load()
+        dev = self._ref_param().device
+        plan = self._get_plan(n, h, w, self._mode(), dev, in_dtype)
+        k = plan.num_ops
+        ms = (C.c_float * k)()
+        kinds = (C.c_int32 * k)()
+        fl = (C.c_double * k)()
+        with torch.cuda.device(dev):
+            L.check(lib.brtpe_plan_profile(plan.handle, L.stream_ptr(dev), ms, kinds, fl),
+                    "brtpe_plan_profile")
+        return list(ms), list(kinds), list(fl)
+
+
+class PoseHigherResolutionNet(_PlanRunner, nn.Module):
     """Same constructor and ``forward(x) -> [y0, y1]`` as the reference
     (pose_higher_hrnet.py:266-287, :637-686)."""
 
@@ -590,14 +728,7 @@ class PoseHigherResolutionNet(nn.Module):
         self.deconv_cat = deconv_cat
         self.num_joints = num_joints
 
-        # execution options (not part of the reference API)
-        self.chunk_size = 8            # images per plan replay (keeps a layer's in+out in L2)
-        self.conv_engine = L.ENGINE_AUTO
-        self.use_cuda_graph = True
-        self.parallel_branches = True  # resolution branches = parallel branches of the CUDA graph
-        self._plans = {}
-        self._sig = None
-        self._frozen = False
+        self._init_runner()
 
     # ---------------------------------------------------------------- construction helpers
     def _make_layer(self, block, planes, blocks, stride=1):
@@ -630,31 +761,8 @@ class PoseHigherResolutionNet(nn.Module):
                 out.append(nn.Sequential(*chain))
         return nn.ModuleList(out)
 
-    # compiled plans own native handles and device arenas: never copied / pickled
-    def __getstate__(self):
-        state = dict(self.__dict__)
-        state["_plans"] = {}
-        state["_sig"] = None
-        return state
-
-    # ---------------------------------------------------------------- weights bookkeeping
-    def invalidate_plans(self):
-        """Drop the compiled plans (packed weights are rebuilt at the next forward)."""
-        self._plans = {}
-        self._sig = None
-
-    def _signature(self):
-        """Cheap fingerprint of every parameter / buffer (storage address + in-place version
-        counter): load_state_dict, .half(), .to() and optimizer steps all change it."""
-        acc = 0
-        for t in list(self.parameters()) + list(self.buffers()):
-            acc = (acc * 1000003 + t.data_ptr() * 31 + t._version) & 0xFFFFFFFFFFFFFFFF
-        return acc
-
-    def freeze(self, frozen=True):
-        """Skip the per-forward parameter fingerprint (weights promised not to change)."""
-        self._frozen = bool(frozen)
-        return self
+    def _ref_param(self):
+        return self.conv1.weight
 
     def init_weights(self, pretrained="", verbose=True):
         """pose_higher_hrnet.py:688-727: N(0, 0.001) convs, unit BN, optional partial load."""
@@ -787,80 +895,7 @@ class PoseHigherResolutionNet(nn.Module):
             outs.append(yo)
         return R, outs
 
-    def _get_plan(self, n, h, w, mode, device, in_dtype):
-        key = (n, h, w, mode, str(device), in_dtype, self.conv_engine, self.parallel_branches)
-        plan = self._plans.get(key)
-        if plan is None:
-            in_is_half = in_dtype == torch.float16
-            in_buf = torch.empty((n, 3, h, w), dtype=in_dtype, device=device)
-            with torch.cuda.device(device):
-                R, outs = self._record(n, h, w, mode, device, in_is_half, in_is_half)
-                handle = R.build(in_buf)
-            plan = _CompiledPlan(handle, in_buf, outs, R)
-            self._plans[key] = plan
-        return plan
-
-    def _mode(self):
-        dt = self.conv1.weight.dtype
-        return "fp32" if dt == torch.float32 else "bf16"
-
     # ---------------------------------------------------------------- forward
     def forward(self, x):
-        lib = L.load()
-        if not isinstance(x, torch.Tensor) or not x.is_cuda:
-            raise L.BrtpeError("PoseHigherResolutionNet.forward needs a CUDA tensor "
-                               "(no CPU fallback); got %r" % (getattr(x, "device", type(x)),))
-        if self.training:
-            raise L.BrtpeError("this implementation is inference-only: call .eval() "
-                               "(BatchNorm is folded with its running statistics)")
-        if x.dim() != 4 or x.shape[1] != 3:
-            raise ValueError("expected input (N, 3, H, W), got %s" % (tuple(x.shape),))
-        n, _, h, w = x.shape
-        if h % 32 or w % 32:
-            raise ValueError("H and W must be multiples of 32 (got %dx%d)" % (h, w))
-        if x.dtype == torch.bfloat16:
-            x = x.to(torch.float32)
-        if x.dtype not in (torch.float32, torch.float16):
-            raise ValueError("input dtype must be float32 or float16")
-        mode = self._mode()
-        dev = x.device
-        x = x.contiguous()
-        if not self._frozen or self._sig is None:
-            sig = self._signature()
-            if sig != self._sig:
-                self._plans = {}
-                self._sig = sig
-        nb = min(self.chunk_size, n)
-        odt = torch.float16 if x.dtype == torch.float16 else torch.float32
-        results = None
-        with torch.cuda.device(dev):
-            st = L.stream_ptr(dev)
-            for s0 in range(0, n, nb):
-                cn = min(nb, n - s0)
-                plan = self._get_plan(cn, h, w, mode, dev, x.dtype)
-                plan.in_buf.copy_(x[s0:s0 + cn])
-                if self.use_cuda_graph:
-                    L.check(lib.brtpe_plan_graph_launch(plan.handle, st), "brtpe_plan_graph_launch")
-                else:
-                    L.check(lib.brtpe_plan_run(plan.handle, st), "brtpe_plan_run")
-                if results is None:
-                    results = [torch.empty((n,) + tuple(o.shape[1:]), dtype=odt, device=dev)
-                               for o in plan.outs]
-                for r, o in zip(results, plan.outs):
-                    r[s0:s0 + cn].copy_(o)
-        return results
-
-    # ---------------------------------------------------------------- introspection
-    def plan_profile(self, n, h, w, in_dtype=torch.float32):
-        """Per-launch device times of one plan replay: (ms[], kind[], flops[])."""
-        lib = L.load()
-        dev = self.conv1.weight.device
-        plan = self._get_plan(n, h, w, self._mode(), dev, in_dtype)
-        k = plan.num_ops
-        ms = (C.c_float * k)()
-        kinds = (C.c_int32 * k)()
-        fl = (C.c_double * k)()
-        with torch.cuda.device(dev):
-            L.check(lib.brtpe_plan_profile(plan.handle, L.stream_ptr(dev), ms, kinds, fl),
-                    "brtpe_plan_profile")
-        return list(ms), list(kinds), list(fl)
+        """pose_higher_hrnet.py:637-686: (N,3,H,W) -> [(N,34,H/4,W/4), (N,17,H/2,W/2)]."""
+        return self._run_plans(x, 32)

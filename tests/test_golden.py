@@ -62,3 +62,19 @@ def test_hhrnet_oracle_matches_reference_fixture():
         want = torch.from_numpy(want)
         assert got.shape == want.shape
         assert ((got - want).abs().max() / want.abs().max()).item() <= 1e-5
+
+
+def test_student_oracle_matches_reference_fixture():
+    """AttentionStudent (config 4): the drop-in's parameter tree filled by (order, shape) gives
+    the weights the reference had, and the oracle reproduces the reference's outputs."""
+    from rtpe_b200.students import AttentionStudent
+    from oracle.student_ref import attention_student_forward_ref
+    z = np.load(os.path.join(GOLD, "student_64x96.npz"))
+    net = AttentionStudent(None, "cpu", inplanes=48, num_heatmaps=17, ae_dims=1, half_precision=False)
+    assert len(net.state_dict()) == int(z["entries"]) == 364
+    fill_params_deterministic(net, int(z["seed"]))
+    att, det = attention_student_forward_ref(net.state_dict(), torch.from_numpy(z["x"]))
+    for got, want in ((att, z["att"]), (det, z["det"])):
+        want = torch.from_numpy(want)
+        assert got.shape == want.shape
+        assert ((got - want).abs().max() / want.abs().max()).item() <= 1e-5

@@ -67,3 +67,26 @@ def test_dropin_state_dict_matches_reference(ref):
     rb = rtpe_b200.get_hrnet_w48_teacher(None).state_dict()
     assert list(ra.keys()) == list(rb.keys())
     assert all(ra[k].dtype == rb[k].dtype for k in ra)
+
+
+def test_student_oracle_vs_reference_class():
+    """oracle/student_ref.py against rtpe.students.AttentionStudent itself (config 4 kwargs),
+    same weights, same input; also pins the drop-in's state-dict layout to the reference's."""
+    from oracle.ref_loader import load_reference_students
+    from oracle.student_ref import attention_student_forward_ref
+    from oracle.weights import fill_params_deterministic
+    from rtpe_b200.students import AttentionStudent
+    S = load_reference_students()
+    torch.manual_seed(0)
+    ref = S.AttentionStudent(None, "cpu", inplanes=48, num_heatmaps=17, ae_dims=1,
+                             half_precision=False).eval()
+    fill_params_deterministic(ref, 3)
+    x = torch.randn(2, 3, 48, 80, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        att, det = ref(x)
+    a2, d2 = attention_student_forward_ref(ref.state_dict(), x)
+    assert torch.equal(att, a2) and torch.equal(det, d2)
+    mine = AttentionStudent(None, "cpu", inplanes=48, num_heatmaps=17, ae_dims=1, half_precision=False)
+    assert [(k, tuple(v.shape)) for k, v in mine.state_dict().items()] == \
+        [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
+    mine.load_state_dict(ref.state_dict(), strict=True)
