@@ -51,6 +51,8 @@ struct alignas(64) HaloParams {
   CUtensorMap tmap_a;
   CUtensorMap tmap_b;
   CUtensorMap tmap_o;           // output (C, W, H, N), box 32 ch x 8 px x 4 rows, SWIZZLE_64B
+  CUtensorMap tmap_r;           // residual (C, W, H, N), box BN ch x 8 px x 16 rows: L2 prefetch only
+  int res_prefetch;             // 1: the producer prefetches every item's residual tiles into L2
   int N, H, W;
   int tiles_x, tiles_y, m_tiles, n_tiles, BN, num_items;
   int num_kb, last_k16, in_coff;
@@ -62,6 +64,7 @@ struct alignas(64) HaloParams {
   int num_units;                // groups of 2*cg pixel tiles
   int acc_stages, tmem_cols;
   int out_slabs;                // staging slabs per epilogue warp (2 when shared memory allows)
+  int tma_out;                  // 1: output through staging slabs + TMA stores, 0: direct stores
   uint32_t idesc;
   FastDiv fd_xy, fd_x, fd_nt;
   const float* bias;
@@ -95,8 +98,10 @@ struct HaloConvPrepared {
   HaloParams p;
   int grid;
   size_t smem;
-  brtpe_conv_desc d;            // to (re-)encode the output tensor map
+  brtpe_conv_desc d;            // to (re-)encode the output / residual tensor maps
   const void* out_encoded;      // output pointer tmap_o was encoded for
+  const void* res_encoded;      // residual pointer tmap_r was encoded for (mutable cache)
+  CUtensorMap tmap_r_cache;
 };
 
 // descriptor halves (see make_kmajor_sw128_desc): lo = start>>4 | LBO(1)<<16, hi = SBO>>4 |
@@ -174,6 +179,7 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const fl
 
   constexpr bool remote = (HL_CG == 2);
   const bool two_slabs = p.out_slabs == 2;
+  const bool tma_out = p.tma_out != 0;
   int slab_sel = 0;   // the accumulator-free barrier lives in the leader CTA
   int item = item0;
   EpiPix px = epi_pixel(p, item, group, m, rank);
@@ -223,13 +229,14 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const fl
               else mbar_arrive(tempty_addr + 8u * acc);
             }
           }
-          if (!two && n_tiles > 1) {
+          if (!tma_out || (!two && n_tiles > 1)) {
             // 16-channel tail of a Cout tile that has a neighbour: the 32-channel store box
             // would spill into the neighbour's channels, so this chunk is stored directly
             if (px.valid) {
               const uint32_t bs = bias_u32 + (uint32_t)((co0 + c * 16) * 4);
-              epi_fast_chunk<RES, RELU, 0>(a, bs, cur[2 * h],
-                                           e.out + px.opix * e.out_ld + e.out_coff + co0 + c * 16);
+              __nv_bfloat16* op = e.out + px.opix * e.out_ld + e.out_coff + co0 + c * 16;
+              epi_fast_chunk<RES, RELU, 0>(a, bs, cur[2 * h], op);
+              if (two) epi_fast_chunk<RES, RELU, 16>(a, bs + 64u, cur[2 * h + 1], op + 16);
             }
           } else {
             // 32 (or 16) channels of 32 pixels -> bf16 in registers -> this warp's staging
@@ -358,6 +365,7 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
     const uint32_t stage_b_bytes = (uint32_t)(tps * BN * 128);          // both CTAs together
     const int in_coff = p.in_coff;
     const int brow0 = rank * BNh;
+    const bool res_prefetch = p.res_prefetch != 0;
     auto sig = [&](const uint64_t* bar) -> uint32_t {                   // barrier the TMA signals
       const uint32_t a = smem_u32(bar);
       return cg2 ? mapa_u32(a, 0u) : a;
@@ -393,6 +401,13 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
       const TileOrg o0 = tile_origin(p, unit * tpi + rank * 2);
       const TileOrg o1 = tile_origin(p, unit * tpi + rank * 2 + 1);
       if (elect_one()) {
+        if (res_prefetch && nx_kb == 0) {
+          // the residual tiles of this item will be read by the epilogue one to two items from
+          // now: pull them into L2 so that those loads do not pay the HBM latency
+          const int rc0 = p.epi.res_coff + (nx_item - unit * n_tiles) * BN;
+          if (o0.n < p.N) tma_prefetch_l2_4d(&p.tmap_r, rc0, o0.x0, o0.y0, o0.n);
+          if (o1.n < p.N) tma_prefetch_l2_4d(&p.tmap_r, rc0, o1.x0, o1.y0, o1.n);
+        }
         const uint32_t fa = smem_u32(&full_a[as_]);
         if (dbg & 8) {
           if (leader) mbar_arrive(fa);
@@ -673,6 +688,25 @@ static bool HL_NAME(g_halo_attr_set) = false;
 // SWIZZLE_64B.  Stores beyond C / W / H / N are clipped by the hardware: that is how ragged
 // tiles, the 16-channel tail of odd channel counts and tiles past the end of the batch are
 // handled.
+// Residual tensor map (L2 prefetch only): (C = res_coff + Cout, W, H, N), box BN ch x 8 x 16.
+static bool halo_encode_res(const brtpe_conv_desc* d, const void* res, int bn, CUtensorMap* map) {
+  auto encode = halo_encode_fn();
+  const cuuint64_t ld_b = (cuuint64_t)d->res_ld * 2;
+  cuuint64_t gdim[4] = {(cuuint64_t)(d->res_coff + d->Cout), (cuuint64_t)d->Wout,
+                        (cuuint64_t)d->Hout, (cuuint64_t)d->N};
+  cuuint64_t gstr[3] = {ld_b, ld_b * d->Wout, ld_b * d->Wout * d->Hout};
+  cuuint32_t box[4] = {(cuuint32_t)bn, (cuuint32_t)HL_TW, (cuuint32_t)HL_TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(res), gdim, gstr,
+                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("halo conv: cuTensorMapEncodeTiled(residual) failed with %d", (int)r);
+    return false;
+  }
+  return true;
+}
+
 static bool halo_encode_out(const brtpe_conv_desc* d, void* out, CUtensorMap* map) {
   auto encode = halo_encode_fn();
   const cuuint64_t ld_b = (cuuint64_t)d->out_ld * 2;
@@ -696,6 +730,7 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
   HaloConvPrepared* P = new HaloConvPrepared();
   P->d = *d;
   P->out_encoded = nullptr;
+  P->res_encoded = nullptr;
   HaloParams& p = P->p;
   memset(&p, 0, sizeof(p));
   p.N = d->N; p.H = d->Hin; p.W = d->Win;
@@ -734,6 +769,10 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
   // shared-memory plan: [A ring][B ring or resident weights][tail]; in pair mode every CTA
   // holds half of the weight rows
   const int tap_bytes = (p.BN / p.cg) * 128;
+  // The 48/64-channel layers are bound by shared-memory bandwidth (MMA operand reads); staging
+  // their output through shared memory costs more than it saves there: direct 32-byte stores.
+  p.tma_out = (p.BN >= 96) ? 1 : 0;
+  if (getenv("BRTPE_HALO_TMA_OUT")) p.tma_out = atoi(getenv("BRTPE_HALO_TMA_OUT")) ? 1 : 0;
   // two output slabs per epilogue warp unless that would push resident weights out / leave the
   // weight ring with fewer than two stages
   p.out_slabs = 2;
@@ -744,6 +783,7 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
     const bool res2 = p.n_tiles == 1 && p.num_kb * 9 * tb + 2 * HL_A_STAGE <= b2;
     if ((res1 && !res2) || (!res2 && 2 * tb > b2 - 2 * HL_A_STAGE)) p.out_slabs = 1;
   }
+  if (!p.tma_out) p.out_slabs = 0;
   const int budget = HL_SMEM_MAX - HL_TAIL - 1024 - p.out_slabs * HL_STAGE_BYTES;
   const int resident_bytes = p.num_kb * 9 * tap_bytes;
   p.resident = (p.n_tiles == 1 && resident_bytes + 2 * HL_A_STAGE <= budget) ? 1 : 0;
@@ -852,6 +892,18 @@ int HL_NAME(halo_conv_launch)(const HaloConvPrepared* P, const float* bias, cons
   p.epi.out = reinterpret_cast<__nv_bfloat16*>(out);
   if (p.epi.fast && out != P->out_encoded) {       // output buffer changed since prepare
     if (!halo_encode_out(&P->d, out, &p.tmap_o)) return BRTPE_ECUDA;
+  }
+  p.res_prefetch = 0;
+  // Opt-in (BRTPE_HALO_RES_PREFETCH=1): measured neutral for 48 channels and 9 % slower for 96
+  // (the epilogue gets its data sooner, but the extra TMA traffic delays the operand loads).
+  if (residual != nullptr && p.epi.fast && getenv("BRTPE_HALO_RES_PREFETCH")) {
+    HaloConvPrepared* PM = const_cast<HaloConvPrepared*>(P);     // cache of the encoded map
+    if (residual != PM->res_encoded) {
+      if (!halo_encode_res(&P->d, residual, p.BN, &PM->tmap_r_cache)) return BRTPE_ECUDA;
+      PM->res_encoded = residual;
+    }
+    p.tmap_r = PM->tmap_r_cache;
+    p.res_prefetch = 1;
   }
   const bool prof = g_halo_prof != nullptr && P->grid <= g_halo_prof_ctas;
   p.prof = prof ? g_halo_prof : nullptr;
