@@ -27,6 +27,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 
 namespace brtpe {
@@ -240,7 +241,16 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 static void umma_n_tiling(int cout_store, int* n_tiles, int* bn) {
   const int cp = (cout_store + 15) / 16 * 16;
-  *n_tiles = (cp + 255) / 256;
+  // Cout tiles of at most 128 channels: two accumulator stages then fit in 256 TMEM columns, so
+  // two CTAs (8 epilogue warps) share an SM.  The wide 1x1 layers (64 -> 256 + residual) are
+  // epilogue / HBM bound, not MMA bound: BRTPE_UMMA_BN_MAX=256 restores one 256-wide tile.
+  static int bn_max = 0;
+  if (!bn_max) {
+    const char* e = getenv("BRTPE_UMMA_BN_MAX");
+    bn_max = e ? atoi(e) : 128;
+    if (bn_max < 16 || bn_max > 256) bn_max = 128;
+  }
+  *n_tiles = (cp + bn_max - 1) / bn_max;
   *bn = ((cp + *n_tiles - 1) / *n_tiles + 15) / 16 * 16;
 }
 
