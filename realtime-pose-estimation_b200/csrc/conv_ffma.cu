@@ -331,6 +331,48 @@ nhwc_to_nchw_kernel(const TS* __restrict__ src, int N, int HW, int C, int ld, in
   }
 }
 
+// bf16 NHWC -> NCHW (half or float), C <= 64 channels, 16-byte aligned channel slices: the
+// network-output case (34 and 17 channels).  128-256 pixels per CTA; the source is read as 16-byte
+// vectors (8 channels), transposed through shared memory and written as 16-byte row segments.
+template <typename TD>
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_bf16_vec_kernel(const __nv_bfloat16* __restrict__ src, int HW, int C, int ld, int coff,
+                             TD* __restrict__ dst) {
+  constexpr int PX = 512 / (int)sizeof(TD);             // 256 (half) / 128 (float) pixels per CTA
+  constexpr int EPV = 16 / (int)sizeof(TD);              // destination elements per 16-byte store
+  __shared__ __align__(16) TD tile[64][PX + EPV];        // [channel][pixel], padded rows
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * PX;
+  const int cv = (C + 7) >> 3;                           // 16-byte vectors per pixel
+  for (int v = threadIdx.x; v < PX * cv; v += 256) {
+    const int pl = v / cv, k = v - pl * cv;
+    const int p = p0 + pl;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (p < HW)
+      q = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)n * HW + p) * ld + coff + k * 8));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = k * 8 + 2 * i;
+      if (c < C) tile[c][pl] = from_f32<TD>(__uint_as_float(w[i] << 16));
+      if (c + 1 < C) tile[c + 1][pl] = from_f32<TD>(__uint_as_float(w[i] & 0xffff0000u));
+    }
+  }
+  __syncthreads();
+  constexpr int SEG = PX / EPV;                          // 16-byte segments per channel row
+  for (int v = threadIdx.x; v < C * SEG; v += 256) {
+    const int c = v / SEG, sg = v - c * SEG;
+    const int p = p0 + sg * EPV;
+    TD* d = dst + ((size_t)n * C + c) * HW + p;
+    if (p + EPV <= HW && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
+      *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(&tile[c][sg * EPV]);
+    } else {
+      for (int e = 0; e < EPV; ++e)
+        if (p + e < HW) d[e] = tile[c][sg * EPV + e];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 int conv_validate(const brtpe_conv_desc* d) {
   BRTPE_CHECK_ARG(d != nullptr, "conv: null descriptor");
@@ -474,6 +516,18 @@ int nhwc_to_nchw_launch(int dtype, const void* src, int N, int H, int W, int C, 
                         void* dst, int dst_is_half, cudaStream_t st) {
   BRTPE_CHECK_ARG(src && dst && N > 0 && H > 0 && W > 0 && C > 0 && ld >= coff + C,
                   "nhwc_to_nchw: bad arguments");
+  if (dtype == BRTPE_DT_BF16 && C <= 64 && (ld % 8) == 0 && (coff % 8) == 0 && N <= 65535 &&
+      (reinterpret_cast<uintptr_t>(src) & 15) == 0 && coff + ((C + 7) / 8) * 8 <= ld) {
+    dim3 vgrid(ceil_div(H * W, dst_is_half ? 256 : 128), N);
+    if (dst_is_half)
+      nhwc_to_nchw_bf16_vec_kernel<__half><<<vgrid, 256, 0, st>>>(
+          reinterpret_cast<const __nv_bfloat16*>(src), H * W, C, ld, coff, reinterpret_cast<__half*>(dst));
+    else
+      nhwc_to_nchw_bf16_vec_kernel<float><<<vgrid, 256, 0, st>>>(
+          reinterpret_cast<const __nv_bfloat16*>(src), H * W, C, ld, coff, reinterpret_cast<float*>(dst));
+    BRTPE_LAUNCH_CHECK();
+    return BRTPE_OK;
+  }
   dim3 grid(ceil_div(H * W, 64), ceil_div(C, 64), N);
 #define BRTPE_T(TS, TD)                                                                    \
   nhwc_to_nchw_kernel<TS, TD><<<grid, 256, 0, st>>>(reinterpret_cast<const TS*>(src), N, H * W, C, \
