@@ -61,7 +61,9 @@ struct alignas(64) HaloParams {
   int resident;                 // 1: all weights stay in smem for the whole kernel
   int cg;                       // 1: one CTA per MMA; 2: CTA pair (tcgen05 cta_group::2): M = 256 over
                                 // two SMs, each CTA holds its 2 pixel tiles and HALF of the weight rows
-  int num_units;                // groups of 2*cg pixel tiles
+  int tpc;                      // pixel tiles per CTA and work item: 2, or 1 for wide Cout tiles (two
+                                // accumulators of BN columns would leave no room for double buffering)
+  int num_units;                // groups of tpc*cg pixel tiles
   int acc_stages, tmem_cols;
   int out_slabs;                // staging slabs per epilogue warp (2 when shared memory allows)
   int tma_out;                  // 1: output through staging slabs + TMA stores, 0: direct stores
@@ -142,7 +144,7 @@ __device__ __forceinline__ EpiPix epi_pixel(const HaloParams& p, int item, int t
   e.opix = 0;
   if (item >= p.num_items) return e;
   const int unit = (int)fdiv((uint32_t)item, p.fd_nt);
-  const int mt = unit * (2 * p.cg) + rank * 2 + tile;
+  const int mt = unit * (p.tpc * p.cg) + rank * p.tpc + tile;
   const TileOrg o = tile_origin(p, mt);
   const int y = o.y0 + (m >> 3), x = o.x0 + (m & 7);
   e.valid = mt < p.m_tiles && y < p.H && x < p.W;
@@ -168,8 +170,14 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const fl
   const EpiParams& e = p.epi;
   const int m = lg * 32 + lane;
   const int BN = p.BN, n_tiles = p.n_tiles, num_items = p.num_items;
-  const int nchunks = BN >> 4;
+  // two tiles per CTA: group g drains tile g; one tile per CTA: both groups drain it, group g the
+  // channel chunks [cbeg, cend)
+  const int tile_sel = (p.tpc == 2) ? group : 0;
+  const int allchunks = BN >> 4;
+  const int cbeg = (p.tpc == 2) ? 0 : group * (allchunks >> 1);
+  const int nchunks = (p.tpc == 2) ? allchunks : cbeg + (group == 0 ? (allchunks >> 1) : allchunks - (allchunks >> 1));
   const int acc_stages = p.acc_stages;
+  const int acc_cols = p.tpc * BN;
   const uint32_t bias_u32 = smem_u32(bias_s);
   Chunk32 nxt[4];
 #pragma unroll
@@ -182,36 +190,36 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const fl
   const bool tma_out = p.tma_out != 0;
   int slab_sel = 0;   // the accumulator-free barrier lives in the leader CTA
   int item = item0;
-  EpiPix px = epi_pixel(p, item, group, m, rank);
+  EpiPix px = epi_pixel(p, item, tile_sel, m, rank);
   int nt = item - (int)fdiv((uint32_t)item, p.fd_nt) * n_tiles;
   epi_fetch_round<RES>(nxt, RES ? e.res + px.opix * e.res_ld + e.res_coff + nt * BN : nullptr,
-                       px.valid, 0, nchunks);
+                       px.valid, cbeg, nchunks);
   int it = 0;
   for (; item < num_items; item += istep, ++it) {
     const int next_item = item + istep;
-    const EpiPix npx = epi_pixel(p, next_item, group, m, rank);
+    const EpiPix npx = epi_pixel(p, next_item, tile_sel, m, rank);
     const int nnt = next_item - (int)fdiv((uint32_t)next_item, p.fd_nt) * n_tiles;
     const int co0 = nt * BN;
     const __nv_bfloat16* rp = RES ? e.res + px.opix * e.res_ld + e.res_coff + co0 : nullptr;
     const __nv_bfloat16* nrp = RES ? e.res + npx.opix * e.res_ld + e.res_coff + nnt * BN : nullptr;
     // origin of this warp's 8 x 4 pixel slab (TMA clips what lies outside the image / batch)
     const TileOrg org = tile_origin(
-        p, (int)fdiv((uint32_t)item, p.fd_nt) * (2 * p.cg) + rank * 2 + group);
+        p, (int)fdiv((uint32_t)item, p.fd_nt) * (p.tpc * p.cg) + rank * p.tpc + tile_sel);
     const int oy = org.y0 + 4 * lg;
     const int acc = (acc_stages == 2) ? (it & 1) : 0;
     const uint32_t accph = (acc_stages == 2) ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
     const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) +
-                            (uint32_t)(acc * 2 * BN + group * BN);
+                            (uint32_t)(acc * acc_cols + tile_sel * BN);
     HL_TIMED(10, mbar_wait(smem_u32(&tfull[acc]), accph));
     if (PROF) pc[11] += 1;
     tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < nchunks; c0 += 4) {
+    for (int c0 = cbeg; c0 < nchunks; c0 += 4) {
       Chunk32 cur[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
       if (c0 + 4 < nchunks) epi_fetch_round<RES>(nxt, rp, px.valid, c0 + 4, nchunks);
-      else epi_fetch_round<RES>(nxt, nrp, npx.valid, 0, nchunks);
+      else epi_fetch_round<RES>(nxt, nrp, npx.valid, cbeg, nchunks);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = c0 + 2 * h;
@@ -305,7 +313,8 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
   const bool leader = rank == 0;
   const int item0 = cg2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int istep = cg2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int tpi = 2 * p.cg;                         // pixel tiles per work item
+  const int tpc = p.tpc;                            // pixel tiles per CTA and work item (1 or 2)
+  const int tpi = tpc * p.cg;                       // pixel tiles per work item
   const int BNh = cg2 ? (BN >> 1) : BN;             // weight rows this CTA holds
 
   uint8_t* a_ring = smem;
@@ -398,8 +407,8 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
         return false;
       }
       const int unit = (int)fdiv((uint32_t)nx_item, p.fd_nt);
-      const TileOrg o0 = tile_origin(p, unit * tpi + rank * 2);
-      const TileOrg o1 = tile_origin(p, unit * tpi + rank * 2 + 1);
+      const TileOrg o0 = tile_origin(p, unit * tpi + rank * tpc);
+      const TileOrg o1 = tile_origin(p, unit * tpi + rank * tpc + 1);      // unused when tpc == 1
       if (elect_one()) {
         if (res_prefetch && nx_kb == 0) {
           // the residual tiles of this item will be read by the epilogue one to two items from
@@ -417,12 +426,14 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
           if (cg2) {
             const uint32_t fas = sig(&full_a[as_]);
             tma_load_5d_cg2(dst, &p.tmap_a, fas, in_coff + nx_kb * 64, o0.x0 - 1, 0, o0.y0 - 1, o0.n);
-            tma_load_5d_cg2(dst + HL_A_TILE, &p.tmap_a, fas, in_coff + nx_kb * 64, o1.x0 - 1, 0,
-                            o1.y0 - 1, o1.n);
+            if (tpc == 2)
+              tma_load_5d_cg2(dst + HL_A_TILE, &p.tmap_a, fas, in_coff + nx_kb * 64, o1.x0 - 1, 0,
+                              o1.y0 - 1, o1.n);
           } else {
             tma_load_5d(dst, &p.tmap_a, fa, in_coff + nx_kb * 64, o0.x0 - 1, 0, o0.y0 - 1, o0.n);
-            tma_load_5d(dst + HL_A_TILE, &p.tmap_a, fa, in_coff + nx_kb * 64, o1.x0 - 1, 0,
-                        o1.y0 - 1, o1.n);
+            if (tpc == 2)
+              tma_load_5d(dst + HL_A_TILE, &p.tmap_a, fa, in_coff + nx_kb * 64, o1.x0 - 1, 0,
+                          o1.y0 - 1, o1.n);
           }
         }
       }
@@ -493,7 +504,7 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
           HL_TIMED(8, mbar_wait(smem_u32(&tempty[acc]), accph ^ 1u));
         }
         tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * BN);
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * tpc * BN);
         const uint32_t d1 = d0 + (uint32_t)BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           HL_TIMED(6, mbar_wait(smem_u32(&full_a[as_]), aph));
@@ -524,22 +535,26 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
                       if (k < k16)
                         umma_f16_lohi_cg2(d0, a0 + a_off + 2u * k, A_HI, bt + 2u * k, B_HI, idesc,
                                           (first | (uint32_t)k) ? 1u : 0u);
+                    if (tpc == 2) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                      if (k < k16)
-                        umma_f16_lohi_cg2(d1, a1 + a_off + 2u * k, A_HI, bt + 2u * k, B_HI, idesc,
-                                          (first | (uint32_t)k) ? 1u : 0u);
+                      for (int k = 0; k < 4; ++k)
+                        if (k < k16)
+                          umma_f16_lohi_cg2(d1, a1 + a_off + 2u * k, A_HI, bt + 2u * k, B_HI, idesc,
+                                            (first | (uint32_t)k) ? 1u : 0u);
+                    }
                   } else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                       if (k < k16)
                         umma_f16_lohi(d0, a0 + a_off + 2u * k, A_HI, bt + 2u * k, B_HI, idesc,
                                       (first | (uint32_t)k) ? 1u : 0u);
+                    if (tpc == 2) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                      if (k < k16)
-                        umma_f16_lohi(d1, a1 + a_off + 2u * k, A_HI, bt + 2u * k, B_HI, idesc,
-                                      (first | (uint32_t)k) ? 1u : 0u);
+                      for (int k = 0; k < 4; ++k)
+                        if (k < k16)
+                          umma_f16_lohi(d1, a1 + a_off + 2u * k, A_HI, bt + 2u * k, B_HI, idesc,
+                                        (first | (uint32_t)k) ? 1u : 0u);
+                    }
                   }
                 }
                 if (++kw == 3) { kw = 0; ++kh; }
@@ -614,7 +629,7 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
         const int acc = (acc_stages == 2) ? (it & 1) : 0;
         const uint32_t accph = (acc_stages == 2) ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
         const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) +
-                                (uint32_t)(acc * 2 * BN + group * BN);
+                                (uint32_t)(acc * tpc * BN + group * BN);
         epi_drain(e, bias_s, t_addr, nchunks, nt * BN, px.valid, px.opix, smem_u32(&tfull[acc]),
                   accph, smem_u32(&tempty[acc]), lane);
       }
@@ -744,7 +759,16 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
     delete P;
     return nullptr;
   }
-  const int tpi = 2 * p.cg;
+  // one tile per CTA when two accumulators of BN columns could not be double-buffered in the 512
+  // TMEM columns (BN > 128): the epilogue of item i then overlaps the MMAs of item i+1 again and
+  // the work items are finer (better balance over the SMs); needs the fast epilogue
+  const int cp0 = (d->Cout_store + 15) / 16 * 16;
+  p.tpc = (cp0 > 128 && cp0 <= HL_MAX_BN && epi_fast_ok(d) && (cp0 / 16) % 2 == 0) ? 1 : 2;
+  if (getenv("BRTPE_HALO_TPC")) {
+    const int v = atoi(getenv("BRTPE_HALO_TPC"));
+    if (v == 2 || (v == 1 && epi_fast_ok(d) && (cp0 / 16) % 2 == 0)) p.tpc = v;
+  }
+  const int tpi = p.tpc * p.cg;
   const int workers = num_sms() / p.cg;               // CTAs (cg 1) or CTA pairs (cg 2)
   const int pairs = ceil_div(p.m_tiles, tpi);         // work units of 2*cg pixel tiles
   p.num_units = pairs;
@@ -761,9 +785,14 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
   p.last_k16 = (d->Cin - (p.num_kb - 1) * 64) / 16;
   p.in_coff = d->in_coff;
   p.dbg = getenv("BRTPE_HALO_DBG") ? atoi(getenv("BRTPE_HALO_DBG")) : 0;
-  p.acc_stages = (4 * p.BN <= 512) ? 2 : 1;
+  if (p.tpc == 1 && (p.BN / 16) % 2 != 0) {        // the two epilogue groups split the chunks evenly
+    delete P;
+    set_error("halo conv: one-tile mode needs an even number of 16-channel chunks (BN %d)", p.BN);
+    return nullptr;
+  }
+  p.acc_stages = (2 * p.tpc * p.BN <= 512) ? 2 : 1;
   int cols = 32;
-  while (cols < p.acc_stages * 2 * p.BN) cols *= 2;
+  while (cols < p.acc_stages * p.tpc * p.BN) cols *= 2;
   p.tmem_cols = cols;
 
   // shared-memory plan: [A ring][B ring or resident weights][tail]; in pair mode every CTA
@@ -825,6 +854,11 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
   p.epi.relu = d->relu; p.epi.vec32 = epi_vec32_ok(d);
   // the fast epilogue walks whole 16-channel chunks of real channels
   p.epi.fast = (epi_fast_ok(d) && p.n_tiles * p.BN == d->Cout) ? 1 : 0;
+  if (p.tpc == 1 && !p.epi.fast) {
+    set_error("halo conv: one-tile mode needs Cout = n_tiles * BN (Cout %d, %d x %d)", d->Cout, p.n_tiles, p.BN);
+    delete P;
+    return nullptr;
+  }
   if (p.cg == 2 && !p.epi.fast) {
     set_error("halo conv: pair mode needs Cout = n_tiles * BN (Cout %d, %d x %d)", d->Cout, p.n_tiles, p.BN);
     delete P;
