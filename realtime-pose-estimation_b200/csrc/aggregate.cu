@@ -13,7 +13,9 @@
 // Both are write-bound streaming kernels: one thread per output pixel, consecutive
 // threads on consecutive x, sources are 4-16x smaller than the output and stay in L1/L2.
 #include "common.cuh"
+#include "umma_ptx.cuh"
 
+#include <cudaTypedefs.h>
 #include <stdlib.h>
 
 namespace brtpe {
@@ -454,6 +456,265 @@ __global__ void __launch_bounds__(256, 2) aggregate_x4_kernel(AggArgs a) {
   }
 }
 
+// ---- the same exact 2x -> 2x cascade with TMA-staged sources --------------------------------
+// aggregate_x4_kernel above is bound by the latency of its ~50 scattered source loads per channel
+// (ncu r01k: 71 % of the stall samples are long-scoreboard, 21 % of the warp slots active).  Here
+// a CTA owns a 32 x 8 block of 1/4-resolution pixels of one image and walks the channels; for
+// every channel a producer lane fetches the 1/4- and 1/2-resolution source tiles (with their
+// one-pixel aprons, zero-filled outside the map and never read there) of the image and of the
+// mirrored flipped image as four cp.async.bulk.tensor boxes into a ring of shared-memory stages
+// (full/empty mbarriers, 4 channels in flight), and the 8 consumer warps compute the 4x4 output
+// blocks from shared memory with the arithmetic of x4_patch / x4_out.
+constexpr int XT_W = 32, XT_H = 8;
+// boxes start 4 columns left of the tile: the innermost TMA coordinate must stay 16-byte aligned
+// (a box starting at column -1 faults), so the one-column apron costs a 4-column margin per side
+constexpr int XQ_X0 = 4;
+constexpr int XQ0_W = XT_W + 2 * XQ_X0, XQ0_H = XT_H + 2;
+constexpr int XQ1_W = 2 * XT_W + 2 * XQ_X0, XQ1_H = 2 * XT_H + 2;
+constexpr int XQ0_BYTES = XQ0_W * XQ0_H * 4, XQ1_BYTES = XQ1_W * XQ1_H * 4;
+constexpr int XQ0_SLOT = (XQ0_BYTES + 127) / 128 * 128, XQ1_SLOT = (XQ1_BYTES + 127) / 128 * 128;
+constexpr int X4_STAGE_BYTES = 2 * (XQ0_SLOT + XQ1_SLOT);
+constexpr int X4_NSTG = 4;
+constexpr int X4_CONSUMERS = XT_W * XT_H / 32;
+constexpr int X4T_THREADS = (X4_CONSUMERS + 1) * 32;
+
+struct X4Maps {
+  CUtensorMap y0, y1, y0f, y1f;
+};
+
+__device__ __forceinline__ void x4_patch_s(const float* __restrict__ q0, const float* __restrict__ q1,
+                                           const int (&r0)[3], const int (&c0)[3],
+                                           const int (&r1)[4], const int (&c1)[4],
+                                           float (&G)[4][4]) {
+  float h[3][4];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    up2_4(q0[r0[r] + c0[0]], q0[r0[r] + c0[1]], q0[r0[r] + c0[2]], h[r]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float col[4];
+    up2_4(h[0][i], h[1][i], h[2][i], col);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) G[j][i] = col[j];
+  }
+  if (q1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) G[j][i] = (G[j][i] + q1[r1[j] + c1[i]]) * 0.5f;
+  }
+}
+
+template <bool FLIP>
+__global__ void __launch_bounds__(X4T_THREADS, 2)
+aggregate_x4_tma_kernel(AggArgs a, const __grid_constant__ X4Maps maps) {
+  extern __shared__ unsigned char x4_dyn[];
+  // TMA destinations must be 128-byte aligned: align by hand (the launch adds 128 bytes of slack)
+  unsigned char* x4_raw = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(x4_dyn) + 127) & ~static_cast<uintptr_t>(127));
+  __shared__ __align__(8) unsigned long long full_bar[X4_NSTG];
+  __shared__ __align__(8) unsigned long long empty_bar[X4_NSTG];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bx0 = blockIdx.x * XT_W, by0 = blockIdx.y * XT_H;
+  const int n = blockIdx.z;
+  const int W4 = a.W4, H4 = a.H4, W2 = a.W2, H2 = a.H2, Wb = a.Wb;
+  const int C0 = a.J + a.A;
+  const int nitems = a.J + (a.tag ? a.A : 0);
+
+  if (tid == 0) {
+    for (int s = 0; s < X4_NSTG; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), X4_CONSUMERS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == X4_CONSUMERS) {
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.y0);
+      tma_prefetch_desc(&maps.y1);
+      if (FLIP) {
+        tma_prefetch_desc(&maps.y0f);
+        tma_prefetch_desc(&maps.y1f);
+      }
+      int slot = 0;
+      uint32_t ephase = 1;
+      for (int it = 0; it < nitems; ++it) {
+        mbar_wait(smem_u32(&empty_bar[slot]), ephase);
+        const uint32_t bar = smem_u32(&full_bar[slot]);
+        const uint32_t base = smem_u32(x4_raw + (size_t)slot * X4_STAGE_BYTES);
+        const bool is_det = it < a.J;
+        const int c = is_det ? it : it - a.J;
+        const int cf = (is_det || a.A == a.J) ? a.flip_index[c] : c;
+        const int ch0 = n * C0 + (is_det ? c : a.J + c);
+        const int ch0f = n * C0 + (is_det ? cf : a.J + cf);
+        const uint32_t bytes = (uint32_t)((FLIP ? 2 : 1) * (XQ0_BYTES + (is_det ? XQ1_BYTES : 0)));
+        mbar_expect_tx(bar, bytes);
+        tma_load_3d(base, &maps.y0, bar, bx0 - XQ_X0, by0 - 1, ch0);
+        if (is_det)
+          tma_load_3d(base + XQ0_SLOT, &maps.y1, bar, 2 * bx0 - XQ_X0, 2 * by0 - 1, n * a.J + c);
+        if (FLIP) {
+          tma_load_3d(base + XQ0_SLOT + XQ1_SLOT, &maps.y0f, bar, W4 - bx0 - (XT_W + XQ_X0), by0 - 1,
+                      ch0f);
+          if (is_det)
+            tma_load_3d(base + 2 * XQ0_SLOT + XQ1_SLOT, &maps.y1f, bar,
+                        W2 - 2 * bx0 - (2 * XT_W + XQ_X0), 2 * by0 - 1, n * a.J + cf);
+        }
+        if (++slot == X4_NSTG) { slot = 0; ephase ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // ---- consumers
+  const int bx = bx0 + (tid & 31), by = by0 + (tid >> 5);
+  const bool active = bx < W4 && by < H4;
+  int r0[3], c0[3], c0f[3], r1[4], c1[4], c1f[4];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    r0[k] = (min(max(by - 1 + k, 0), H4 - 1) - (by0 - 1)) * XQ0_W;
+    c0[k] = min(max(bx - 1 + k, 0), W4 - 1) - (bx0 - XQ_X0);
+    c0f[k] = (XQ0_W - 1) - c0[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    r1[k] = (min(max(2 * by - 1 + k, 0), H2 - 1) - (2 * by0 - 1)) * XQ1_W;
+    c1[k] = min(max(2 * bx - 1 + k, 0), W2 - 1) - (2 * bx0 - XQ_X0);
+    c1f[k] = (XQ1_W - 1) - c1[k];
+  }
+  if (!active) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { r0[k] = 0; c0[k] = 0; c0f[k] = 0; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { r1[k] = 0; c1[k] = 0; c1f[k] = 0; }
+  }
+  const size_t pb = (size_t)a.Hb * Wb;
+  const size_t obase = (size_t)(4 * by) * Wb + 4 * bx;
+  constexpr int T = FLIP ? 2 : 1;
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int it = 0; it < nitems; ++it) {
+    mbar_wait(smem_u32(&full_bar[slot]), phase);
+    const float* q0 = reinterpret_cast<const float*>(x4_raw + (size_t)slot * X4_STAGE_BYTES);
+    const float* q1 = q0 + XQ0_SLOT / 4;
+    const float* q0f = q1 + XQ1_SLOT / 4;
+    const float* q1f = q0f + XQ0_SLOT / 4;
+    if (active) {
+      if (it < a.J) {
+        const int c = it;
+        float G[4][4], O[4][4];
+        x4_patch_s(q0, q1, r0, c0, r1, c1, G);
+        if (FLIP) {
+          float Gf[4][4];
+          x4_patch_s(q0f, q1f, r0, c0f, r1, c1f, Gf);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) G[j][i] = (G[j][i] + Gf[j][i]) * 0.5f;
+        }
+        x4_out(G, O);
+        float* d = a.det + ((size_t)n * a.J + c) * pb + obase;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 v = make_float4(O[j][0], O[j][1], O[j][2], O[j][3]);
+          float4* dp = reinterpret_cast<float4*>(d + (size_t)j * Wb);
+          if (a.accumulate) {
+            const float4 o = *dp;
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+          }
+          if (a.final_div != 0.0f) {
+            v.x = __fdiv_rn(v.x, a.final_div); v.y = __fdiv_rn(v.y, a.final_div);
+            v.z = __fdiv_rn(v.z, a.final_div); v.w = __fdiv_rn(v.w, a.final_div);
+          }
+          *dp = v;
+        }
+      } else {
+        const int t = it - a.J;
+        float G[4][4], O[4][4];
+        x4_patch_s(q0, nullptr, r0, c0, r1, c1, G);
+        x4_out(G, O);
+        float* o = a.tag + (((size_t)n * a.A + t) * pb + obase) * T;
+        if (FLIP) {
+          float Gf[4][4], Of[4][4];
+          x4_patch_s(q0f, nullptr, r0, c0f, r1, c1f, Gf);
+          x4_out(Gf, Of);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4* op = reinterpret_cast<float4*>(o + (size_t)j * Wb * 2);
+            op[0] = make_float4(O[j][0], Of[j][0], O[j][1], Of[j][1]);
+            op[1] = make_float4(O[j][2], Of[j][2], O[j][3], Of[j][3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(o + (size_t)j * Wb) = make_float4(O[j][0], O[j][1], O[j][2], O[j][3]);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&empty_bar[slot]));
+    if (++slot == X4_NSTG) { slot = 0; phase ^= 1u; }
+  }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 agg_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// (W, H, planes) fp32 tensor map with a (bw, bh, 1) box
+static bool agg_make_map(CUtensorMap* m, const float* ptr, int W, int H, long long planes, int bw,
+                         int bh) {
+  auto encode = agg_encode_fn();
+  if (!encode) return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+  cuuint64_t gstr[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+  cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), gdim, gstr, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// returns 1 when launched, 0 when the shape / alignment does not qualify, < 0 on error
+static int launch_x4_tma(const AggArgs& a, cudaStream_t st) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (a.W4 % 4 != 0 || a.W4 < XQ0_W || a.H4 < XQ0_H) return 0;
+  if (!al16(a.y0) || !al16(a.y1) || (a.y0f && (!al16(a.y0f) || !al16(a.y1f)))) return 0;
+  X4Maps maps;
+  const long long p0 = (long long)a.N * (a.J + a.A), p1 = (long long)a.N * a.J;
+  if (!agg_make_map(&maps.y0, a.y0, a.W4, a.H4, p0, XQ0_W, XQ0_H)) return 0;
+  if (!agg_make_map(&maps.y1, a.y1, a.W2, a.H2, p1, XQ1_W, XQ1_H)) return 0;
+  if (a.y0f) {
+    if (!agg_make_map(&maps.y0f, a.y0f, a.W4, a.H4, p0, XQ0_W, XQ0_H)) return 0;
+    if (!agg_make_map(&maps.y1f, a.y1f, a.W2, a.H2, p1, XQ1_W, XQ1_H)) return 0;
+  } else {
+    maps.y0f = maps.y0;
+    maps.y1f = maps.y1;
+  }
+  const size_t smem = (size_t)X4_NSTG * X4_STAGE_BYTES + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BRTPE_CUDA(cudaFuncSetAttribute(aggregate_x4_tma_kernel<true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BRTPE_CUDA(cudaFuncSetAttribute(aggregate_x4_tma_kernel<false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(a.W4, XT_W), ceil_div(a.H4, XT_H), a.N);
+  if (a.y0f) aggregate_x4_tma_kernel<true><<<grid, X4T_THREADS, smem, st>>>(a, maps);
+  else aggregate_x4_tma_kernel<false><<<grid, X4T_THREADS, smem, st>>>(a, maps);
+  return 1;
+}
+
 }  // namespace brtpe
 
 using namespace brtpe;
@@ -513,7 +774,14 @@ extern "C" int brtpe_aggregate_scale(const float* y0, const float* y1, const flo
                        (!tag_out || (reinterpret_cast<uintptr_t>(tag_out) & 15) == 0);
   const bool x4 = aligned && H2 == 2 * H4 && W2 == 2 * W4 && Hb == 2 * H2 && Wb == 2 * W2 &&
                   N <= 65535 && ceil_div(H4, 4) <= 65535 && !getenv("BRTPE_AGG_GENERIC");
-  if (x4) {
+  int tma = 0;
+  if (x4 && !getenv("BRTPE_AGG_X4_V1")) {
+    tma = launch_x4_tma(a, (cudaStream_t)stream);
+    if (tma < 0) return tma;
+  }
+  if (tma == 1) {
+    // launched above
+  } else if (x4) {
     dim3 grid(ceil_div(W4, 64), ceil_div(H4, 4), N);
     if (y0f) aggregate_x4_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     else aggregate_x4_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(a);

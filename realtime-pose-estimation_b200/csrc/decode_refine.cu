@@ -14,6 +14,9 @@
 //                            touched near real candidates;
 //   3. refine_fill_kernel  : +0.5 / quarter-pixel offsets and the in-place fill.
 #include "common.cuh"
+#include "umma_ptx.cuh"
+
+#include <stdlib.h>
 
 namespace brtpe {
 
@@ -239,6 +242,235 @@ refine_scan_kernel(RefineArgs a, int splits) {
   }
 }
 
+// ---- streaming version (default when the planes are 16-byte aligned) -------------------
+// det and tag of the CTA's pixel range are pulled through a ring of shared-memory stages by 1-D
+// bulk async copies (cp.async.bulk + mbarrier complete_tx) issued by a producer warp; full/empty
+// mbarriers, no CTA-wide barrier in the loop: NS-1 stages (tens of KB per CTA) are in flight
+// independent of registers and occupancy -- the v1 kernel above had one 16-byte load per thread
+// in flight and ran at 30 % of the HBM peak.  All persons missing the joint (up to RF_PMAX per
+// pass) are evaluated against the stage while it sits in shared memory, so the maps are read
+// from DRAM once whatever the number of persons.  A thread owns 4 pixel pairs per stage; per
+// person it reduces them to one 64-bit key (order(score) << 32 | ~index: np.argmax's first
+// maximum) before touching the shared per-person best, and it evaluates a pixel only if
+// det >= the person's current lower bound, since score <= det.
+constexpr int RF_PMAX = 32;
+constexpr int RF_CH = 2048;                       // pixels per stage
+constexpr int RF_CONSUMERS = 16;
+constexpr int RFS_THREADS = (RF_CONSUMERS + 1) * 32;
+constexpr int RF_PAIRS = RF_CH / 2 / (RF_CONSUMERS * 32);   // pixel pairs per thread per stage
+constexpr unsigned RF_LB0 = 0x00800000u;          // order key of -FLT_MAX: -inf padding never passes
+
+template <int T>
+__global__ void __launch_bounds__(RFS_THREADS)
+refine_stream_kernel(RefineArgs a, int splits, int NS) {
+  extern __shared__ __align__(128) unsigned char rf_ring_raw[];
+  __shared__ int plist[RF_LIST_CAP];
+  __shared__ int pcount;
+  __shared__ float sprev[RF_PMAX][MAXT];
+  __shared__ unsigned int slb[RF_PMAX];      // order keys of the per-person lower bounds
+  __shared__ unsigned int slbmin;
+  __shared__ unsigned long long sbest[RF_PMAX];
+  __shared__ __align__(8) unsigned long long full_bar[4];
+  __shared__ __align__(8) unsigned long long empty_bar[4];
+
+  float* ring = reinterpret_cast<float*>(rf_ring_raw);
+  const int plane = blockIdx.x;
+  const int split = blockIdx.y;
+  const int n = plane / a.J, j = plane - n * a.J;
+  const int width = 3 + a.T;
+  const int P = min(a.count[n], a.Pmax);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- persons of this image that miss joint j (warp 0 compacts in person order)
+  if (tid == 0) pcount = 0;
+  __syncthreads();
+  if (warp == 0) {
+    int cnt = 0;
+    for (int base = 0; base < P; base += 32) {
+      const int p = base + lane;
+      bool miss = false;
+      if (p < P) {
+        const size_t pi = (size_t)n * a.Pmax + p;
+        miss = a.valid[pi] && (a.ans[(pi * a.J + j) * width + 2] == 0.0f);
+      }
+      const unsigned m = __ballot_sync(FULL_MASK, miss);
+      if (miss) {
+        const int slot = cnt + __popc(m & ((1u << lane) - 1u));
+        if (slot < RF_LIST_CAP) plist[slot] = p;
+      }
+      cnt += __popc(m);
+    }
+    if (lane == 0) {
+      pcount = min(cnt, RF_LIST_CAP);
+      for (int s = 0; s < NS; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), RF_CONSUMERS);
+      }
+      fence_mbar_init();
+    }
+  }
+  __syncthreads();
+  const int np = pcount;
+  if (np == 0) return;
+
+  const int HW = a.H * a.W;
+  const int jt = (a.Jt == a.J) ? j : 0;
+  const float* __restrict__ dplane = a.det + (size_t)plane * HW;
+  const float* __restrict__ tplane = a.tag + ((size_t)n * a.Jt + jt) * (size_t)HW * T;
+  const int ngroups = HW >> 2;
+  const int g0 = (int)(((long long)ngroups * split) / splits);
+  const int g1 = (int)(((long long)ngroups * (split + 1)) / splits);
+  const int px0 = g0 << 2, px1 = g1 << 2;
+  if (px1 <= px0) return;
+  const int nst = (px1 - px0 + RF_CH - 1) / RF_CH;
+  const int passes = (np + RF_PMAX - 1) / RF_PMAX;
+  const int total = nst * passes;
+  constexpr int STAGE_FLOATS = RF_CH * (1 + T);
+
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+  const uint32_t ring0 = smem_u32(ring);
+  if (warp == RF_CONSUMERS) {
+    // ---- producer
+    if (lane == 0) {
+      int slot = 0, st = 0;
+      uint32_t ephase = 1;                       // first wait on a fresh barrier passes
+      for (int k = 0; k < total; ++k) {
+        mbar_wait(empty0 + 8u * slot, ephase);
+        const int p0 = px0 + st * RF_CH;
+        const uint32_t cnt = (uint32_t)min(RF_CH, px1 - p0);
+        const uint32_t bar = full0 + 8u * slot;
+        const uint32_t dst = ring0 + (uint32_t)slot * (STAGE_FLOATS * 4u);
+        mbar_expect_tx(bar, cnt * 4u * (1 + T));
+        bulk_load_1d(dst, dplane + p0, cnt * 4u, bar);
+        bulk_load_1d(dst + RF_CH * 4u, tplane + (size_t)p0 * T, cnt * 4u * T, bar);
+        if (++st == nst) st = 0;
+        if (++slot == NS) { slot = 0; ephase ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // ---- consumers (named barrier 1 at pass boundaries)
+  const float ninf = __int_as_float(0xff800000);
+  int slot = 0, st = 0, q0 = 0, nq = 0;
+  uint32_t phase = 0;
+  for (int k = 0; k < total; ++k) {
+    if (st == 0) {
+      // new pass: flush the previous person batch, load the next
+      if (k > 0) {
+        named_bar_sync(1, RF_CONSUMERS * 32);
+        if (tid < nq && sbest[tid] != 0ull) {
+          const size_t pi = (size_t)n * a.Pmax + plist[q0 + tid];
+          atomicMax(&a.best[pi * a.J + j], sbest[tid]);
+        }
+        named_bar_sync(1, RF_CONSUMERS * 32);
+        q0 += RF_PMAX;
+      }
+      nq = min(RF_PMAX, np - q0);
+      if (tid < RF_PMAX) {
+        slb[tid] = RF_LB0;
+        sbest[tid] = 0ull;
+        if (tid < nq) {
+          const size_t pi = (size_t)n * a.Pmax + plist[q0 + tid];
+#pragma unroll
+          for (int t = 0; t < T; ++t) sprev[tid][t] = a.prev[pi * MAXT + t];
+        }
+      }
+      if (tid == 0) slbmin = RF_LB0;
+      named_bar_sync(1, RF_CONSUMERS * 32);
+    }
+    mbar_wait(full0 + 8u * slot, phase);
+    const float* sd = ring + (size_t)slot * STAGE_FLOATS;
+    const float* stg = sd + RF_CH;
+    const int p0 = px0 + st * RF_CH;
+    const int npairs = min(RF_CH, px1 - p0) >> 1;
+
+    float d[2 * RF_PAIRS];
+    float dmax = ninf;
+#pragma unroll
+    for (int m = 0; m < RF_PAIRS; ++m) {
+      const int pp = tid + m * (RF_CONSUMERS * 32);
+      float2 v = make_float2(ninf, ninf);
+      if (pp < npairs) v = *reinterpret_cast<const float2*>(sd + 2 * pp);
+      d[2 * m] = v.x; d[2 * m + 1] = v.y;
+      dmax = fmaxf(dmax, fmaxf(v.x, v.y));
+    }
+    const unsigned kmax = float_order_key(dmax);
+    if (kmax >= *(volatile unsigned int*)&slbmin) {
+      float tv[2 * RF_PAIRS][T];
+      unsigned kd[2 * RF_PAIRS];
+#pragma unroll
+      for (int m = 0; m < RF_PAIRS; ++m) {
+        const int pp = tid + m * (RF_CONSUMERS * 32);
+        kd[2 * m] = float_order_key(d[2 * m]);
+        kd[2 * m + 1] = float_order_key(d[2 * m + 1]);
+        if (pp < npairs) {
+          if (T == 2) {
+            const float4 w = *reinterpret_cast<const float4*>(stg + 4 * pp);
+            tv[2 * m][0] = w.x; tv[2 * m][T - 1] = w.y; tv[2 * m + 1][0] = w.z; tv[2 * m + 1][T - 1] = w.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+              for (int t = 0; t < T; ++t) tv[2 * m + e][t] = stg[(2 * pp + e) * T + t];
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int t = 0; t < T; ++t) tv[2 * m + e][t] = 0.0f;
+        }
+      }
+      for (int q = 0; q < nq; ++q) {
+        const unsigned lb = *(volatile unsigned int*)&slb[q];
+        if (kmax < lb) continue;
+        float pv[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) pv[t] = sprev[q][t];
+        unsigned long long best = 0ull;
+#pragma unroll
+        for (int e = 0; e < 2 * RF_PAIRS; ++e) {
+          if (kd[e] >= lb) {
+            float s = 0.0f;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              const float df = __fsub_rn(tv[e][t], pv[t]);
+              const float sq = __fmul_rn(df, df);
+              s = (t == 0) ? sq : __fadd_rn(s, sq);
+            }
+            const float score = __fsub_rn(d[e], rintf(__fsqrt_rn(s)));
+            const int idx = p0 + 2 * (tid + (e >> 1) * (RF_CONSUMERS * 32)) + (e & 1);
+            const unsigned long long key = ((unsigned long long)float_order_key(score) << 32) |
+                                           (unsigned long long)(0xffffffffu - (uint32_t)idx);
+            best = key > best ? key : best;
+          }
+        }
+        const unsigned kb = (unsigned)(best >> 32);
+        if (kb >= lb) {
+          atomicMax(&sbest[q], best);
+          if (kb > lb) {
+            const unsigned old = atomicMax(&slb[q], kb);
+            if (old <= *(volatile unsigned int*)&slbmin) {
+              unsigned mn = 0xffffffffu;
+              for (int qq = 0; qq < nq; ++qq) mn = min(mn, *(volatile unsigned int*)&slb[qq]);
+              atomicMax(&slbmin, mn);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0 + 8u * slot);
+    if (++st == nst) st = 0;
+    if (++slot == NS) { slot = 0; phase ^= 1u; }
+  }
+  named_bar_sync(1, RF_CONSUMERS * 32);
+  if (tid < nq && sbest[tid] != 0ull) {
+    const size_t pi = (size_t)n * a.Pmax + plist[q0 + tid];
+    atomicMax(&a.best[pi * a.J + j], sbest[tid]);
+  }
+}
+
 // one thread per (image, person, joint)
 __global__ void refine_fill_kernel(RefineArgs a) {
   const size_t total = (size_t)a.N * a.Pmax * a.J;
@@ -313,17 +545,47 @@ extern "C" int brtpe_refine(const float* det, const float* tag, float* ans, cons
   BRTPE_LAUNCH_CHECK();
 
   const int planes = N * J;
-  int splits = ceil_div(4 * num_sms(), planes);
-  const int ngroups = (H * W + 3) / 4;
-  const int max_splits = ngroups / (RF_THREADS * 4) > 0 ? ngroups / (RF_THREADS * 4) : 1;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  dim3 grid(planes, splits);
-  switch (T) {
-    case 1: refine_scan_kernel<1><<<grid, RF_THREADS, 0, st>>>(a, splits); break;
-    case 2: refine_scan_kernel<2><<<grid, RF_THREADS, 0, st>>>(a, splits); break;
-    case 3: refine_scan_kernel<3><<<grid, RF_THREADS, 0, st>>>(a, splits); break;
-    case 4: refine_scan_kernel<4><<<grid, RF_THREADS, 0, st>>>(a, splits); break;
+  const int HW = H * W;
+  const bool stream_ok = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(det) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(tag) & 15) == 0) && !getenv("BRTPE_REFINE_V1");
+  if (stream_ok) {
+    const int NS = (T <= 2) ? 4 : 3;
+    const size_t smem = (size_t)NS * RF_CH * (1 + T) * sizeof(float);
+    int splits = ceil_div(8 * num_sms(), planes);
+    const int max_splits = HW / (RF_CH * 4) > 0 ? HW / (RF_CH * 4) : 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    dim3 grid(planes, splits);
+#define BRTPE_RF_CASE(TT)                                                                         \
+  case TT: {                                                                                      \
+    static bool attr_set = false;                                                                 \
+    if (!attr_set) {                                                                              \
+      BRTPE_CUDA(cudaFuncSetAttribute(refine_stream_kernel<TT>,                                   \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));  \
+      attr_set = true;                                                                            \
+    }                                                                                             \
+    refine_stream_kernel<TT><<<grid, RFS_THREADS, smem, st>>>(a, splits, NS);                      \
+  } break;
+    switch (T) {
+      BRTPE_RF_CASE(1)
+      BRTPE_RF_CASE(2)
+      BRTPE_RF_CASE(3)
+      BRTPE_RF_CASE(4)
+    }
+#undef BRTPE_RF_CASE
+  } else {
+    int splits = ceil_div(4 * num_sms(), planes);
+    const int ngroups = (H * W + 3) / 4;
+    const int max_splits = ngroups / (RF_THREADS * 4) > 0 ? ngroups / (RF_THREADS * 4) : 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    dim3 grid(planes, splits);
+    switch (T) {
+      case 1: refine_scan_kernel<1><<<grid, RF_THREADS, 0, st>>>(a, splits); break;
+      case 2: refine_scan_kernel<2><<<grid, RF_THREADS, 0, st>>>(a, splits); break;
+      case 3: refine_scan_kernel<3><<<grid, RF_THREADS, 0, st>>>(a, splits); break;
+      case 4: refine_scan_kernel<4><<<grid, RF_THREADS, 0, st>>>(a, splits); break;
+    }
   }
   BRTPE_LAUNCH_CHECK();
 

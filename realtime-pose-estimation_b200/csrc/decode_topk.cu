@@ -20,6 +20,9 @@
 //     in a tiny second kernel, which also zero-fills (first zero-valued positions in
 //     index order, like topk over the NMS'd map), gathers the tags and writes (x, y).
 #include "common.cuh"
+#include "umma_ptx.cuh"
+
+#include <stdlib.h>
 
 namespace brtpe {
 
@@ -328,6 +331,237 @@ topk_merge_kernel(const float* __restrict__ det, int planes, int H, int W, int R
   topk_finalize<S>(L, det + (size_t)plane * H * W, plane, H, W, R, out, lane);
 }
 
+// ---- streaming version (the default whenever rows are 16-byte aligned) ----------------
+// The row band of a CTA is pulled through a ring of shared-memory stages by 1-D bulk async
+// copies (cp.async.bulk + mbarrier complete_tx) issued by a producer warp: stage = SR whole
+// rows = one contiguous range of the plane, NS stages, full/empty mbarriers, no CTA-wide
+// barrier in the loop.  NS-3 stages (tens of KB per CTA) are in flight whatever the register
+// budget is -- the v1 kernel above had one 16-byte load per thread in flight and ran at 22 %
+// of the HBM peak.  A consumer warp takes (row, 128-column window) items of the current stage.
+// Fast path per item: one LDS.128, max of the four values, one vote against the running
+// threshold (the largest K-th best any warp of the CTA -- or any CTA of the plane, through a
+// global word -- has proven so far).  Only row segments that still hold a candidate compute
+// the (2R+1)^2 maximum, from shared memory, with no halo lanes; survivors go into the warp's
+// register-resident sorted list (a shared list under a lock was 3x slower: r01k notes).
+constexpr int TKS_CONSUMERS = 8;
+constexpr int TKS_THREADS = (TKS_CONSUMERS + 1) * 32;
+
+template <int R, int S>
+__global__ void __launch_bounds__(TKS_THREADS)
+nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, int sr_shift,
+                       int ns_shift, unsigned long long* __restrict__ ws_keys,
+                       unsigned int* __restrict__ gthr, TopkOut out) {
+  extern __shared__ __align__(128) unsigned char tk_ring_raw[];
+  __shared__ unsigned long long sh[TKS_CONSUMERS][32 * S];
+  __shared__ __align__(8) unsigned long long full_bar[8];
+  __shared__ __align__(8) unsigned long long empty_bar[8];
+  __shared__ unsigned int s_thr;
+
+  float* ring = reinterpret_cast<float*>(tk_ring_raw);
+  const int plane = blockIdx.x;
+  const int split = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* __restrict__ plane_ptr = det + (size_t)plane * H * W;
+  const int SR = 1 << sr_shift, NS = 1 << ns_shift, ns_mask = NS - 1;
+  const int Y0 = (int)(((long long)H * split) / splits);
+  const int Y1 = (int)(((long long)H * (split + 1)) / splits);
+  const int ybase = max(0, Y0 - R), yend = min(H, Y1 + R);
+  const int nst = (yend - ybase + SR - 1) >> sr_shift;
+  const int stage_floats = SR * W;
+  const int ncw = (W + 127) >> 7;
+  const float ninf = neg_inf();
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), TKS_CONSUMERS);
+    }
+    s_thr = gthr ? *(volatile unsigned int*)(gthr + plane) : 0u;
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  TopList<S> L;
+  L.clear();
+  unsigned long long mink = 0ull;
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+  if (warp == TKS_CONSUMERS) {
+    // ---- producer: one lane keeps the ring full
+    if (lane == 0) {
+      for (int k = 0; k < nst; ++k) {
+        const int slot = k & ns_mask;
+        if (k >= NS) mbar_wait(empty0 + 8u * slot, ((k >> ns_shift) - 1) & 1);
+        const int r0 = ybase + (k << sr_shift);
+        const uint32_t bytes = (uint32_t)(min(SR, yend - r0) * W) * 4u;
+        const uint32_t bar = full0 + 8u * slot;
+        mbar_expect_tx(bar, bytes);
+        bulk_load_1d(smem_u32(ring) + (uint32_t)slot * (uint32_t)stage_floats * 4u, plane_ptr + (size_t)r0 * W,
+                     bytes, bar);
+        if (gthr && (k & 3) == 3) atomicMax(&s_thr, *(volatile unsigned int*)(gthr + plane));
+      }
+    }
+  } else {
+    // address of row y (ybase <= y < yend) in the ring
+    auto row_ptr = [&](int y) -> const float* {
+      const int rel = y - ybase;
+      return ring + (size_t)((rel >> sr_shift) & ns_mask) * stage_floats + (rel & (SR - 1)) * W;
+    };
+    for (int i = 0; i < nst; ++i) {
+      if (i == 0) mbar_wait(full0, 0);
+      if (i + 1 < nst) mbar_wait(full0 + 8u * ((i + 1) & ns_mask), ((i + 1) >> ns_shift) & 1);
+      const int s0 = ybase + (i << sr_shift);
+      const int rb = min(Y1, s0 + SR);
+      int yc = max(Y0, s0);
+      int cw = (warp + 5 * i) & (TKS_CONSUMERS - 1);     // rotate so no warp is always heavier
+      while (cw >= ncw) { cw -= ncw; ++yc; }
+      while (yc < rb) {
+        const int xb = (cw << 7) + 4 * lane;
+        cw += TKS_CONSUMERS;
+        const int ycur = yc;
+        while (cw >= ncw) { cw -= ncw; ++yc; }
+        const bool in = xb < W;                     // W % 4 == 0: a strip is all in or all out
+        float4 c = make_float4(ninf, ninf, ninf, ninf);
+        if (in) c = *reinterpret_cast<const float4*>(row_ptr(ycur) + xb);
+        const float t = __uint_as_float(*(volatile unsigned int*)&s_thr);
+        const float m = fmaxf(fmaxf(c.x, c.y), fmaxf(c.z, c.w));
+        if (!__any_sync(FULL_MASK, (m > 0.0f) && (m >= t))) continue;
+
+        // ---- slow path: full NMS of this row segment from shared memory
+        float4 vl = make_float4(ninf, ninf, ninf, ninf), vc = vl, vr = vl;
+        const bool hasl = in && (xb >= 4), hasr = in && (xb + 4 < W);
+#pragma unroll
+        for (int d = -R; d <= R; ++d) {
+          const int yy = ycur + d;
+          if (yy < 0 || yy >= H) continue;
+          const float* rr = row_ptr(yy);
+          if (in) vc = max4(vc, *reinterpret_cast<const float4*>(rr + xb));
+          if (R > 0) {
+            if (hasl) vl = max4(vl, *reinterpret_cast<const float4*>(rr + xb - 4));
+            if (hasr) vr = max4(vr, *reinterpret_cast<const float4*>(rr + xb + 4));
+          }
+        }
+        const float a[12] = {vl.x, vl.y, vl.z, vl.w, vc.x, vc.y, vc.z, vc.w, vr.x, vr.y, vr.z, vr.w};
+        const float cc[4] = {c.x, c.y, c.z, c.w};
+        unsigned long long key[4];
+        unsigned any = 0u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float hm = a[4 + q];
+#pragma unroll
+          for (int d = 1; d <= R; ++d) hm = fmaxf(hm, fmaxf(a[4 + q - d], a[4 + q + d]));
+          const float v = cc[q];
+          const bool cand = in && (hm == v) && (v > 0.0f) && (v >= t);
+          key[q] = cand ? make_sel_key(v, (uint32_t)(ycur * W + xb + q)) : 0ull;
+          any |= cand ? 1u : 0u;
+        }
+        if (!__any_sync(FULL_MASK, any != 0u)) continue;
+
+        // ---- insert into the warp's list
+        bool grew = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          unsigned mm = __ballot_sync(FULL_MASK, key[q] > mink);
+          while (mm) {
+            const int src = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const unsigned long long kk = __shfl_sync(FULL_MASK, key[q], src);
+            if (kk > mink) {
+              L.insert(kk, lane);
+              mink = L.min_key();
+              grew = true;
+            }
+          }
+        }
+        if (grew && lane == 0 && mink != 0ull) {
+          const unsigned nt = __float_as_uint(sel_key_value(mink));
+          if (nt > __float_as_uint(t)) {
+            atomicMax(&s_thr, nt);
+            if (gthr) atomicMax(gthr + plane, nt);
+          }
+        }
+      }
+      if (i >= 1) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8u * ((i - 1) & ns_mask));
+      }
+    }
+  }
+
+  // ---- merge the consumer warps of this CTA
+  if (warp < TKS_CONSUMERS) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) sh[warp][lane + 32 * s] = L.k[s];
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  for (int w = 1; w < TKS_CONSUMERS; ++w) {
+    for (int e = 0; e < 32 * S; ++e) {
+      const unsigned long long kk = sh[w][e];
+      if (kk == 0ull || kk <= mink) break;  // lists are sorted descending
+      L.insert(kk, lane);
+      mink = L.min_key();
+    }
+  }
+  if (splits == 1) {
+    topk_finalize<S>(L, plane_ptr, plane, H, W, R, out, lane);
+  } else {
+    unsigned long long* dst = ws_keys + ((size_t)plane * splits + split) * (32 * S);
+#pragma unroll
+    for (int s = 0; s < S; ++s) dst[lane + 32 * s] = L.k[s];
+  }
+}
+
+// stage geometry of the streaming kernel; false = use the v1 kernel
+static bool topk_stream_geometry(int planes, int H, int W, int R, int* sr_shift, int* ns_shift,
+                                 int* splits, size_t* smem) {
+  if (W % 4 != 0 || W < 4) return false;
+  int sr = 4;                                   // >= R for every supported kernel size
+  while (sr < 32 && (size_t)sr * 2 * W * 4 <= 12288) sr *= 2;
+  const size_t stage = (size_t)sr * W * 4;
+  int ns;
+  if (stage * 8 <= 168 * 1024) ns = 8;
+  else if (stage * 4 <= 168 * 1024) ns = 4;
+  else return false;                            // very wide maps: v1
+  int s = ceil_div(4 * num_sms(), planes);
+  // every split should own at least four stages of rows
+  const int max_splits = H / (4 * sr) > 0 ? H / (4 * sr) : 1;
+  if (s > max_splits) s = max_splits;
+  if (s > 64) s = 64;
+  if (s < 1) s = 1;
+  int sh = 0;
+  while ((1 << sh) < sr) ++sh;
+  *sr_shift = sh;
+  *ns_shift = ns == 8 ? 3 : 2;
+  *splits = s;
+  *smem = stage * ns;
+  (void)R;
+  return true;
+}
+
+template <int R, int S>
+static int launch_topk_stream(const float* det, int planes, int H, int W, int sr_shift, int ns_shift,
+                              int splits, size_t smem, unsigned long long* ws, unsigned int* gthr,
+                              const TopkOut& o, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    BRTPE_CUDA(cudaFuncSetAttribute(nms_topk_stream_kernel<R, S>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
+    attr_set = true;
+  }
+  if (gthr) BRTPE_CUDA(cudaMemsetAsync(gthr, 0, (size_t)planes * sizeof(unsigned int), st));
+  dim3 grid(planes, splits);
+  nms_topk_stream_kernel<R, S><<<grid, TKS_THREADS, smem, st>>>(det, H, W, splits, sr_shift,
+                                                                ns_shift, ws, gthr, o);
+  BRTPE_LAUNCH_CHECK();
+  if (splits > 1) {
+    const int wpb = 4;
+    topk_merge_kernel<S><<<ceil_div(planes, wpb), wpb * 32, 0, st>>>(det, planes, H, W, R, splits,
+                                                                     ws, o);
+    BRTPE_LAUNCH_CHECK();
+  }
+  return BRTPE_OK;
+}
+
 __global__ void nms_kernel(const float* __restrict__ det, float* __restrict__ out, int planes,
                            int H, int W, int R) {
   const size_t total = (size_t)planes * H * W;
@@ -397,8 +631,8 @@ extern "C" int brtpe_nms(const float* det, float* out, int planes, int H, int W,
 
 extern "C" size_t brtpe_topk_workspace_bytes(int N, int J, int H, int W, int K) {
   if (N <= 0 || J <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
-  // worst case splits = 64, S = 2
-  return (size_t)N * J * 64 * 64 * sizeof(unsigned long long);
+  // worst case splits = 64, S = 2; + one threshold word per plane (streaming kernel)
+  return (size_t)N * J * 64 * 64 * sizeof(unsigned long long) + align_up((size_t)N * J * 4, 256);
 }
 
 extern "C" int brtpe_nms_topk_gather(const float* det, const float* tag, int N, int J, int Jt,
@@ -421,19 +655,48 @@ extern "C" int brtpe_nms_topk_gather(const float* det, const float* tag, int N, 
     BRTPE_CHECK_ARG(Jt == J || Jt == 1, "brtpe_nms_topk_gather: Jt must be J or 1");
     BRTPE_CHECK_ARG(T >= 1, "brtpe_nms_topk_gather: T must be >= 1");
   }
+  const int S = (K <= 32) ? 1 : 2;
+  const int R = padding;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* ws = reinterpret_cast<unsigned long long*>(workspace);
+  TopkOut o{tag, val_k, ind_k, loc_k, tag_k, J, Jt, T, K};
+  const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(det) & 15) == 0);
+  {
+    int sr_shift, ns_shift, ssplits;
+    size_t smem;
+    if (vec && !getenv("BRTPE_TOPK_V1") &&
+        topk_stream_geometry(N * J, H, W, R, &sr_shift, &ns_shift, &ssplits, &smem)) {
+      const size_t keys = (size_t)N * J * ssplits * 32 * S * sizeof(unsigned long long);
+      const size_t sneed = align_up(keys, 256) + (size_t)N * J * sizeof(unsigned int);
+      if (sneed > workspace_bytes || !workspace) {
+        set_error("brtpe_nms_topk_gather: workspace %zu < %zu", workspace_bytes, sneed);
+        return BRTPE_EWORKSPACE;
+      }
+      unsigned int* gthr = ssplits > 1
+          ? reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(workspace) + align_up(keys, 256))
+          : nullptr;
+#define BRTPE_TOPKS_CASE(RR)                                                                     \
+  case RR:                                                                                       \
+    return (S == 1) ? launch_topk_stream<RR, 1>(det, N * J, H, W, sr_shift, ns_shift, ssplits,   \
+                                                smem, ws, gthr, o, st)                           \
+                    : launch_topk_stream<RR, 2>(det, N * J, H, W, sr_shift, ns_shift, ssplits,   \
+                                                smem, ws, gthr, o, st);
+      switch (R) {
+        BRTPE_TOPKS_CASE(0)
+        BRTPE_TOPKS_CASE(1)
+        BRTPE_TOPKS_CASE(2)
+        BRTPE_TOPKS_CASE(3)
+      }
+#undef BRTPE_TOPKS_CASE
+    }
+  }
   int band_h, nbands, ncg, splits;
   topk_geometry(N * J, H, W, &band_h, &nbands, &ncg, &splits);
-  const int S = (K <= 32) ? 1 : 2;
   const size_t need = (splits > 1) ? (size_t)N * J * splits * 32 * S * sizeof(unsigned long long) : 0;
   if (need > workspace_bytes || (need && !workspace)) {
     set_error("brtpe_nms_topk_gather: workspace %zu < %zu", workspace_bytes, need);
     return BRTPE_EWORKSPACE;
   }
-  TopkOut o{tag, val_k, ind_k, loc_k, tag_k, J, Jt, T, K};
-  const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(det) & 15) == 0);
-  cudaStream_t st = (cudaStream_t)stream;
-  unsigned long long* ws = reinterpret_cast<unsigned long long*>(workspace);
-  const int R = padding;
 #define BRTPE_TOPK_CASE(RR)                                                                    \
   case RR:                                                                                     \
     return (S == 1) ? launch_topk<RR, 1>(det, N * J, H, W, vec, band_h, nbands, ncg, splits, ws, o, st) \

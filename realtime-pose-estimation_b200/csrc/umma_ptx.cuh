@@ -309,4 +309,22 @@ __device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* map, int c
                : "memory");
 }
 
+// 1-D bulk async copy global -> shared (no tensor map): 16-byte aligned source, destination
+// and size; completion is counted in bytes on an mbarrier like a tensor TMA load.
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes,
+                                             uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// named barrier over a subset of the CTA's warps
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 }  // namespace brtpe

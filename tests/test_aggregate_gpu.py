@@ -63,3 +63,20 @@ def test_aggregate_multi_scale_flip(cuda_device):
         [(s, [t.cuda() for t in o], [t.cuda() for t in f]) for s, o, f in per], (96, 64))
     assert tag.shape == rtag.shape == (1, 17, 64, 96, 2)
     assert close(det, rdet) and close(tag, rtag)
+
+
+@pytest.mark.parametrize("flip", [True, False])
+@pytest.mark.parametrize("h4,w4", [(40, 56), (44, 40), (10, 100)])
+def test_aggregate_exact_x4_tma_path(cuda_device, flip, h4, w4):
+    """base = 4 x the 1/4-resolution map and W4 % 4 == 0: the TMA-staged 2x -> 2x cascade kernel
+    (tiles with aprons on every border, partial tiles in both directions)."""
+    g = torch.Generator().manual_seed(3 + h4)
+    outs = [torch.randn(3, 34, h4, w4, generator=g), torch.randn(3, 17, 2 * h4, 2 * w4, generator=g)]
+    outs_f = [torch.randn(3, 34, h4, w4, generator=g), torch.randn(3, 17, 2 * h4, 2 * w4, generator=g)] \
+        if flip else None
+    base = (4 * w4, 4 * h4)
+    rdet, rtag = A.aggregate_flip_multiscale_ref([(1.0, outs, outs_f)], base)
+    det, tag = inference.aggregate_flip_multiscale(
+        [(1.0, [o.cuda() for o in outs], [o.cuda() for o in outs_f] if flip else None)], base)
+    assert det.shape == rdet.shape and tag.shape == rtag.shape
+    assert close(det, rdet) and close(tag, rtag)
