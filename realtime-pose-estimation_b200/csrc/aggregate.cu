@@ -510,8 +510,8 @@ __global__ void __launch_bounds__(X4T_THREADS, 2)
 aggregate_x4_tma_kernel(AggArgs a, const __grid_constant__ X4Maps maps) {
   extern __shared__ unsigned char x4_dyn[];
   // TMA destinations must be 128-byte aligned: align by hand (the launch adds 128 bytes of slack)
-  unsigned char* x4_raw = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(x4_dyn) + 127) & ~static_cast<uintptr_t>(127));
+  // (offset arithmetic, not a pointer round trip, so the loads below stay LDS and not generic LD)
+  unsigned char* x4_raw = x4_dyn + ((128u - (smem_u32(x4_dyn) & 127u)) & 127u);
   __shared__ __align__(8) unsigned long long full_bar[X4_NSTG];
   __shared__ __align__(8) unsigned long long empty_bar[X4_NSTG];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -540,10 +540,12 @@ aggregate_x4_tma_kernel(AggArgs a, const __grid_constant__ X4Maps maps) {
       }
       int slot = 0;
       uint32_t ephase = 1;
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      const uint32_t ring0 = smem_u32(x4_raw);
       for (int it = 0; it < nitems; ++it) {
-        mbar_wait(smem_u32(&empty_bar[slot]), ephase);
-        const uint32_t bar = smem_u32(&full_bar[slot]);
-        const uint32_t base = smem_u32(x4_raw + (size_t)slot * X4_STAGE_BYTES);
+        mbar_wait(empty0 + 8u * slot, ephase);
+        const uint32_t bar = full0 + 8u * slot;
+        const uint32_t base = ring0 + (uint32_t)slot * X4_STAGE_BYTES;
         const bool is_det = it < a.J;
         const int c = is_det ? it : it - a.J;
         const int cf = (is_det || a.A == a.J) ? a.flip_index[c] : c;
@@ -594,8 +596,9 @@ aggregate_x4_tma_kernel(AggArgs a, const __grid_constant__ X4Maps maps) {
   constexpr int T = FLIP ? 2 : 1;
   int slot = 0;
   uint32_t phase = 0;
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
   for (int it = 0; it < nitems; ++it) {
-    mbar_wait(smem_u32(&full_bar[slot]), phase);
+    mbar_wait(full0 + 8u * slot, phase);
     const float* q0 = reinterpret_cast<const float*>(x4_raw + (size_t)slot * X4_STAGE_BYTES);
     const float* q1 = q0 + XQ0_SLOT / 4;
     const float* q0f = q1 + XQ1_SLOT / 4;
@@ -653,7 +656,7 @@ aggregate_x4_tma_kernel(AggArgs a, const __grid_constant__ X4Maps maps) {
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(smem_u32(&empty_bar[slot]));
+    if (lane == 0) mbar_arrive(empty0 + 8u * slot);
     if (++slot == X4_NSTG) { slot = 0; phase ^= 1u; }
   }
 }

@@ -396,7 +396,9 @@ refine_stream_kernel(RefineArgs a, int splits, int NS) {
       dmax = fmaxf(dmax, fmaxf(v.x, v.y));
     }
     const unsigned kmax = float_order_key(dmax);
-    if (kmax >= *(volatile unsigned int*)&slbmin) {
+    // warp-uniform from here on: one vote per (warp, person), one shared atomic per record
+    const unsigned wkmax = __reduce_max_sync(FULL_MASK, kmax);
+    if (wkmax >= *(volatile unsigned int*)&slbmin) {
       float tv[2 * RF_PAIRS][T];
       unsigned kd[2 * RF_PAIRS];
 #pragma unroll
@@ -423,7 +425,7 @@ refine_stream_kernel(RefineArgs a, int splits, int NS) {
       }
       for (int q = 0; q < nq; ++q) {
         const unsigned lb = *(volatile unsigned int*)&slb[q];
-        if (kmax < lb) continue;
+        if (wkmax < lb) continue;
         float pv[T];
 #pragma unroll
         for (int t = 0; t < T; ++t) pv[t] = sprev[q][t];
@@ -446,16 +448,20 @@ refine_stream_kernel(RefineArgs a, int splits, int NS) {
           }
         }
         const unsigned kb = (unsigned)(best >> 32);
-        if (kb >= lb) {
-          atomicMax(&sbest[q], best);
-          if (kb > lb) {
-            const unsigned old = atomicMax(&slb[q], kb);
-            if (old <= *(volatile unsigned int*)&slbmin) {
-              unsigned mn = 0xffffffffu;
-              for (int qq = 0; qq < nq; ++qq) mn = min(mn, *(volatile unsigned int*)&slb[qq]);
-              atomicMax(&slbmin, mn);
-            }
-          }
+        const unsigned wb = __reduce_max_sync(FULL_MASK, kb);
+        if (wb < lb || wb == 0u) continue;
+        // smallest index among the lanes holding the warp's best score
+        const unsigned wlo = __reduce_max_sync(FULL_MASK, kb == wb ? (unsigned)best : 0u);
+        unsigned old = 0xffffffffu;
+        if (lane == 0) {
+          atomicMax(&sbest[q], ((unsigned long long)wb << 32) | wlo);
+          if (wb > lb) old = atomicMax(&slb[q], wb);
+        }
+        old = __shfl_sync(FULL_MASK, old, 0);
+        if (old <= *(volatile unsigned int*)&slbmin) {
+          const unsigned mine = lane < nq ? *(volatile unsigned int*)&slb[lane] : 0xffffffffu;
+          const unsigned mn = __reduce_min_sync(FULL_MASK, mine);
+          if (lane == 0) atomicMax(&slbmin, mn);
         }
       }
     }

@@ -356,6 +356,7 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
   __shared__ __align__(8) unsigned long long full_bar[8];
   __shared__ __align__(8) unsigned long long empty_bar[8];
   __shared__ unsigned int s_thr;
+  __shared__ unsigned int s_ver[TKS_CONSUMERS];      // seqlock per published list
 
   float* ring = reinterpret_cast<float*>(tk_ring_raw);
   const int plane = blockIdx.x;
@@ -379,6 +380,8 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
     s_thr = gthr ? *(volatile unsigned int*)(gthr + plane) : 0u;
     fence_mbar_init();
   }
+  if (tid < TKS_CONSUMERS) s_ver[tid] = 0u;
+  for (int e = tid; e < TKS_CONSUMERS * 32 * S; e += TKS_THREADS) (&sh[0][0])[e] = 0ull;
   __syncthreads();
 
   TopList<S> L;
@@ -386,18 +389,52 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
   unsigned long long mink = 0ull;
   const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
   if (warp == TKS_CONSUMERS) {
-    // ---- producer: one lane keeps the ring full
-    if (lane == 0) {
-      for (int k = 0; k < nst; ++k) {
+    // ---- producer: lane 0 keeps the ring full; every fourth stage the (otherwise idle) warp
+    // selects the K-th best key over the lists the consumer warps have published -- a CTA-wide
+    // threshold, much sharper than any single warp's own K-th best
+    for (int k = 0; k < nst; ++k) {
+      if (lane == 0) {
         const int slot = k & ns_mask;
         if (k >= NS) mbar_wait(empty0 + 8u * slot, ((k >> ns_shift) - 1) & 1);
         const int r0 = ybase + (k << sr_shift);
         const uint32_t bytes = (uint32_t)(min(SR, yend - r0) * W) * 4u;
         const uint32_t bar = full0 + 8u * slot;
         mbar_expect_tx(bar, bytes);
-        bulk_load_1d(smem_u32(ring) + (uint32_t)slot * (uint32_t)stage_floats * 4u, plane_ptr + (size_t)r0 * W,
-                     bytes, bar);
-        if (gthr && (k & 3) == 3) atomicMax(&s_thr, *(volatile unsigned int*)(gthr + plane));
+        bulk_load_1d(smem_u32(ring) + (uint32_t)slot * (uint32_t)stage_floats * 4u,
+                     plane_ptr + (size_t)r0 * W, bytes, bar);
+      }
+      __syncwarp();
+      if ((k & 3) != 3) continue;
+      unsigned hi[TKS_CONSUMERS * S];
+#pragma unroll
+      for (int w = 0; w < TKS_CONSUMERS; ++w) {
+        const unsigned v1 = *(volatile unsigned int*)&s_ver[w];
+        __threadfence_block();
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+          hi[w * S + s] = (unsigned)(*(volatile unsigned long long*)&sh[w][lane + 32 * s] >> 32);
+        __threadfence_block();
+        const unsigned v2 = *(volatile unsigned int*)&s_ver[w];
+        if (!__all_sync(FULL_MASK, v1 == v2 && (v1 & 1u) == 0u)) {   // torn snapshot: skip it
+#pragma unroll
+          for (int s = 0; s < S; ++s) hi[w * S + s] = 0u;
+        }
+      }
+      unsigned prefix = 0u;
+      for (int bit = 31; bit >= 0; --bit) {
+        const unsigned cand = prefix | (1u << bit);
+        int cnt = 0;
+#pragma unroll
+        for (int e = 0; e < TKS_CONSUMERS * S; ++e) cnt += hi[e] >= cand ? 1 : 0;
+        if (__reduce_add_sync(FULL_MASK, cnt) >= out.K) prefix = cand;
+      }
+      if (lane == 0) {
+        unsigned nt = (prefix & 0x80000000u) ? (prefix & 0x7fffffffu) : 0u;   // positive floats only
+        if (gthr) {
+          if (nt) atomicMax(gthr + plane, nt);
+          nt = max(nt, *(volatile unsigned int*)(gthr + plane));
+        }
+        if (nt) atomicMax(&s_thr, nt);
       }
     }
   } else {
@@ -406,6 +443,8 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
       const int rel = y - ybase;
       return ring + (size_t)((rel >> sr_shift) & ns_mask) * stage_floats + (rel & (SR - 1)) * W;
     };
+    bool dirty = false;
+    unsigned ver = 0u;
     for (int i = 0; i < nst; ++i) {
       if (i == 0) mbar_wait(full0, 0);
       if (i + 1 < nst) mbar_wait(full0 + 8u * ((i + 1) & ns_mask), ((i + 1) >> ns_shift) & 1);
@@ -472,13 +511,24 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
             }
           }
         }
+        dirty |= grew;
         if (grew && lane == 0 && mink != 0ull) {
           const unsigned nt = __float_as_uint(sel_key_value(mink));
-          if (nt > __float_as_uint(t)) {
-            atomicMax(&s_thr, nt);
-            if (gthr) atomicMax(gthr + plane, nt);
-          }
+          if (nt > __float_as_uint(t)) atomicMax(&s_thr, nt);
         }
+      }
+      if (dirty) {
+        // publish the list for the producer warp's CTA-wide selection (seqlock: odd = writing)
+        if (lane == 0) *(volatile unsigned int*)&s_ver[warp] = ver + 1u;
+        __syncwarp();
+        __threadfence_block();
+#pragma unroll
+        for (int s = 0; s < S; ++s) *(volatile unsigned long long*)&sh[warp][lane + 32 * s] = L.k[s];
+        __threadfence_block();
+        __syncwarp();
+        ver += 2u;
+        if (lane == 0) *(volatile unsigned int*)&s_ver[warp] = ver;
+        dirty = false;
       }
       if (i >= 1) {
         __syncwarp();
@@ -487,11 +537,7 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
     }
   }
 
-  // ---- merge the consumer warps of this CTA
-  if (warp < TKS_CONSUMERS) {
-#pragma unroll
-    for (int s = 0; s < S; ++s) sh[warp][lane + 32 * s] = L.k[s];
-  }
+  // ---- merge the consumer warps of this CTA (every changed list was published at stage end)
   __syncthreads();
   if (warp != 0) return;
   for (int w = 1; w < TKS_CONSUMERS; ++w) {
