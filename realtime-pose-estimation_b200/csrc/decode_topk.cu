@@ -344,7 +344,7 @@ topk_merge_kernel(const float* __restrict__ det, int planes, int H, int W, int R
 // the (2R+1)^2 maximum, from shared memory, with no halo lanes; survivors go into the warp's
 // register-resident sorted list (a shared list under a lock was 3x slower: r01k notes).
 constexpr int TKS_CONSUMERS = 8;
-constexpr int TKS_THREADS = (TKS_CONSUMERS + 1) * 32;
+constexpr int TKS_THREADS = (TKS_CONSUMERS + 2) * 32;   // + producer warp + selector warp
 
 template <int R, int S>
 __global__ void __launch_bounds__(TKS_THREADS)
@@ -357,6 +357,7 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
   __shared__ __align__(8) unsigned long long empty_bar[8];
   __shared__ unsigned int s_thr;
   __shared__ unsigned int s_ver[TKS_CONSUMERS];      // seqlock per published list
+  __shared__ int s_done;
 
   float* ring = reinterpret_cast<float*>(tk_ring_raw);
   const int plane = blockIdx.x;
@@ -370,6 +371,7 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
   const int nst = (yend - ybase + SR - 1) >> sr_shift;
   const int stage_floats = SR * W;
   const int ncw = (W + 127) >> 7;
+  const int inv_ncw = (65536 + ncw - 1) / ncw;     // it / ncw == (it * inv_ncw) >> 16 for it < 2^11
   const float ninf = neg_inf();
 
   if (tid == 0) {
@@ -378,6 +380,7 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
       mbar_init(smem_u32(&empty_bar[s]), TKS_CONSUMERS);
     }
     s_thr = gthr ? *(volatile unsigned int*)(gthr + plane) : 0u;
+    s_done = 0;
     fence_mbar_init();
   }
   if (tid < TKS_CONSUMERS) s_ver[tid] = 0u;
@@ -389,11 +392,9 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
   unsigned long long mink = 0ull;
   const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
   if (warp == TKS_CONSUMERS) {
-    // ---- producer: lane 0 keeps the ring full; every fourth stage the (otherwise idle) warp
-    // selects the K-th best key over the lists the consumer warps have published -- a CTA-wide
-    // threshold, much sharper than any single warp's own K-th best
-    for (int k = 0; k < nst; ++k) {
-      if (lane == 0) {
+    // ---- producer: one lane keeps the ring full
+    if (lane == 0) {
+      for (int k = 0; k < nst; ++k) {
         const int slot = k & ns_mask;
         if (k >= NS) mbar_wait(empty0 + 8u * slot, ((k >> ns_shift) - 1) & 1);
         const int r0 = ybase + (k << sr_shift);
@@ -403,8 +404,13 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
         bulk_load_1d(smem_u32(ring) + (uint32_t)slot * (uint32_t)stage_floats * 4u,
                      plane_ptr + (size_t)r0 * W, bytes, bar);
       }
-      __syncwarp();
-      if ((k & 3) != 3) continue;
+      *(volatile int*)&s_done = 1;
+    }
+  } else if (warp == TKS_CONSUMERS + 1) {
+    // ---- selector: K-th best key over the lists the consumer warps have published = a CTA-wide
+    // threshold, much sharper than any single warp's own K-th best; exchanged with the other
+    // CTAs of the plane through gthr
+    while (*(volatile int*)&s_done == 0) {
       unsigned hi[TKS_CONSUMERS * S];
 #pragma unroll
       for (int w = 0; w < TKS_CONSUMERS; ++w) {
@@ -436,6 +442,7 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
         }
         if (nt) atomicMax(&s_thr, nt);
       }
+      __nanosleep(500);
     }
   } else {
     // address of row y (ybase <= y < yend) in the ring
@@ -445,80 +452,86 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
     };
     bool dirty = false;
     unsigned ver = 0u;
+
+    // full NMS of one 128-column row segment from shared memory; survivors go into L
+    auto slow_row = [&](int ycur, int xb, bool in, const float4& c, float t) {
+      float4 vl = make_float4(ninf, ninf, ninf, ninf), vc = vl, vr = vl;
+      const bool hasl = in && (xb >= 4), hasr = in && (xb + 4 < W);
+#pragma unroll
+      for (int d = -R; d <= R; ++d) {
+        const int yy = ycur + d;
+        if (yy < 0 || yy >= H) continue;
+        const float* rr = row_ptr(yy);
+        if (in) vc = max4(vc, *reinterpret_cast<const float4*>(rr + xb));
+        if (R > 0) {
+          if (hasl) vl = max4(vl, *reinterpret_cast<const float4*>(rr + xb - 4));
+          if (hasr) vr = max4(vr, *reinterpret_cast<const float4*>(rr + xb + 4));
+        }
+      }
+      const float a[12] = {vl.x, vl.y, vl.z, vl.w, vc.x, vc.y, vc.z, vc.w, vr.x, vr.y, vr.z, vr.w};
+      const float cc[4] = {c.x, c.y, c.z, c.w};
+      unsigned long long key[4];
+      unsigned any = 0u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float hm = a[4 + q];
+#pragma unroll
+        for (int d = 1; d <= R; ++d) hm = fmaxf(hm, fmaxf(a[4 + q - d], a[4 + q + d]));
+        const float v = cc[q];
+        const bool cand = in && (hm == v) && (v > 0.0f) && (v >= t);
+        key[q] = cand ? make_sel_key(v, (uint32_t)(ycur * W + xb + q)) : 0ull;
+        any |= cand ? 1u : 0u;
+      }
+      if (!__any_sync(FULL_MASK, any != 0u)) return;
+      bool grew = false;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        unsigned mm = __ballot_sync(FULL_MASK, key[q] > mink);
+        while (mm) {
+          const int src = __ffs(mm) - 1;
+          mm &= mm - 1;
+          const unsigned long long kk = __shfl_sync(FULL_MASK, key[q], src);
+          if (kk > mink) {
+            L.insert(kk, lane);
+            mink = L.min_key();
+            grew = true;
+          }
+        }
+      }
+      dirty |= grew;
+      if (grew && lane == 0 && mink != 0ull) {
+        const unsigned nt = __float_as_uint(sel_key_value(mink));
+        if (nt > __float_as_uint(t)) atomicMax(&s_thr, nt);
+      }
+    };
+
     for (int i = 0; i < nst; ++i) {
       if (i == 0) mbar_wait(full0, 0);
       if (i + 1 < nst) mbar_wait(full0 + 8u * ((i + 1) & ns_mask), ((i + 1) >> ns_shift) & 1);
       const int s0 = ybase + (i << sr_shift);
-      const int rb = min(Y1, s0 + SR);
-      int yc = max(Y0, s0);
-      int cw = (warp + 5 * i) & (TKS_CONSUMERS - 1);     // rotate so no warp is always heavier
-      while (cw >= ncw) { cw -= ncw; ++yc; }
-      while (yc < rb) {
-        const int xb = (cw << 7) + 4 * lane;
-        cw += TKS_CONSUMERS;
-        const int ycur = yc;
-        while (cw >= ncw) { cw -= ncw; ++yc; }
+      const int ra = max(Y0, s0), rb = min(Y1, s0 + SR);
+      // item = two consecutive rows x one 128-column window; rotate so no warp is always heavier
+      const int items = ((rb - ra + 1) >> 1) * ncw;
+      for (int it = (warp + 5 * i) & (TKS_CONSUMERS - 1); it < items; it += TKS_CONSUMERS) {
+        const int rp = (it * inv_ncw) >> 16;
+        const int xb = ((it - rp * ncw) << 7) + 4 * lane;
+        const int ya = ra + 2 * rp;
         const bool in = xb < W;                     // W % 4 == 0: a strip is all in or all out
-        float4 c = make_float4(ninf, ninf, ninf, ninf);
-        if (in) c = *reinterpret_cast<const float4*>(row_ptr(ycur) + xb);
+        const bool two = ya + 1 < rb;               // both rows lie in this stage: contiguous
+        const float* rowa = row_ptr(ya) + xb;
+        float4 c0 = make_float4(ninf, ninf, ninf, ninf), c1 = c0;
+        if (in) c0 = *reinterpret_cast<const float4*>(rowa);
+        if (in && two) c1 = *reinterpret_cast<const float4*>(rowa + W);
         const float t = __uint_as_float(*(volatile unsigned int*)&s_thr);
-        const float m = fmaxf(fmaxf(c.x, c.y), fmaxf(c.z, c.w));
-        if (!__any_sync(FULL_MASK, (m > 0.0f) && (m >= t))) continue;
-
-        // ---- slow path: full NMS of this row segment from shared memory
-        float4 vl = make_float4(ninf, ninf, ninf, ninf), vc = vl, vr = vl;
-        const bool hasl = in && (xb >= 4), hasr = in && (xb + 4 < W);
-#pragma unroll
-        for (int d = -R; d <= R; ++d) {
-          const int yy = ycur + d;
-          if (yy < 0 || yy >= H) continue;
-          const float* rr = row_ptr(yy);
-          if (in) vc = max4(vc, *reinterpret_cast<const float4*>(rr + xb));
-          if (R > 0) {
-            if (hasl) vl = max4(vl, *reinterpret_cast<const float4*>(rr + xb - 4));
-            if (hasr) vr = max4(vr, *reinterpret_cast<const float4*>(rr + xb + 4));
-          }
-        }
-        const float a[12] = {vl.x, vl.y, vl.z, vl.w, vc.x, vc.y, vc.z, vc.w, vr.x, vr.y, vr.z, vr.w};
-        const float cc[4] = {c.x, c.y, c.z, c.w};
-        unsigned long long key[4];
-        unsigned any = 0u;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float hm = a[4 + q];
-#pragma unroll
-          for (int d = 1; d <= R; ++d) hm = fmaxf(hm, fmaxf(a[4 + q - d], a[4 + q + d]));
-          const float v = cc[q];
-          const bool cand = in && (hm == v) && (v > 0.0f) && (v >= t);
-          key[q] = cand ? make_sel_key(v, (uint32_t)(ycur * W + xb + q)) : 0ull;
-          any |= cand ? 1u : 0u;
-        }
-        if (!__any_sync(FULL_MASK, any != 0u)) continue;
-
-        // ---- insert into the warp's list
-        bool grew = false;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          unsigned mm = __ballot_sync(FULL_MASK, key[q] > mink);
-          while (mm) {
-            const int src = __ffs(mm) - 1;
-            mm &= mm - 1;
-            const unsigned long long kk = __shfl_sync(FULL_MASK, key[q], src);
-            if (kk > mink) {
-              L.insert(kk, lane);
-              mink = L.min_key();
-              grew = true;
-            }
-          }
-        }
-        dirty |= grew;
-        if (grew && lane == 0 && mink != 0ull) {
-          const unsigned nt = __float_as_uint(sel_key_value(mink));
-          if (nt > __float_as_uint(t)) atomicMax(&s_thr, nt);
-        }
+        const float m0 = fmaxf(fmaxf(c0.x, c0.y), fmaxf(c0.z, c0.w));
+        const float m1 = fmaxf(fmaxf(c1.x, c1.y), fmaxf(c1.z, c1.w));
+        const unsigned hit = __ballot_sync(FULL_MASK, (m0 > 0.0f) && (m0 >= t)) ? 1u : 0u;
+        const unsigned hit1 = __ballot_sync(FULL_MASK, (m1 > 0.0f) && (m1 >= t)) ? 1u : 0u;
+        if (hit) slow_row(ya, xb, in, c0, t);
+        if (hit1) slow_row(ya + 1, xb, in, c1, t);
       }
       if (dirty) {
-        // publish the list for the producer warp's CTA-wide selection (seqlock: odd = writing)
+        // publish the list for the selector warp (seqlock: odd = writing)
         if (lane == 0) *(volatile unsigned int*)&s_ver[warp] = ver + 1u;
         __syncwarp();
         __threadfence_block();
