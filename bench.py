@@ -68,7 +68,9 @@ def make_input(batch, size, seed=1):
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    # started BEFORE the warm-up (nvidia-smi needs up to a second to come up on an 8-GPU box);
+    # only the samples whose timestamp falls inside the timed region are used
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -81,12 +83,20 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.tmp,
+                 "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.tmp,
                 stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
-    def stop(self):
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text, "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, t0=None, t1=None):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
@@ -102,6 +112,9 @@ class ClockSampler:
         for line in self.tmp.read().splitlines():
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 9:
+                continue
+            ts = self._stamp(parts[0])
+            if t0 is not None and ts is not None and not (t0 - 0.05 <= ts <= t1 + 0.05):
                 continue
             try:
                 sm.append(float(parts[1]))
@@ -247,23 +260,25 @@ def run_ours(args, rank, world, local_rank):
             finish_e2e(ans, count, scores)
 
     def timed(fn, steps, warmup, sample_clocks):
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
         for _ in range(warmup):
             fn()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank) if sample_clocks else None
-        if sampler:
-            sampler.start()
+        t_wall0 = time.time()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
         torch.cuda.synchronize()
+        t_wall1 = time.time()
         if world > 1:
             dist.barrier()
-        clocks = sampler.stop() if sampler else None
+        clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -120,6 +120,19 @@ int brtpe_bilinear_resize(const float* src, long long src_plane_stride, int plan
                           int Wi, float* dst, int Ho, int Wo, int dst_inner, int dst_off,
                           int align_corners, void* stream);
 
+/* Image pre-processing of the teacher-inference driver, fused:
+ *   cv2.warpAffine(image, trans, (Wo, Ho))  -- rtpe/third_party/transforms.py:183-190 (uint8 HxWx3,
+ *       INTER_LINEAR, BORDER_CONSTANT 0; OpenCV's fixed-point arithmetic reproduced bit for bit)
+ *   torchvision ToTensor() + Normalize(mean, std) -- teacher_inference.py:70-73, :79
+ * img: device uint8 (Hs, Ws, 3) with row pitch src_pitch bytes; trans_host: host double[6], the
+ * forward 2x3 matrix exactly as the reference hands it to cv2.warpAffine; mean_host / std_host:
+ * host float[3].  out_f32: device (3, Ho, Wo) float32 = ((u8 / 255) - mean) / std, or NULL;
+ * out_u8: device (Ho, Wo, 3) uint8 = the warped image, or NULL (at least one is required). */
+int brtpe_preprocess_warp_normalize(const uint8_t* img, int Hs, int Ws, int src_pitch,
+                                    const double* trans_host, int Ho, int Wo,
+                                    const float* mean_host, const float* std_host, float* out_f32,
+                                    uint8_t* out_u8, void* stream);
+
 /* Flip-test / multi-scale aggregation of ONE scale (upstream HigherHRNet
  * get_multi_stage_outputs + aggregate_results; in-tree callers legacy/valid_ae_avg.py:176-185,
  * legacy/valid_ae1dim.py:176-191; configuration legacy/distillation.py:85-92):

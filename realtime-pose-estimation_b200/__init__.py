@@ -12,4 +12,7 @@ from .hhrnet import PoseHigherResolutionNet, BasicBlock, Bottleneck, HighResolut
 from .precision import network_to_half, tofp16, tofp32, BN_convert_float, \
     get_hrnet_w48_teacher, W48_KWARGS  # noqa: F401
 from .students import AttentionStudent, ContextAwareModule, SELayer, StemHRNet  # noqa: F401
+from .teacher_dump import TeacherDumpWriter, TeacherDumper, load_teacher_data, \
+    HEATMAPS_ORDER  # noqa: F401
+from . import preprocess  # noqa: F401
 from ._lib import BrtpeError, LIB_PATH  # noqa: F401

@@ -70,6 +70,8 @@ _SIGS = {
     "brtpe_refine_workspace_bytes": (C.c_size_t, [_I] * 4),
     "brtpe_refine": (_I, [_P, _P, _P, _P] + [_I] * 7 + [_P, C.c_size_t, _P]),
     "brtpe_bilinear_resize": (_I, [_P, C.c_longlong, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "brtpe_preprocess_warp_normalize": (_I, [_P, _I, _I, _I, C.POINTER(C.c_double), _I, _I,
+                                            C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, _P]),
     "brtpe_aggregate_scale": (_I, [_P, _P, _P, _P] + [_I] * 9 + [C.POINTER(C.c_int32), _I,
                                                                  C.c_float, _P, _P, _P]),
     "brtpe_conv_run": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),

@@ -442,7 +442,7 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
         }
         if (nt) atomicMax(&s_thr, nt);
       }
-      __nanosleep(500);
+      __nanosleep(1500);
     }
   } else {
     // address of row y (ybase <= y < yend) in the ring
