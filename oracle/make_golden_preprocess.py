@@ -63,6 +63,15 @@ def main():
         cases["scale_%d" % k] = scale
         if k in (0, 5):                       # float32 tensors are 4x the bytes: two cases only
             cases["tensor_%d" % k] = t
+    # post-processing (transforms.py:50-56, :195-202): person arrays back to image coordinates
+    for k, (h, w, size) in enumerate([(480, 640, 640), (555, 640, 640), (640, 427, 512)]):
+        dsize, center, scale = RT.get_multi_scale_size(np.zeros((h, w, 3), np.uint8), size, 1, 1)
+        persons = [rng.uniform(0, min(dsize), (17, 5)).astype(np.float32) for _ in range(3)]
+        final = RT.get_final_preds([persons], center, scale, [dsize[0], dsize[1]])
+        cases["post_hw_%d" % k] = np.array([h, w, size])
+        cases["post_in_%d" % k] = np.stack(persons)
+        cases["post_out_%d" % k] = np.stack(final)
+    cases["n_post"] = np.array(3)
     cases["n"] = np.array(6)
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, "preprocess_cases.npz"), **cases)

@@ -343,20 +343,18 @@ topk_merge_kernel(const float* __restrict__ det, int planes, int H, int W, int R
 // global word -- has proven so far).  Only row segments that still hold a candidate compute
 // the (2R+1)^2 maximum, from shared memory, with no halo lanes; survivors go into the warp's
 // register-resident sorted list (a shared list under a lock was 3x slower: r01k notes).
-constexpr int TKS_CONSUMERS = 8;
-constexpr int TKS_THREADS = (TKS_CONSUMERS + 2) * 32;   // + producer warp + selector warp
-
-template <int R, int S>
-__global__ void __launch_bounds__(TKS_THREADS)
+// NC consumer warps + producer warp + selector warp
+template <int R, int S, int NC>
+__global__ void __launch_bounds__((NC + 2) * 32)
 nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, int sr_shift,
                        int ns_shift, unsigned long long* __restrict__ ws_keys,
                        unsigned int* __restrict__ gthr, TopkOut out) {
   extern __shared__ __align__(128) unsigned char tk_ring_raw[];
-  __shared__ unsigned long long sh[TKS_CONSUMERS][32 * S];
+  __shared__ unsigned long long sh[NC][32 * S];
   __shared__ __align__(8) unsigned long long full_bar[8];
   __shared__ __align__(8) unsigned long long empty_bar[8];
   __shared__ unsigned int s_thr;
-  __shared__ unsigned int s_ver[TKS_CONSUMERS];      // seqlock per published list
+  __shared__ unsigned int s_ver[NC];      // seqlock per published list
   __shared__ int s_done;
 
   float* ring = reinterpret_cast<float*>(tk_ring_raw);
@@ -377,21 +375,21 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), TKS_CONSUMERS);
+      mbar_init(smem_u32(&empty_bar[s]), NC);
     }
     s_thr = gthr ? *(volatile unsigned int*)(gthr + plane) : 0u;
     s_done = 0;
     fence_mbar_init();
   }
-  if (tid < TKS_CONSUMERS) s_ver[tid] = 0u;
-  for (int e = tid; e < TKS_CONSUMERS * 32 * S; e += TKS_THREADS) (&sh[0][0])[e] = 0ull;
+  if (tid < NC) s_ver[tid] = 0u;
+  for (int e = tid; e < NC * 32 * S; e += ((NC + 2) * 32)) (&sh[0][0])[e] = 0ull;
   __syncthreads();
 
   TopList<S> L;
   L.clear();
   unsigned long long mink = 0ull;
   const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
-  if (warp == TKS_CONSUMERS) {
+  if (warp == NC) {
     // ---- producer: one lane keeps the ring full
     if (lane == 0) {
       for (int k = 0; k < nst; ++k) {
@@ -406,14 +404,14 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
       }
       *(volatile int*)&s_done = 1;
     }
-  } else if (warp == TKS_CONSUMERS + 1) {
+  } else if (warp == NC + 1) {
     // ---- selector: K-th best key over the lists the consumer warps have published = a CTA-wide
     // threshold, much sharper than any single warp's own K-th best; exchanged with the other
     // CTAs of the plane through gthr
     while (*(volatile int*)&s_done == 0) {
-      unsigned hi[TKS_CONSUMERS * S];
+      unsigned hi[NC * S];
 #pragma unroll
-      for (int w = 0; w < TKS_CONSUMERS; ++w) {
+      for (int w = 0; w < NC; ++w) {
         const unsigned v1 = *(volatile unsigned int*)&s_ver[w];
         __threadfence_block();
 #pragma unroll
@@ -431,7 +429,7 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
         const unsigned cand = prefix | (1u << bit);
         int cnt = 0;
 #pragma unroll
-        for (int e = 0; e < TKS_CONSUMERS * S; ++e) cnt += hi[e] >= cand ? 1 : 0;
+        for (int e = 0; e < NC * S; ++e) cnt += hi[e] >= cand ? 1 : 0;
         if (__reduce_add_sync(FULL_MASK, cnt) >= out.K) prefix = cand;
       }
       if (lane == 0) {
@@ -512,7 +510,7 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
       const int ra = max(Y0, s0), rb = min(Y1, s0 + SR);
       // item = two consecutive rows x one 128-column window; rotate so no warp is always heavier
       const int items = ((rb - ra + 1) >> 1) * ncw;
-      for (int it = (warp + 5 * i) & (TKS_CONSUMERS - 1); it < items; it += TKS_CONSUMERS) {
+      for (int it = (warp + 5 * i) & (NC - 1); it < items; it += NC) {
         const int rp = (it * inv_ncw) >> 16;
         const int xb = ((it - rp * ncw) << 7) + 4 * lane;
         const int ya = ra + 2 * rp;
@@ -553,7 +551,7 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
   // ---- merge the consumer warps of this CTA (every changed list was published at stage end)
   __syncthreads();
   if (warp != 0) return;
-  for (int w = 1; w < TKS_CONSUMERS; ++w) {
+  for (int w = 1; w < NC; ++w) {
     for (int e = 0; e < 32 * S; ++e) {
       const unsigned long long kk = sh[w][e];
       if (kk == 0ull || kk <= mink) break;  // lists are sorted descending
@@ -572,16 +570,24 @@ nms_topk_stream_kernel(const float* __restrict__ det, int H, int W, int splits, 
 
 // stage geometry of the streaming kernel; false = use the v1 kernel
 static bool topk_stream_geometry(int planes, int H, int W, int R, int* sr_shift, int* ns_shift,
-                                 int* splits, size_t* smem) {
+                                 int* splits, size_t* smem, int* nc) {
   if (W % 4 != 0 || W < 4) return false;
   int sr = 4;                                   // >= R for every supported kernel size
   while (sr < 32 && (size_t)sr * 2 * W * 4 <= 12288) sr *= 2;
+  if (const char* e = getenv("BRTPE_TOPK_SR")) sr = atoi(e);
   const size_t stage = (size_t)sr * W * 4;
   int ns;
   if (stage * 8 <= 168 * 1024) ns = 8;
   else if (stage * 4 <= 168 * 1024) ns = 4;
   else return false;                            // very wide maps: v1
+  if (const char* e = getenv("BRTPE_TOPK_NS")) ns = atoi(e);
+  *nc = 8;
+  if (const char* e = getenv("BRTPE_TOPK_NC")) *nc = atoi(e);
+  if ((ns != 4 && ns != 8) || (*nc != 8 && *nc != 16) || stage * ns > 200 * 1024 || sr < 4 ||
+      (sr & (sr - 1)))
+    return false;
   int s = ceil_div(4 * num_sms(), planes);
+  if (const char* e = getenv("BRTPE_TOPK_SPLITS")) s = atoi(e);
   // every split should own at least four stages of rows
   const int max_splits = H / (4 * sr) > 0 ? H / (4 * sr) : 1;
   if (s > max_splits) s = max_splits;
@@ -597,20 +603,20 @@ static bool topk_stream_geometry(int planes, int H, int W, int R, int* sr_shift,
   return true;
 }
 
-template <int R, int S>
-static int launch_topk_stream(const float* det, int planes, int H, int W, int sr_shift, int ns_shift,
-                              int splits, size_t smem, unsigned long long* ws, unsigned int* gthr,
-                              const TopkOut& o, cudaStream_t st) {
+template <int R, int S, int NC>
+static int launch_topk_stream_nc(const float* det, int planes, int H, int W, int sr_shift,
+                                 int ns_shift, int splits, size_t smem, unsigned long long* ws,
+                                 unsigned int* gthr, const TopkOut& o, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    BRTPE_CUDA(cudaFuncSetAttribute(nms_topk_stream_kernel<R, S>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
+    BRTPE_CUDA(cudaFuncSetAttribute(nms_topk_stream_kernel<R, S, NC>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   if (gthr) BRTPE_CUDA(cudaMemsetAsync(gthr, 0, (size_t)planes * sizeof(unsigned int), st));
   dim3 grid(planes, splits);
-  nms_topk_stream_kernel<R, S><<<grid, TKS_THREADS, smem, st>>>(det, H, W, splits, sr_shift,
-                                                                ns_shift, ws, gthr, o);
+  nms_topk_stream_kernel<R, S, NC><<<grid, (NC + 2) * 32, smem, st>>>(det, H, W, splits, sr_shift,
+                                                                     ns_shift, ws, gthr, o);
   BRTPE_LAUNCH_CHECK();
   if (splits > 1) {
     const int wpb = 4;
@@ -619,6 +625,17 @@ static int launch_topk_stream(const float* det, int planes, int H, int W, int sr
     BRTPE_LAUNCH_CHECK();
   }
   return BRTPE_OK;
+}
+
+template <int R, int S>
+static int launch_topk_stream(const float* det, int planes, int H, int W, int sr_shift, int ns_shift,
+                              int splits, size_t smem, int nc, unsigned long long* ws,
+                              unsigned int* gthr, const TopkOut& o, cudaStream_t st) {
+  if (nc == 16)
+    return launch_topk_stream_nc<R, S, 16>(det, planes, H, W, sr_shift, ns_shift, splits, smem, ws,
+                                           gthr, o, st);
+  return launch_topk_stream_nc<R, S, 8>(det, planes, H, W, sr_shift, ns_shift, splits, smem, ws, gthr,
+                                        o, st);
 }
 
 __global__ void nms_kernel(const float* __restrict__ det, float* __restrict__ out, int planes,
@@ -721,10 +738,10 @@ extern "C" int brtpe_nms_topk_gather(const float* det, const float* tag, int N, 
   TopkOut o{tag, val_k, ind_k, loc_k, tag_k, J, Jt, T, K};
   const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(det) & 15) == 0);
   {
-    int sr_shift, ns_shift, ssplits;
+    int sr_shift, ns_shift, ssplits, nc;
     size_t smem;
     if (vec && !getenv("BRTPE_TOPK_V1") &&
-        topk_stream_geometry(N * J, H, W, R, &sr_shift, &ns_shift, &ssplits, &smem)) {
+        topk_stream_geometry(N * J, H, W, R, &sr_shift, &ns_shift, &ssplits, &smem, &nc)) {
       const size_t keys = (size_t)N * J * ssplits * 32 * S * sizeof(unsigned long long);
       const size_t sneed = align_up(keys, 256) + (size_t)N * J * sizeof(unsigned int);
       if (sneed > workspace_bytes || !workspace) {
@@ -737,9 +754,9 @@ extern "C" int brtpe_nms_topk_gather(const float* det, const float* tag, int N, 
 #define BRTPE_TOPKS_CASE(RR)                                                                     \
   case RR:                                                                                       \
     return (S == 1) ? launch_topk_stream<RR, 1>(det, N * J, H, W, sr_shift, ns_shift, ssplits,   \
-                                                smem, ws, gthr, o, st)                           \
+                                                smem, nc, ws, gthr, o, st)                       \
                     : launch_topk_stream<RR, 2>(det, N * J, H, W, sr_shift, ns_shift, ssplits,   \
-                                                smem, ws, gthr, o, st);
+                                                smem, nc, ws, gthr, o, st);
       switch (R) {
         BRTPE_TOPKS_CASE(0)
         BRTPE_TOPKS_CASE(1)

@@ -52,6 +52,32 @@ def get_affine_transform(center, scale, output_size):
                      [0.0, s, float(dcy) - s * float(cy)]], dtype=np.float64)
 
 
+def get_inverse_affine_transform(center, scale, output_size):
+    """transforms.py:59-93 with inv = 1 (``cv2.getAffineTransform(dst, src)``): maps heat-map /
+    network-input coordinates back to the original image."""
+    m = get_affine_transform(center, scale, output_size)
+    s = m[0, 0]
+    return np.array([[1.0 / s, 0.0, -m[0, 2] / s], [0.0, 1.0 / s, -m[1, 2] / s]], dtype=np.float64)
+
+
+def transform_preds(coords, center, scale, output_size):
+    """transforms.py:50-56: columns 0:2 of ``coords`` (P, >=2) through the inverse transform, the
+    other columns (score, tags) unchanged; returns a copy like the reference."""
+    target = coords.copy()
+    t = get_inverse_affine_transform(center, scale, output_size)
+    if coords.shape[0]:
+        xy1 = np.concatenate([coords[:, 0:2].astype(np.float64),
+                              np.ones((coords.shape[0], 1))], 1)
+        target[:, 0:2] = xy1 @ t.T
+    return target
+
+
+def get_final_preds(grouped_joints, center, scale, heatmap_size):
+    """transforms.py:195-202: ``grouped_joints = [list of (J, 3+T) person arrays]`` (the first
+    element of ``HeatmapParser.parse``'s result) -> one transformed array per person."""
+    return [transform_preds(person, center, scale, heatmap_size) for person in grouped_joints[0]]
+
+
 def _as_device_u8(image, device):
     if isinstance(image, np.ndarray):
         image = torch.from_numpy(np.ascontiguousarray(image))

@@ -177,3 +177,60 @@ def test_errors_are_loud(cuda_device):
     hp2 = rtpe_b200.HeatmapParser(nms_ksize=5, nms_padding=1, **PARSER_KW)
     with pytest.raises(rtpe_b200.BrtpeError):
         hp2.nms(det.cuda())
+
+
+@pytest.mark.parametrize("k,people,dense", [(3, 30, True), (7, 30, True), (5, 40, True), (5, 64, False),
+                                            (1, 30, True)])
+def test_topk_stream_kernel_variants(cuda_device, k, people, dense):
+    """the bulk-copy streaming top-k (rows 16-byte aligned) for every NMS radius, for K > 32 (two
+    list slots per lane) and for dense maps where almost every row segment holds a candidate."""
+    g = torch.Generator().manual_seed(31 * k + people)
+    if dense:
+        det = torch.randn(3, 17, 72, 256, generator=g) * 0.2
+        tag = torch.randn(3, 17, 72, 256, 2, generator=g)
+    else:
+        det, tag = rtpe_b200.synth_decode_batch(3, height=200, width=132, tag_dims=2, seed=9)
+    hp, p = make_parser(max_num_people=people, nms_ksize=k, nms_padding=(k - 1) // 2)
+    got = hp.top_k(det.cuda(), tag.cuda())
+    want = G.top_k_ref(det.numpy(), tag.numpy(), p)
+    for key in ("val_k", "loc_k", "tag_k"):
+        assert np.array_equal(got[key], want[key]), key
+
+
+def test_topk_stream_full_size_bands(cuda_device):
+    """640 x 640 maps of one image: 17 planes split into many row bands per plane (the global
+    threshold word and the merge kernel), against the oracle."""
+    det, tag = rtpe_b200.synth_decode_batch(1, height=640, width=640, tag_dims=2, seed=21)
+    det = det + 0.02 * torch.randn(det.shape, generator=torch.Generator().manual_seed(3))
+    hp, p = make_parser()
+    got = hp.top_k(det.cuda(), tag.cuda())
+    want = G.top_k_ref(det.numpy(), tag.numpy(), p)
+    for key in ("val_k", "loc_k", "tag_k"):
+        assert np.array_equal(got[key], want[key]), key
+
+
+@pytest.mark.parametrize("t", [1, 3])
+def test_refine_more_missing_persons_than_one_pass(cuda_device, t):
+    """40 persons that all miss joints 0-2 (their peaks stay below the detection threshold): the
+    streaming refine kernel evaluates them in two passes of 32 persons over the same maps."""
+    h = w = 160
+    g = torch.Generator().manual_seed(4)
+    det = torch.rand(1, 17, h, w, generator=g) * 0.01
+    tag = torch.randn(1, 17, h, w, t, generator=g) * 0.01
+    pid = 0
+    for y in range(10, 150, 20):
+        for x in range(10, 150, 20):
+            if pid >= 40:
+                break
+            for j in range(17):
+                yy, xx = y + (j % 4), x + (j // 4)
+                amp = 0.05 if j < 3 else 0.5                 # joints 0-2: never detected
+                det[0, j, yy, xx] = amp + 0.0005 * ((pid + 7 * j) % 40) + 0.00001 * j
+                tag[0, j, yy - 2:yy + 3, xx - 2:xx + 3, :] = 3.0 * pid
+            pid += 1
+    hp, p = make_parser()
+    got = hp.parse_batch(det.cuda(), tag.cuda(), True, True)
+    want = G.parse_batch_ref(det.numpy().copy(), tag.numpy().copy(), p, True, True)
+    assert want[0][0].shape[0] >= 40
+    assert (np.asarray(want[0][0])[:, :3, 2] > 0).any()      # refine filled missing joints
+    assert_people_equal(got, want)
