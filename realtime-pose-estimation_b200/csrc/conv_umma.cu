@@ -50,6 +50,7 @@ struct alignas(64) UmmaParams {
   FastDiv fd_nt, fd_xy, fd_x, fd_tw, fd_twh;
   const float* bias;
   int Hout, Wout, out_scale, out_oy, out_ox;
+  int res_l2_prefetch;    // epilogue prefetches the next tile's residual rows into L2
   EpiParams epi;
 };
 
@@ -193,7 +194,8 @@ conv_umma_kernel(const __grid_constant__ UmmaParams p) {
     const int Wm = p.Wm, Hm = p.Hm, N = p.N, Hout = p.Hout, Wout = p.Wout;
     const int out_scale = p.out_scale, out_oy = p.out_oy, out_ox = p.out_ox, acc_cols = p.acc_cols;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    // output pixel / channel offset of this thread in a tile (valid = inside the tensor)
+    auto locate = [&](int tile, size_t& opix, int& co0) -> bool {
       const int mt = (int)fdiv((uint32_t)tile, p.fd_nt);
       const int nt = tile - mt * n_tiles;
       const int tn_ = (int)fdiv((uint32_t)mt, p.fd_xy);
@@ -203,11 +205,28 @@ conv_umma_kernel(const __grid_constant__ UmmaParams p) {
       const int ym = ty_ * TH + th;
       const int n = tn_ * TN + tn;
       const bool valid = (tn < TN) && xm < Wm && ym < Hm && n < N;
-      const size_t opix =
-          valid ? ((size_t)n * Hout + (size_t)(ym * out_scale + out_oy)) * Wout +
-                      (size_t)(xm * out_scale + out_ox)
-                : 0;
-      const int co0 = nt * BN;
+      opix = valid ? ((size_t)n * Hout + (size_t)(ym * out_scale + out_oy)) * Wout +
+                         (size_t)(xm * out_scale + out_ox)
+                   : 0;
+      co0 = nt * BN;
+      return valid;
+    };
+    const bool res_pf = p.res_l2_prefetch != 0 && e.res != nullptr;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      size_t opix;
+      int co0;
+      const bool valid = locate(tile, opix, co0);
+      if (res_pf && tile + (int)gridDim.x < total_tiles) {
+        // the residual row of this thread's pixel in the NEXT tile -> L2 (no registers held): the
+        // HBM-bound 1x1 layers wait on exactly these loads (ncu: 70 % long-scoreboard)
+        size_t opix_n;
+        int co0_n;
+        if (locate(tile + (int)gridDim.x, opix_n, co0_n)) {
+          const char* rp = reinterpret_cast<const char*>(e.res + opix_n * e.res_ld + e.res_coff + co0_n);
+          for (int b = 0; b < BN * 2; b += 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + b));
+        }
+      }
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * acc_cols);
@@ -349,6 +368,11 @@ UmmaConvPrepared* umma_conv_prepare(const brtpe_conv_desc* d, const void* in, co
   p.bias = nullptr;
   p.Hout = d->Hout; p.Wout = d->Wout; p.out_scale = d->out_scale; p.out_oy = d->out_oy;
   p.out_ox = d->out_ox;
+  {
+    // on for residual layers unless BRTPE_UMMA_RES_PREFETCH=0 (A/B switch)
+    const char* e = getenv("BRTPE_UMMA_RES_PREFETCH");
+    p.res_l2_prefetch = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
   p.epi.out = nullptr; p.epi.res = nullptr;
   p.epi.out_ld = d->out_ld; p.epi.out_coff = d->out_coff; p.epi.res_ld = d->res_ld;
   p.epi.res_coff = d->res_coff; p.epi.Cout = d->Cout; p.epi.Cout_store = d->Cout_store;
