@@ -704,17 +704,16 @@ static int launch_x4_tma(const AggArgs& a, cudaStream_t st) {
     maps.y1f = maps.y1;
   }
   const size_t smem = (size_t)X4_NSTG * X4_STAGE_BYTES + 128;
-  static bool attr_set = false;
-  if (!attr_set) {
+  dim3 grid(ceil_div(a.W4, XT_W), ceil_div(a.H4, XT_H), a.N);
+  if (a.y0f) {
     BRTPE_CUDA(cudaFuncSetAttribute(aggregate_x4_tma_kernel<true>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    aggregate_x4_tma_kernel<true><<<grid, X4T_THREADS, smem, st>>>(a, maps);
+  } else {
     BRTPE_CUDA(cudaFuncSetAttribute(aggregate_x4_tma_kernel<false>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    aggregate_x4_tma_kernel<false><<<grid, X4T_THREADS, smem, st>>>(a, maps);
   }
-  dim3 grid(ceil_div(a.W4, XT_W), ceil_div(a.H4, XT_H), a.N);
-  if (a.y0f) aggregate_x4_tma_kernel<true><<<grid, X4T_THREADS, smem, st>>>(a, maps);
-  else aggregate_x4_tma_kernel<false><<<grid, X4T_THREADS, smem, st>>>(a, maps);
   return 1;
 }
 

@@ -564,12 +564,8 @@ extern "C" int brtpe_refine(const float* det, const float* tag, float* ans, cons
     dim3 grid(planes, splits);
 #define BRTPE_RF_CASE(TT)                                                                         \
   case TT: {                                                                                      \
-    static bool attr_set = false;                                                                 \
-    if (!attr_set) {                                                                              \
-      BRTPE_CUDA(cudaFuncSetAttribute(refine_stream_kernel<TT>,                                   \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));  \
-      attr_set = true;                                                                            \
-    }                                                                                             \
+    BRTPE_CUDA(cudaFuncSetAttribute(refine_stream_kernel<TT>,                                     \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));    \
     refine_stream_kernel<TT><<<grid, RFS_THREADS, smem, st>>>(a, splits, NS);                      \
   } break;
     switch (T) {

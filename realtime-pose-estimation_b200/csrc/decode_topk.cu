@@ -607,12 +607,9 @@ template <int R, int S, int NC>
 static int launch_topk_stream_nc(const float* det, int planes, int H, int W, int sr_shift,
                                  int ns_shift, int splits, size_t smem, unsigned long long* ws,
                                  unsigned int* gthr, const TopkOut& o, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    BRTPE_CUDA(cudaFuncSetAttribute(nms_topk_stream_kernel<R, S, NC>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  // per call (a few hundred ns): the attribute is per device, and callers may use several
+  BRTPE_CUDA(cudaFuncSetAttribute(nms_topk_stream_kernel<R, S, NC>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if (gthr) BRTPE_CUDA(cudaMemsetAsync(gthr, 0, (size_t)planes * sizeof(unsigned int), st));
   dim3 grid(planes, splits);
   nms_topk_stream_kernel<R, S, NC><<<grid, (NC + 2) * 32, smem, st>>>(det, H, W, splits, sr_shift,
