@@ -120,3 +120,29 @@ def test_config5_decode_stress_full_size(cuda_device):
     pm = min(a3.shape[1], ans.shape[1])
     live = (torch.arange(pm, device=det.device)[None, :] < c3[:, None])
     assert torch.equal(a3[:, :pm][live], ans[:64][perm][:, :pm][live])
+
+
+@pytest.mark.parametrize("early", [None, 0, 1, 3])
+def test_run_stream_equals_run_device(cuda_device, early):
+    """the pipelined host loop (double-buffered H2D copies, part of the next copy released while the
+    network runs) returns, batch by batch, exactly what the device-resident call returns -- different
+    host batches in flight must never mix."""
+    net = rtpe_b200.PoseHigherResolutionNet()
+    fill_params_deterministic(net, 5)
+    model = rtpe_b200.network_to_half(net).cuda().eval()
+    parser = rtpe_b200.HeatmapParser(**PARSER_KW)
+    pipe = inference.TeacherPipeline(model, parser, flip_test=True)
+    g = torch.Generator().manual_seed(2)
+    batches = [torch.randn(3, 3, 64, 96, generator=g).pin_memory() for _ in range(4)]
+    want = []
+    for xb in batches:
+        ans, count, scores = pipe.run_device(xb.cuda())
+        want.append((ans.cpu(), count.cpu(), scores.cpu()))
+    got = [(a.cpu(), c.cpu(), s.cpu()) for a, c, s in pipe.run_stream(iter(batches), early_images=early)]
+    assert len(got) == len(want)
+    for (ga, gc, gs), (wa, wc, ws) in zip(got, want):
+        assert torch.equal(gc, wc)
+        for i in range(ga.shape[0]):
+            n = int(gc[i])
+            assert torch.equal(ga[i, :n], wa[i, :n]) and torch.equal(gs[i, :n], ws[i, :n])
+    assert list(pipe.run_stream(iter([]))) == []
