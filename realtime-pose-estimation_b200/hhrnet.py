@@ -243,7 +243,7 @@ class _Recorder:
 
     # -- ops
     def conv(self, x, conv, bn, relu, residual=None, out=None, out_coff=0, in_coff=0,
-             cin_store=None, cout_store=None):
+             cin_store=None, cout_store=None, pad_cout=False):
         """conv (+BN) (+residual) (+ReLU) over virtual tensor x -> virtual tensor."""
         k = conv.kernel_size[0]
         s = conv.stride[0]
@@ -258,6 +258,13 @@ class _Recorder:
         w, b = self._fold(conv, bn)
         ktaps = _TAPS3 if k == 3 else [(0, 0)]
         wt = torch.stack([w[:, :, dy + (k // 2), dx + (k // 2)] for dy, dx in ktaps], 0)
+        if pad_cout and cout_store % 16 == 0 and cout < cout_store and self.mode == "bf16":
+            # heads with 17 / 34 real channels: zero weights + zero bias for the pad channels, so
+            # that the layer is a whole number of 16-channel chunks (vectorised epilogue; the pad
+            # channels were written as zeros before, too)
+            wt = torch.cat((wt, wt.new_zeros(wt.shape[0], cout_store - cout, wt.shape[2])), dim=1)
+            b = torch.cat((b, b.new_zeros(cout_store - cout)))
+            cout = cout_store
         d = self._desc(x, in_coff, cin_store, taps, s, ho, wo, out, 1, 0, 0, cout, cout_store,
                        out_coff, residual, relu)
         self._emit_conv(d, x, wt, b, residual, out, cin_store)
@@ -873,12 +880,13 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
         if cat:
             pad_store = cat_ld - c0
             R.conv(x, head0, None, False, out=x, out_coff=c0, in_coff=0, cin_store=c0,
-                   cout_store=pad_store)
+                   cout_store=pad_store, pad_cout=True)
             R.lane = 1 if par else 0
             R.to_nchw(x, head0.out_channels, c0, y0_out)
             R.lane = 0
         else:
-            y = R.conv(x, head0, None, False)
+            y = R.conv(x, head0, None, False, cout_store=(head0.out_channels + 15) // 16 * 16,
+                       pad_cout=True)
             R.to_nchw(y, head0.out_channels, 0, y0_out)
         for i in range(self.num_deconvs):
             dl = self.deconv_layers[i]
@@ -889,7 +897,8 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
                 t = R.conv(x, blk.conv1, blk.bn1, True)
                 x = R.conv(t, blk.conv2, blk.bn2, True, residual=x)
             head = self.final_layers[i + 1]
-            y = R.conv(x, head, None, False)
+            y = R.conv(x, head, None, False, cout_store=(head.out_channels + 15) // 16 * 16,
+                       pad_cout=True)
             yo = torch.empty((n, head.out_channels, x.h, x.w), dtype=odt, device=device)
             R.to_nchw(y, head.out_channels, 0, yo)
             outs.append(yo)
