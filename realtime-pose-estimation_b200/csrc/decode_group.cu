@@ -134,6 +134,18 @@ __device__ int munkres_warp(GroupSmem& sm, int n, int lane, int start_rule) {
   }
   colcov = 0u;
 
+  // zero mask of every row (lane i holds row i: bit j <=> C[i][j] == 0), rebuilt only when step 6
+  // changes the matrix: step 4 then finds the next uncovered zero with ONE vote instead of a
+  // scan of up to n rows with one shared-memory read and one vote each (same visiting order)
+  unsigned zrow = 0u;
+  auto rebuild_zero_masks = [&]() {
+    for (int i = 0; i < n; ++i) {
+      const unsigned m = __ballot_sync(FULL_MASK, act && (C[i * GRP_LD + lane] == 0.0));
+      if (lane == i) zrow = m;
+    }
+  };
+  rebuild_zero_masks();
+
   int step = 3;
   int z0r = 0, z0c = 0;
   int guard = 0;
@@ -155,17 +167,16 @@ __device__ int munkres_warp(GroupSmem& sm, int n, int lane, int start_rule) {
         const int i0 = start_rule ? 0 : row;
         const int j0 = start_rule ? 0 : col;
         int fr = -1, fc = -1;
-        for (int r = 0; r < n; ++r) {
-          int i = i0 + r;
-          if (i >= n) i -= n;
-          if ((rowcov >> i) & 1u) continue;
-          bool z = act && (C[i * GRP_LD + lane] == 0.0) && !((colcov >> lane) & 1u);
-          unsigned m = __ballot_sync(FULL_MASK, z);
-          if (m) {
-            unsigned low = m & ((1u << j0) - 1u);  // columns visited last in cyclic order
+        {
+          // rows with an uncovered zero; the first one in cyclic order starting at i0
+          const unsigned rows = __ballot_sync(
+              FULL_MASK, act && !((rowcov >> lane) & 1u) && (zrow & ~colcov) != 0u);
+          if (rows) {
+            const unsigned from = rows & ~((1u << i0) - 1u);
+            fr = __ffs(from ? from : rows) - 1;
+            const unsigned m = __shfl_sync(FULL_MASK, zrow, fr) & ~colcov;
+            const unsigned low = m & ((1u << j0) - 1u);  // columns visited last in cyclic order
             fc = low ? (31 - __clz(low)) : (31 - __clz(m));
-            fr = i;
-            break;
           }
         }
         if (fr < 0) {
@@ -223,6 +234,7 @@ __device__ int munkres_warp(GroupSmem& sm, int n, int lane, int start_rule) {
         }
       }
       __syncwarp();
+      rebuild_zero_masks();
       step = 4;
     }
   }
