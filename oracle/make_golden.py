@@ -91,6 +91,21 @@ def student_fixture(ref_students, name, h, w, seed):
           float(det.abs().max()))
 
 
+def cam_student_fixture(ref_students, name, h, w, seed):
+    """CamStudent (rtpe/students.py:502-592), default hyper-parameters, fp32."""
+    torch.manual_seed(0)
+    net = ref_students.CamStudent(None, "cpu", inplanes=48, num_stages=3, num_heatmaps=17, ae_dims=1,
+                                  half_precision=False).eval()
+    fill_params_deterministic(net, seed)
+    x = torch.randn(2, 3, h, w, generator=torch.Generator().manual_seed(seed + 1))
+    with torch.no_grad():
+        (pred,) = net(x)
+        (pred_up,) = net(x, out_hw=(21, 35))
+    np.savez_compressed(os.path.join(OUT, name), x=x.numpy(), pred=pred.numpy(), pred_up=pred_up.numpy(),
+                        seed=np.int64(seed), entries=np.int64(len(net.state_dict())))
+    print(name, tuple(pred.shape), tuple(pred_up.shape), float(pred.abs().max()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref_group, ref_model = load_reference()
@@ -101,6 +116,7 @@ def main():
     decode_fixture(ref_group, "decode_shared_tag.npz", 2, 48, 56, 1, 4, seed=24, tag_per_joint=False)
     model_fixture(ref_model, "hhrnet_64x96.npz", 64, 96, seed=7)
     student_fixture(load_reference_students(), "student_64x96.npz", 64, 96, seed=9)
+    cam_student_fixture(load_reference_students(), "cam_student_64x96.npz", 64, 96, seed=10)
 
 
 if __name__ == "__main__":

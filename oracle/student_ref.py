@@ -53,8 +53,9 @@ def stem_ref(sd, x, p="stem.1"):
     return x
 
 
-def cam_ref(sd, x, p):
-    """students.py:181-201 (no HDC upsampling: the dilated convs keep the size)."""
+def cam_ref(sd, x, p, dilations=None):
+    """students.py:181-201 (no HDC upsampling: the dilated convs keep the size).  ``dilations``:
+    the module's ``hdc_dilations`` (default 1..n, the attention student's)."""
     residual = F.relu(_bn(_conv(x, sd, p + ".residual.0"), sd, p + ".residual.1"))
     y = x.mean(dim=(2, 3))                                                    # AdaptiveAvgPool2d(1)
     y = F.relu(F.linear(y, sd[p + ".se.fc.0.weight"].to(x.dtype), sd[p + ".se.fc.0.bias"].to(x.dtype)))
@@ -62,7 +63,7 @@ def cam_ref(sd, x, p):
     outs = []
     i = 0
     while (p + ".hdcs.%d.0.weight" % i) in sd:
-        d = i + 1                                                             # dilations 1..n (:659,:688)
+        d = i + 1 if dilations is None else dilations[i]                      # 1..n (:659,:688)
         outs.append(F.relu(_bn(_conv(x, sd, p + ".hdcs.%d.0" % i, padding=d, dilation=d), sd,
                                p + ".hdcs.%d.1" % i)))
         i += 1
@@ -98,3 +99,26 @@ def attention_student_forward_ref(state_dict, x, dtype=torch.float32):
     det = hi + lo_up + lo_up
     det = _conv(det, sd, "det_top.0", padding=1)
     return att, det
+
+
+CAM_STUDENT_DILATIONS = (1, 2, 3, 5, 8, 12)                                  # students.py:563
+
+
+@torch.no_grad()
+def cam_student_forward_ref(state_dict, x, out_hw=None, dtype=torch.float32):
+    """``CamStudent.forward`` (students.py:568-592): -> [pred]; the sum of all context-aware
+    modules applied to the SAME mid-stem output, then ``hm_convs[-1]`` only (:581)."""
+    sd = state_dict
+    x = x.to(dtype)
+    s = stem_ref(sd, x)
+    s = F.relu(_bn(_conv(s, sd, "mid_stem.0", padding=1), sd, "mid_stem.1"))
+    n = 0
+    while ("cams.%d.residual.0.weight" % n) in sd:
+        n += 1
+    acc = cam_ref(sd, s, "cams.0", CAM_STUDENT_DILATIONS)
+    for i in range(1, n):
+        acc = acc + cam_ref(sd, s, "cams.%d" % i, CAM_STUDENT_DILATIONS)
+    out = _conv(acc, sd, "hm_convs.%d" % (n - 1), padding=1)
+    if out_hw is not None:
+        out = F.interpolate(out, out_hw, mode="bilinear", align_corners=True)
+    return [out]

@@ -257,3 +257,97 @@ class AttentionStudent(_PlanRunner, nn.Module):
         """students.py:733-768 -> (att, det)."""
         att, det = self._run_plans(x, 16)
         return att, det
+
+
+class CamStudent(_PlanRunner, nn.Module):
+    """Same constructor, attributes and ``forward(x, out_hw=None) -> [pred]`` as
+    ``rtpe.students.CamStudent`` (students.py:502-592): HigherHRNet stem -> one 3x3 mid-stem conv ->
+    ``num_stages`` context-aware modules (dilations 1, 2, 3, 5, 8, 12) that all read the mid-stem
+    output and are summed -> the LAST 3x3 head (the reference builds one head per stage and uses
+    only ``hm_convs[-1]``, :581) -> optional bilinear ``align_corners=True`` resize to ``out_hw``."""
+
+    def __init__(self, hhrnet_statedict_path=None, device="cuda", inplanes=48, num_stages=3,
+                 num_heatmaps=17, ae_dims=1, half_precision=True,
+                 init_fn=torch.nn.init.kaiming_normal_, trainable_stem=False, bn_momentum=0.1):
+        super().__init__()
+        self.bn_momentum = bn_momentum
+        self.num_stages = num_stages
+        self.num_heatmaps = num_heatmaps
+        self.ae_dims = ae_dims
+        self.stem = StemHRNet()
+        self.stem_out_chans = self.stem.layer1[-1].bn3.num_features
+        self.trainable_stem = trainable_stem
+        self.inplanes = inplanes
+        self.mid_stem = nn.Sequential(
+            nn.Conv2d(self.stem_out_chans, inplanes, kernel_size=3, stride=1, dilation=1, padding=1,
+                      bias=False),
+            nn.BatchNorm2d(inplanes, momentum=bn_momentum), nn.ReLU(inplace=True))
+        self.cams, self.hm_convs = self._make_body()
+        if init_fn is not None:
+            self.apply(lambda module: init_weights(module, init_fn, 0.0))
+        self.half_precision = bool(half_precision)
+        if half_precision:
+            self.stem = network_to_half(self.stem)
+        else:
+            self.stem = nn.Sequential(nn.Identity(), self.stem)
+        if hhrnet_statedict_path is not None:
+            self.stem[1].load_pretrained(hhrnet_statedict_path, device, check=False)
+        self._init_runner()
+        self.to(device)
+        self.device = device
+
+    def _make_body(self):
+        """students.py:555-566."""
+        hm_out_ch = self.num_heatmaps + self.ae_dims
+        cams, hms = nn.ModuleList(), nn.ModuleList()
+        for _ in range(self.num_stages):
+            cams.append(ContextAwareModule(self.inplanes, hdc_dilations=[1, 2, 3, 5, 8, 12]))
+            hms.append(nn.Conv2d(self.inplanes, hm_out_ch, kernel_size=3, padding=1, bias=True))
+        return cams, hms
+
+    def _ref_param(self):
+        return self.mid_stem[0].weight
+
+    def _mode(self):
+        return "bf16" if self.half_precision else "fp32"
+
+    _cam = AttentionStudent._cam
+
+    def _record(self, n, h, w, mode, device, in_is_half, out_half):
+        R = _Recorder(self, n, h, w, mode, self.conv_engine, device, in_is_half)
+        stem = self.stem[1]
+        if mode == "bf16" and self.conv_engine != L.ENGINE_FFMA:
+            x = R.stem_tc(stem.conv1, stem.bn1)
+        else:
+            x = R.stem(stem.conv1, stem.bn1)
+        x = R.conv(x, stem.conv2, stem.bn2, True)
+        for blk in stem.layer1:
+            res = x
+            if blk.downsample is not None:
+                res = R.conv(x, blk.downsample[0], blk.downsample[1], False)
+            t = R.conv(x, blk.conv1, blk.bn1, True)
+            t = R.conv(t, blk.conv2, blk.bn2, True)
+            x = R.conv(t, blk.conv3, blk.bn3, True, residual=res)
+        s = R.conv(x, self.mid_stem[0], self.mid_stem[1], True)
+        c = self.inplanes
+        outs = [self._cam(R, cam, s) for cam in self.cams]          # x = cam0(s) + cam1(s) + ...
+        acc = outs[0]
+        for k in range(1, len(outs), 3):                            # the fuse kernel sums up to 4 terms
+            terms = [acc] + outs[k:k + 3]
+            acc = R.fuse(terms, [0] * len(terms), c, False)
+        head = self.hm_convs[-1]
+        y = R.conv(acc, head, None, False)
+        cout = head.out_channels
+        out = torch.empty((n, cout, s.h, s.w), dtype=torch.float32, device=device)
+        R.to_nchw(y, cout, 0, out)
+        return R, [out]
+
+    def forward(self, x, out_hw=None, return_intermediate=False):
+        """students.py:568-592 -> [pred (N, num_heatmaps + ae_dims, H/4, W/4 or out_hw)]."""
+        if return_intermediate:
+            raise NotImplementedError                       # as the reference (:579)
+        (pred,) = self._run_plans(x, 4)
+        if out_hw is not None:
+            from .inference import bilinear_resize
+            pred = bilinear_resize(pred, out_hw, True)
+        return [pred]

@@ -78,3 +78,22 @@ def test_student_oracle_matches_reference_fixture():
         want = torch.from_numpy(want)
         assert got.shape == want.shape
         assert ((got - want).abs().max() / want.abs().max()).item() <= 1e-5
+
+
+def test_cam_student_oracle_matches_reference_fixture():
+    """CamStudent (students.py:502-592): the drop-in's parameter tree filled by (order, shape) gives
+    the weights the reference had, and the oracle reproduces the reference's outputs."""
+    from rtpe_b200.students import CamStudent
+    from oracle.student_ref import cam_student_forward_ref
+    z = np.load(os.path.join(GOLD, "cam_student_64x96.npz"))
+    net = CamStudent(None, "cpu", inplanes=48, num_stages=3, num_heatmaps=17, ae_dims=1,
+                     half_precision=False)
+    assert len(net.state_dict()) == int(z["entries"])
+    fill_params_deterministic(net, int(z["seed"]))
+    x = torch.from_numpy(z["x"])
+    (pred,) = cam_student_forward_ref(net.state_dict(), x)
+    (pred_up,) = cam_student_forward_ref(net.state_dict(), x, out_hw=tuple(z["pred_up"].shape[2:]))
+    for got, want in ((pred, z["pred"]), (pred_up, z["pred_up"])):
+        want = torch.from_numpy(want)
+        assert got.shape == want.shape
+        assert ((got - want).abs().max() / want.abs().max()).item() <= 1e-5

@@ -90,3 +90,30 @@ def test_student_oracle_vs_reference_class():
     assert [(k, tuple(v.shape)) for k, v in mine.state_dict().items()] == \
         [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
     mine.load_state_dict(ref.state_dict(), strict=True)
+
+
+def test_cam_student_oracle_vs_reference_class():
+    """oracle cam_student_forward_ref against rtpe.students.CamStudent itself,
+    same weights, same input, with and without the out_hw resize; also pins the drop-in's
+    state-dict layout to the reference's."""
+    from oracle.ref_loader import load_reference_students
+    from oracle.student_ref import cam_student_forward_ref
+    from oracle.weights import fill_params_deterministic
+    from rtpe_b200.students import CamStudent
+    S = load_reference_students()
+    torch.manual_seed(0)
+    ref = S.CamStudent(None, "cpu", inplanes=48, num_stages=3, num_heatmaps=17, ae_dims=1,
+                       half_precision=False).eval()
+    fill_params_deterministic(ref, 5)
+    x = torch.randn(2, 3, 48, 80, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        (a,) = ref(x)
+        (b,) = ref(x, out_hw=(30, 50))
+    (a2,) = cam_student_forward_ref(ref.state_dict(), x)
+    (b2,) = cam_student_forward_ref(ref.state_dict(), x, out_hw=(30, 50))
+    assert torch.equal(a, a2) and torch.equal(b, b2)
+    mine = CamStudent(None, "cpu", inplanes=48, num_stages=3, num_heatmaps=17, ae_dims=1,
+                      half_precision=False)
+    assert [(k, tuple(v.shape)) for k, v in mine.state_dict().items()] == \
+        [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
+    mine.load_state_dict(ref.state_dict(), strict=True)

@@ -86,3 +86,47 @@ def test_student_decode_shared_tag_plane(cuda_device):
     for (gp, gs), (wp, ws) in zip(got, want):
         assert gp.shape == np.asarray(wp).shape and np.array_equal(gp, wp)
         assert np.array_equal(np.asarray(gs, np.float32), np.asarray(ws, np.float32))
+
+
+# ---- CamStudent (rtpe/students.py:502-592)
+def _cam_student(half, seed):
+    from rtpe_b200.students import CamStudent
+    net = CamStudent(None, "cpu", inplanes=48, num_stages=3, num_heatmaps=17, ae_dims=1,
+                     half_precision=half)
+    fill_params_deterministic(net, seed)
+    return net.eval()
+
+
+def test_cam_student_fp32_vs_oracle_and_fixture(cuda_device):
+    from oracle.student_ref import cam_student_forward_ref
+    net = _cam_student(False, 21)
+    x = torch.randn(3, 3, 96, 128, generator=torch.Generator().manual_seed(22))
+    (ref,) = cam_student_forward_ref(net.state_dict(), x)
+    (ref_up,) = cam_student_forward_ref(net.state_dict(), x, out_hw=(50, 70))
+    net = net.cuda()
+    with torch.no_grad():
+        (pred,) = net(x.cuda())
+        (pred_up,) = net(x.cuda(), out_hw=(50, 70))
+    assert pred.shape == ref.shape == (3, 18, 24, 32) and pred_up.shape == ref_up.shape
+    assert _rel(pred, ref) <= 1e-4 and _rel(pred_up, ref_up) <= 1e-4
+    z = np.load(os.path.join(GOLD, "cam_student_64x96.npz"))
+    net = _cam_student(False, int(z["seed"])).cuda()
+    with torch.no_grad():
+        (pred,) = net(torch.from_numpy(z["x"]).cuda())
+        (pred_up,) = net(torch.from_numpy(z["x"]).cuda(), out_hw=tuple(z["pred_up"].shape[2:]))
+    assert _rel(pred, torch.from_numpy(z["pred"])) <= 1e-4
+    assert _rel(pred_up, torch.from_numpy(z["pred_up"])) <= 1e-4
+    with pytest.raises(NotImplementedError):
+        net(torch.from_numpy(z["x"]).cuda(), return_intermediate=True)
+
+
+def test_cam_student_bf16_vs_oracle(cuda_device):
+    from oracle.student_ref import cam_student_forward_ref
+    net = _cam_student(True, 23)
+    sd = {k: v.float() for k, v in net.state_dict().items()}
+    x = torch.randn(2, 3, 128, 128, generator=torch.Generator().manual_seed(24))
+    (ref,) = cam_student_forward_ref(sd, x)
+    net = net.cuda()
+    with torch.no_grad():
+        (pred,) = net(x.cuda())
+    assert _rel(pred, ref) <= 2e-2
