@@ -106,6 +106,20 @@ def cam_student_fixture(ref_students, name, h, w, seed):
     print(name, tuple(pred.shape), tuple(pred_up.shape), float(pred.abs().max()))
 
 
+def refiner_student_fixture(ref_students, name, h, w, seed):
+    """RefinerStudent (rtpe/students.py:302-386), default hyper-parameters, fp32."""
+    torch.manual_seed(0)
+    net = ref_students.RefinerStudent(None, "cpu", half_precision=False).eval()
+    fill_params_deterministic(net, seed)
+    x = torch.randn(2, 3, h, w, generator=torch.Generator().manual_seed(seed + 1))
+    with torch.no_grad():
+        pred = net(x)
+        pred_up = net(x, out_hw=(21, 35))
+    np.savez_compressed(os.path.join(OUT, name), x=x.numpy(), pred=pred.numpy(), pred_up=pred_up.numpy(),
+                        seed=np.int64(seed), entries=np.int64(len(net.state_dict())))
+    print(name, tuple(pred.shape), tuple(pred_up.shape), float(pred.abs().max()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref_group, ref_model = load_reference()
@@ -117,6 +131,7 @@ def main():
     model_fixture(ref_model, "hhrnet_64x96.npz", 64, 96, seed=7)
     student_fixture(load_reference_students(), "student_64x96.npz", 64, 96, seed=9)
     cam_student_fixture(load_reference_students(), "cam_student_64x96.npz", 64, 96, seed=10)
+    refiner_student_fixture(load_reference_students(), "refiner_student_64x96.npz", 64, 96, seed=11)
 
 
 if __name__ == "__main__":

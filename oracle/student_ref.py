@@ -122,3 +122,30 @@ def cam_student_forward_ref(state_dict, x, out_hw=None, dtype=torch.float32):
     if out_hw is not None:
         out = F.interpolate(out, out_hw, mode="bilinear", align_corners=True)
     return [out]
+
+
+def skip_conv_ref(sd, x, p):
+    """SkipConv.forward (students.py:73-90) with 3x3 / padding-1 convs (get_straight_skip_conv)."""
+    residual = _bn(_conv(x, sd, p + ".downsample.0"), sd, p + ".downsample.1")
+    i = 0
+    while (p + ".convs.%d.weight" % i) in sd:
+        k = sd[p + ".convs.%d.weight" % i].shape[-1]
+        x = F.relu(_bn(_conv(x, sd, p + ".convs.%d" % i, padding=k // 2), sd, p + ".bns.%d" % i))
+        i += 1
+    return F.relu(x + residual)
+
+
+@torch.no_grad()
+def refiner_student_forward_ref(state_dict, x, out_hw=None, dtype=torch.float32):
+    """``RefinerStudent.forward`` (students.py:374-386)."""
+    sd = state_dict
+    s = stem_ref(sd, x.to(dtype))
+    n = 0
+    while ("stages.%d.convs.0.weight" % n) in sd:
+        n += 1
+    y = skip_conv_ref(sd, s, "stages.0")
+    for i in range(1, n):
+        y = skip_conv_ref(sd, s + y, "stages.%d" % i)
+    if out_hw is not None:
+        y = F.interpolate(y, out_hw, mode="bilinear", align_corners=True)
+    return y

@@ -682,9 +682,18 @@ static void halo_n_tiling(int cout_store, int pairs, int workers, int* n_tiles, 
   int best_nt = 0, best_bn = 0;
   double best = 0;
   const int nt0 = (cp + HL_MAX_BN - 1) / HL_MAX_BN;
+  // tilings that cover the channels exactly (n_tiles * BN == Cout) keep the fast epilogue, which
+  // the one-tile and the CTA-pair modes require: when one exists, only those compete
+  bool have_exact = false;
   for (int nt = nt0; nt <= nt0 + 3; ++nt) {
     const int b = ((cp + nt - 1) / nt + 15) / 16 * 16;
     if (nt > nt0 && b < 96) break;
+    if (nt * b == cp) have_exact = true;
+  }
+  for (int nt = nt0; nt <= nt0 + 3; ++nt) {
+    const int b = ((cp + nt - 1) / nt + 15) / 16 * 16;
+    if (nt > nt0 && b < 96) break;
+    if (have_exact && nt * b != cp) continue;
     const long long items = (long long)pairs * nt;
     const double rounds = (double)((items + sms - 1) / sms);
     const double cost = rounds * mma_cycles(b) + 0.05 * nt;   // tie -> fewer tiles

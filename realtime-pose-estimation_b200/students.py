@@ -351,3 +351,144 @@ class CamStudent(_PlanRunner, nn.Module):
             from .inference import bilinear_resize
             pred = bilinear_resize(pred, out_hw, True)
         return [pred]
+
+
+class SkipConv(nn.Module):
+    """Parameter container of students.py:37-90: a chain of conv + BN + ReLU with a (1x1 conv + BN)
+    skip, ``relu(chain(x) + downsample(x))``."""
+
+    def __init__(self, in_chans, out_chans, ksizes, strides=None, dilations=None, paddings=None,
+                 downsample=None, bn_momentum=0.1):
+        super().__init__()
+        if strides is None:
+            strides = [1 for _ in in_chans]
+        if dilations is None:
+            dilations = [1 for _ in in_chans]
+        if paddings is None:
+            paddings = [0 for _ in in_chans]
+        assert len(in_chans) == len(out_chans) == len(ksizes) == len(strides) == len(dilations) == \
+            len(paddings), "Channels, ksizes, strides and dilations must be of same length!"
+        self.convs = nn.ModuleList(
+            [nn.Conv2d(i, o, kernel_size=k, stride=st, dilation=d, padding=p, bias=False)
+             for (i, o, k, st, d, p) in zip(in_chans, out_chans, ksizes, strides, dilations, paddings)])
+        self.bns = nn.ModuleList([nn.BatchNorm2d(o, momentum=bn_momentum) for o in out_chans])
+        self.relus = nn.ModuleList([nn.ReLU(inplace=True) for _ in out_chans])
+        self.downsample = downsample
+        self.final_relu = nn.ReLU(inplace=True)
+
+
+def get_straight_skip_conv(in_chans, out_chans, bn_momentum=0.1):
+    """students.py:93-112."""
+    assert len(in_chans) == len(out_chans), "in_chans and out_chans must have same length!"
+    n = len(in_chans)
+    downsample = nn.Sequential(
+        nn.Conv2d(in_chans[0], out_chans[-1], kernel_size=1, stride=1, padding=0, bias=False),
+        nn.BatchNorm2d(out_chans[-1], momentum=bn_momentum))
+    return SkipConv(in_chans, out_chans, [3] * n, [1] * n, [1] * n, [1] * n, downsample, bn_momentum)
+
+
+def _record_stem(R, stem, mode, conv_engine):
+    """StemHRNet.forward (students.py:252-264) on the recorder."""
+    if mode == "bf16" and conv_engine != L.ENGINE_FFMA:
+        x = R.stem_tc(stem.conv1, stem.bn1)
+    else:
+        x = R.stem(stem.conv1, stem.bn1)
+    x = R.conv(x, stem.conv2, stem.bn2, True)
+    for blk in stem.layer1:
+        res = x
+        if blk.downsample is not None:
+            res = R.conv(x, blk.downsample[0], blk.downsample[1], False)
+        t = R.conv(x, blk.conv1, blk.bn1, True)
+        t = R.conv(t, blk.conv2, blk.bn2, True)
+        x = R.conv(t, blk.conv3, blk.bn3, True, residual=res)
+    return x
+
+
+def _record_skip_conv(R, skc, x):
+    """SkipConv.forward (students.py:73-90): the last ReLU of the chain comes BEFORE the skip is
+    added, so the sum is a separate fuse op (relu(relu(c) + r) != relu(c + r))."""
+    def c16(conv):
+        return (conv.out_channels + 15) // 16 * 16
+    res = R.conv(x, skc.downsample[0], skc.downsample[1], False, cout_store=c16(skc.downsample[0]),
+                 pad_cout=True)
+    for conv, bn in zip(skc.convs, skc.bns):
+        if conv.kernel_size[0] not in (1, 3) or conv.stride[0] != 1:
+            raise NotImplementedError("SkipConv with kernel %s / stride %s" % (conv.kernel_size, conv.stride))
+        x = R.conv(x, conv, bn, True, cout_store=c16(conv), pad_cout=True)
+    return R.fuse([x, res], [0, 0], x.ld, True)          # pad channels are zeros on both sides
+
+
+class RefinerStudent(_PlanRunner, nn.Module):
+    """Same constructor, attributes and ``forward(x, out_hw=None) -> pred`` as
+    ``rtpe.students.RefinerStudent`` (students.py:302-386): HigherHRNet stem, then ``SkipConv`` stages
+    on the 256-channel stem output, ``x = stage_k(stem_out + x)``; the last stage ends in
+    ``num_heatmaps + ae_dims`` channels."""
+
+    def __init__(self, hhrnet_statedict_path=None, device="cuda", layers_per_stage=[3, 3, 3],
+                 num_heatmaps=17, ae_dims=1, half_precision=True,
+                 init_fn=torch.nn.init.kaiming_normal_, trainable_stem=False, bn_momentum=0.1):
+        super().__init__()
+        self.bn_momentum = bn_momentum
+        self.layers_per_stage = layers_per_stage
+        self.num_heatmaps = num_heatmaps
+        self.ae_dims = ae_dims
+        self.stem = StemHRNet()
+        self.stem_out_chans = self.stem.layer1[-1].bn3.num_features
+        self.trainable_stem = trainable_stem
+        self.stages = self._make_body()
+        if init_fn is not None:
+            self.apply(lambda module: init_weights(module, init_fn, 0.0))
+        self.half_precision = bool(half_precision)
+        if half_precision:
+            self.stem = network_to_half(self.stem)
+        else:
+            self.stem = nn.Sequential(nn.Identity(), self.stem)
+        if hhrnet_statedict_path is not None:
+            self.stem[1].load_pretrained(hhrnet_statedict_path, device, check=False)
+        self._init_runner()
+        self.to(device)
+        self.device = device
+
+    def save_body(self, out_path):
+        torch.save(self.stages.state_dict(), out_path)
+
+    def load_body(self, statedict_path):
+        self.stages.load_state_dict(torch.load(statedict_path))
+        self.invalidate_plans()
+
+    def _make_body(self):
+        """students.py:351-372."""
+        stages = nn.ModuleList()
+        ch = self.stem_out_chans
+        for n in self.layers_per_stage[:-1]:
+            stages.append(get_straight_skip_conv([ch] * n, [ch] * n, self.bn_momentum))
+        n = self.layers_per_stage[-1]
+        out_chans = [ch] * n
+        out_chans[-1] = self.num_heatmaps + self.ae_dims
+        stages.append(get_straight_skip_conv([ch] * n, out_chans, self.bn_momentum))
+        return stages
+
+    def _ref_param(self):
+        return self.stages[0].convs[0].weight
+
+    def _mode(self):
+        return "bf16" if self.half_precision else "fp32"
+
+    def _record(self, n, h, w, mode, device, in_is_half, out_half):
+        R = _Recorder(self, n, h, w, mode, self.conv_engine, device, in_is_half)
+        s = _record_stem(R, self.stem[1], mode, self.conv_engine)
+        x = _record_skip_conv(R, self.stages[0], s)
+        for st in self.stages[1:]:
+            x = _record_skip_conv(R, st, R.fuse([s, x], [0, 0], s.ld, False))
+        cout = self.stages[-1].convs[-1].out_channels
+        out = torch.empty((n, cout, s.h, s.w), dtype=torch.float32, device=device)
+        R.to_nchw(x, cout, 0, out)
+        return R, [out]
+
+    def forward(self, x, out_hw=None):
+        """students.py:374-386 -> pred (N, num_heatmaps + ae_dims, H/4, W/4 or out_hw)."""
+        (pred,) = self._run_plans(x, 4)
+        if out_hw is not None:
+            from .inference import bilinear_resize
+            pred = bilinear_resize(pred, out_hw, True)
+        return pred

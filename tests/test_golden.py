@@ -97,3 +97,20 @@ def test_cam_student_oracle_matches_reference_fixture():
         want = torch.from_numpy(want)
         assert got.shape == want.shape
         assert ((got - want).abs().max() / want.abs().max()).item() <= 1e-5
+
+
+def test_refiner_student_oracle_matches_reference_fixture():
+    """RefinerStudent (students.py:302-386)."""
+    from rtpe_b200.students import RefinerStudent
+    from oracle.student_ref import refiner_student_forward_ref
+    z = np.load(os.path.join(GOLD, "refiner_student_64x96.npz"))
+    net = RefinerStudent(None, "cpu", half_precision=False)
+    assert len(net.state_dict()) == int(z["entries"])
+    fill_params_deterministic(net, int(z["seed"]))
+    x = torch.from_numpy(z["x"])
+    pred = refiner_student_forward_ref(net.state_dict(), x)
+    pred_up = refiner_student_forward_ref(net.state_dict(), x, out_hw=tuple(z["pred_up"].shape[2:]))
+    for got, want in ((pred, z["pred"]), (pred_up, z["pred_up"])):
+        want = torch.from_numpy(want)
+        assert got.shape == want.shape
+        assert ((got - want).abs().max() / want.abs().max()).item() <= 1e-5

@@ -117,3 +117,26 @@ def test_cam_student_oracle_vs_reference_class():
     assert [(k, tuple(v.shape)) for k, v in mine.state_dict().items()] == \
         [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
     mine.load_state_dict(ref.state_dict(), strict=True)
+
+
+def test_refiner_student_oracle_vs_reference_class():
+    """oracle refiner_student_forward_ref against rtpe.students.RefinerStudent itself."""
+    from oracle.ref_loader import load_reference_students
+    from oracle.student_ref import refiner_student_forward_ref
+    from oracle.weights import fill_params_deterministic
+    from rtpe_b200.students import RefinerStudent
+    S = load_reference_students()
+    torch.manual_seed(0)
+    ref = S.RefinerStudent(None, "cpu", half_precision=False).eval()
+    fill_params_deterministic(ref, 7)
+    x = torch.randn(2, 3, 48, 80, generator=torch.Generator().manual_seed(8))
+    with torch.no_grad():
+        a = ref(x)
+        b = ref(x, out_hw=(30, 50))
+    a2 = refiner_student_forward_ref(ref.state_dict(), x)
+    b2 = refiner_student_forward_ref(ref.state_dict(), x, out_hw=(30, 50))
+    assert torch.equal(a, a2) and torch.equal(b, b2)
+    mine = RefinerStudent(None, "cpu", half_precision=False)
+    assert [(k, tuple(v.shape)) for k, v in mine.state_dict().items()] == \
+        [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
+    mine.load_state_dict(ref.state_dict(), strict=True)

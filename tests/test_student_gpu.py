@@ -130,3 +130,44 @@ def test_cam_student_bf16_vs_oracle(cuda_device):
     with torch.no_grad():
         (pred,) = net(x.cuda())
     assert _rel(pred, ref) <= 2e-2
+
+
+# ---- RefinerStudent (rtpe/students.py:302-386)
+def _refiner_student(half, seed):
+    from rtpe_b200.students import RefinerStudent
+    net = RefinerStudent(None, "cpu", half_precision=half)
+    fill_params_deterministic(net, seed)
+    return net.eval()
+
+
+def test_refiner_student_fp32_vs_oracle_and_fixture(cuda_device):
+    from oracle.student_ref import refiner_student_forward_ref
+    net = _refiner_student(False, 31)
+    x = torch.randn(3, 3, 64, 96, generator=torch.Generator().manual_seed(32))
+    ref = refiner_student_forward_ref(net.state_dict(), x)
+    ref_up = refiner_student_forward_ref(net.state_dict(), x, out_hw=(50, 70))
+    net = net.cuda()
+    with torch.no_grad():
+        pred = net(x.cuda())
+        pred_up = net(x.cuda(), out_hw=(50, 70))
+    assert pred.shape == ref.shape == (3, 18, 16, 24) and pred_up.shape == ref_up.shape
+    assert _rel(pred, ref) <= 1e-4 and _rel(pred_up, ref_up) <= 1e-4
+    z = np.load(os.path.join(GOLD, "refiner_student_64x96.npz"))
+    net = _refiner_student(False, int(z["seed"])).cuda()
+    with torch.no_grad():
+        pred = net(torch.from_numpy(z["x"]).cuda())
+        pred_up = net(torch.from_numpy(z["x"]).cuda(), out_hw=tuple(z["pred_up"].shape[2:]))
+    assert _rel(pred, torch.from_numpy(z["pred"])) <= 1e-4
+    assert _rel(pred_up, torch.from_numpy(z["pred_up"])) <= 1e-4
+
+
+def test_refiner_student_bf16_vs_oracle(cuda_device):
+    from oracle.student_ref import refiner_student_forward_ref
+    net = _refiner_student(True, 33)
+    sd = {k: v.float() for k, v in net.state_dict().items()}
+    x = torch.randn(2, 3, 128, 128, generator=torch.Generator().manual_seed(34))
+    ref = refiner_student_forward_ref(sd, x)
+    net = net.cuda()
+    with torch.no_grad():
+        pred = net(x.cuda())
+    assert _rel(pred, ref) <= 2e-2
