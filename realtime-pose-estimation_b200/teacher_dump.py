@@ -165,10 +165,23 @@ class TeacherDumper:
         self._slots = {}
         self._turn = 0
         self._copy_stream = torch.cuda.Stream()
+        self._inflight = None                      # (slot, paths) whose D2H copy is still running
+
+    def _finish_inflight(self):
+        if self._inflight is None:
+            return
+        slot, paths = self._inflight
+        self._inflight = None
+        slot.event.synchronize()                   # the copy has landed in the pinned buffers
+        p0, p1 = slot.y0.numpy(), slot.y1.numpy()
+        for i, path in enumerate(paths):
+            self.writer.submit(path, p0[i], p1[i], on_done=slot.release_one)
 
     @torch.no_grad()
     def dump_batch(self, x, img_paths):
-        """x (N,3,H,W) CUDA tensor of pre-processed images; one file per entry of ``img_paths``."""
+        """x (N,3,H,W) CUDA tensor of pre-processed images; one file per entry of ``img_paths``.
+        The forward and the D2H copy of this batch are only ENQUEUED here; the files of the previous
+        batch are handed to the writer while they run (``close`` flushes the last batch)."""
         if x.shape[0] != len(img_paths):
             raise ValueError("%d images but %d paths" % (x.shape[0], len(img_paths)))
         y0, y1 = self.model(x)
@@ -179,6 +192,8 @@ class TeacherDumper:
         slot = self._slots.get(key)
         if slot is None:
             slot = self._slots[key] = _PinnedSlot(y0, y1)
+        if self._inflight is not None and self._inflight[0] is slot:
+            self._finish_inflight()                       # same buffers (shape changed back): drain first
         slot.wait_free()                                  # its previous files are on disk
         done = torch.cuda.Event()
         done.record()
@@ -190,12 +205,11 @@ class TeacherDumper:
         y0.record_stream(self._copy_stream)
         y1.record_stream(self._copy_stream)
         slot.pending = len(img_paths)
-        slot.event.synchronize()
-        p0, p1 = slot.y0.numpy(), slot.y1.numpy()
-        for i, path in enumerate(img_paths):
-            self.writer.submit(path, p0[i], p1[i], on_done=slot.release_one)
+        self._finish_inflight()                           # previous batch: overlaps this batch's GPU work
+        self._inflight = (slot, list(img_paths))
 
     def close(self):
+        self._finish_inflight()
         self.writer.flush()
 
 
