@@ -209,8 +209,12 @@ int brtpe_stem_conv1(const void* img, int img_dtype_is_half, int N, int H, int W
 /* Stem im2col, the bf16 / tcgen05 form of conv1 (pose_higher_hrnet.py:363-365): NCHW
  * float32/half image -> NHWC bf16 (N, H/2, W/2, 32); channel k = (ky*3 + kx)*3 + ci is the
  * 3x3 / stride-2 / pad-1 window of output pixel (oy, ox), channels 27..31 are zero.  conv1
- * + BN + ReLU is then brtpe_conv_run with a 1x1 tap table and Cin = 32. */
-int brtpe_stem_im2col(const void* img, int img_dtype_is_half, int N, int H, int W, void* out,
+ * + BN + ReLU is then brtpe_conv_run with a 1x1 tap table and Cin = 32.
+ * img_mode: bit 0 = the image is half (else float32); bit 1 = flip pair: img holds N/2 images and
+ * image n >= N/2 of the batch is image n - N/2 mirrored in x (the flip-test batch cat(x, flip(x))
+ * of the upstream get_multi_stage_outputs caller, never materialised); bit 2 = a float32 image is
+ * rounded through fp16 first, like fp16util.py's tofp16 in front of the network. */
+int brtpe_stem_im2col(const void* img, int img_mode, int N, int H, int W, void* out,
                       void* stream);
 
 /* y_i = relu?( sum_k up_{2^shift_k}(term_k) ) of HighResolutionModule.forward
@@ -238,7 +242,7 @@ int brtpe_plan_add_fuse(brtpe_plan*, int dtype, int nterms, const void* const* t
                         int C, void* out, int out_ld, int relu);
 int brtpe_plan_add_nhwc_to_nchw(brtpe_plan*, int dtype, const void* src, int N, int H, int W,
                                 int C, int ld, int coff, void* dst, int dst_is_half);
-int brtpe_plan_add_stem_im2col(brtpe_plan*, const void* img, int img_is_half, int N, int H, int W,
+int brtpe_plan_add_stem_im2col(brtpe_plan*, const void* img, int img_mode, int N, int H, int W,
                                void* out);
 /* Scheduling annotation of the op added last: `lane` (0..7) is the capture stream the op is
  * issued on, deps[ndeps] are indices of EARLIER ops that must have completed before it (ops

@@ -195,14 +195,22 @@ stem_conv1_kernel(const TI* __restrict__ img, int N, int H, int W, const float* 
 // (oy, ox) and channels 27..31 are zero; conv1 then is a 1x1 tcgen05 conv with K = 32.
 // One thread per output pixel: 27 strided reads (L1 keeps the 2x overlap), one 64-byte write.
 // ------------------------------------------------------------------------------------------
+// mode bit 1 (flip pair): `img` holds N/2 images; image n >= N/2 of the batch is image n - N/2
+// mirrored in x -- the flip-test batch cat(x, flip(x)) without materialising it.  mode bit 2: a
+// float32 image is rounded through fp16 first, like the reference's network_to_half wrapper
+// (tofp16) does before the network sees it.
 template <typename TI>
 __global__ void __launch_bounds__(256)
-stem_im2col_kernel(const TI* __restrict__ img, int N, int H, int W, __nv_bfloat16* __restrict__ out) {
+stem_im2col_kernel(const TI* __restrict__ img, int N, int H, int W, __nv_bfloat16* __restrict__ out,
+                   int mode) {
   const int Ho = H >> 1, Wo = W >> 1;
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
   if (ox >= Wo) return;
   const int row = blockIdx.y;                 // n * Ho + oy
   const int n = row / Ho, oy = row - n * Ho;
+  const bool mirror = (mode & 2) && n >= (N >> 1);
+  const int ns = mirror ? n - (N >> 1) : n;
+  const bool via_half = (mode & 4) != 0;
   float v[32];
 #pragma unroll
   for (int k = 27; k < 32; ++k) v[k] = 0.0f;
@@ -213,9 +221,13 @@ stem_im2col_kernel(const TI* __restrict__ img, int N, int H, int W, __nv_bfloat1
     for (int kx = 0; kx < 3; ++kx) {
       const int ix = ox * 2 + kx - 1;
       const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+      const int sx = mirror ? W - 1 - ix : ix;
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci)
-        v[(ky * 3 + kx) * 3 + ci] = ok ? to_f32(img[(((size_t)n * 3 + ci) * H + iy) * W + ix]) : 0.0f;
+      for (int ci = 0; ci < 3; ++ci) {
+        float t = ok ? to_f32(img[(((size_t)ns * 3 + ci) * H + iy) * W + sx]) : 0.0f;
+        if (via_half) t = __half2float(__float2half_rn(t));
+        v[(ky * 3 + kx) * 3 + ci] = t;
+      }
     }
   }
   uint4* o = reinterpret_cast<uint4*>(out + ((size_t)row * Wo + ox) * 32);
@@ -442,14 +454,19 @@ int stem_conv1_launch(const void* img, int img_is_half, int N, int H, int W, con
   return BRTPE_OK;
 }
 
-int stem_im2col_launch(const void* img, int img_is_half, int N, int H, int W, void* out,
+int stem_im2col_launch(const void* img, int img_mode, int N, int H, int W, void* out,
                        cudaStream_t st) {
+  // img_mode: bit 0 = half input, bit 1 = flip pair, bit 2 = round float32 through fp16
+  const int img_is_half = img_mode & 1;
+  const int kmode = img_mode & 6;
   BRTPE_CHECK_ARG(img && out && N > 0 && H > 0 && W > 0, "stem_im2col: bad arguments");
   BRTPE_CHECK_ARG((H % 2) == 0 && (W % 2) == 0, "stem_im2col: H and W must be even");
   BRTPE_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "stem_im2col: out must be 16-byte aligned");
+  BRTPE_CHECK_ARG(!(kmode & 2) || (N % 2) == 0, "stem_im2col: flip-pair mode needs an even N");
   const int rows = N * (H / 2);
   dim3 grid(ceil_div(W / 2, 128), rows);
   if (rows > 65535) {
+    BRTPE_CHECK_ARG(!(kmode & 2), "stem_im2col: flip-pair mode needs N * H / 2 <= 65535");
     // blockIdx.y is limited to 65535: split the batch
     const int per = 65535 / (H / 2);
     BRTPE_CHECK_ARG(per >= 1, "stem_im2col: image too tall");
@@ -457,7 +474,7 @@ int stem_im2col_launch(const void* img, int img_is_half, int N, int H, int W, vo
     for (int n0 = 0; n0 < N; n0 += per) {
       const int nn = std::min(per, N - n0);
       int rc = stem_im2col_launch(reinterpret_cast<const char*>(img) + (size_t)n0 * 3 * H * W * isz,
-                                  img_is_half, nn, H, W,
+                                  img_mode, nn, H, W,
                                   reinterpret_cast<__nv_bfloat16*>(out) + (size_t)n0 * (H / 2) * (W / 2) * 32,
                                   st);
       if (rc) return rc;
@@ -466,10 +483,10 @@ int stem_im2col_launch(const void* img, int img_is_half, int N, int H, int W, vo
   }
   if (img_is_half)
     stem_im2col_kernel<__half><<<grid, 128, 0, st>>>(reinterpret_cast<const __half*>(img), N, H, W,
-                                                     reinterpret_cast<__nv_bfloat16*>(out));
+                                                     reinterpret_cast<__nv_bfloat16*>(out), kmode & 2);
   else
     stem_im2col_kernel<float><<<grid, 128, 0, st>>>(reinterpret_cast<const float*>(img), N, H, W,
-                                                    reinterpret_cast<__nv_bfloat16*>(out));
+                                                    reinterpret_cast<__nv_bfloat16*>(out), kmode);
   BRTPE_LAUNCH_CHECK();
   return BRTPE_OK;
 }

@@ -179,6 +179,7 @@ class _Recorder:
         self.tensors = []
         self.keepalive = []                       # packed weights / biases
         self.in_is_half = in_is_half
+        self.stem_mode = 0                        # im2col mode bits 1 / 2 (flip pair, via fp16)
         self.lane = 0                             # lane of the ops being recorded
         self.op_lane = []                         # per op: lane
         self.op_rw = []                           # per op: (reads, writes, phase group)
@@ -495,8 +496,8 @@ class _Recorder:
                 elif kind == "im2col":
                     _, cols = op
                     L.check(lib.brtpe_plan_add_stem_im2col(
-                        plan, L.ptr(in_buf), int(self.in_is_half), self.n, self.h, self.w,
-                        L.ptr(cols.buf[1])), "brtpe_plan_add_stem_im2col")
+                        plan, L.ptr(in_buf), int(self.in_is_half) | int(self.stem_mode), self.n,
+                        self.h, self.w, L.ptr(cols.buf[1])), "brtpe_plan_add_stem_im2col")
                 k = lib.brtpe_plan_num_ops(plan) - 1
                 deps = self.deps[k]
                 arr = (C.c_int32 * max(len(deps), 1))(*deps)
@@ -570,20 +571,30 @@ class _PlanRunner:
     def _mode(self):
         return "fp32" if self._ref_param().dtype == torch.float32 else "bf16"
 
-    def _get_plan(self, n, h, w, mode, device, in_dtype):
-        key = (n, h, w, mode, str(device), in_dtype, self.conv_engine, self.parallel_branches)
+    def _get_plan(self, n, h, w, mode, device, in_dtype, stem_mode=0):
+        key = (n, h, w, mode, str(device), in_dtype, self.conv_engine, self.parallel_branches,
+               stem_mode)
         plan = self._plans.get(key)
         if plan is None:
             in_is_half = in_dtype == torch.float16
-            in_buf = torch.empty((n, 3, h, w), dtype=in_dtype, device=device)
+            # flip-pair plans (stem_mode bit 1) read n / 2 images and run n forwards
+            in_buf = torch.empty((n // 2 if stem_mode & 2 else n, 3, h, w), dtype=in_dtype,
+                                 device=device)
             with torch.cuda.device(device):
-                R, outs = self._record(n, h, w, mode, device, in_is_half, in_is_half)
+                if stem_mode:
+                    R, outs = self._record(n, h, w, mode, device, in_is_half, in_is_half,
+                                           stem_mode=stem_mode)
+                else:
+                    R, outs = self._record(n, h, w, mode, device, in_is_half, in_is_half)
                 handle = R.build(in_buf)
             plan = _CompiledPlan(handle, in_buf, outs, R)
             self._plans[key] = plan
         return plan
 
-    def _run_plans(self, x, size_multiple):
+    def _run_plans(self, x, size_multiple, flip_pair=False, via_half=False):
+        """``flip_pair``: run the network on cat(x, flip(x, [3])) without materialising the batch
+        (rows [0:N] of every output belong to x, rows [N:2N] to the mirrored images);
+        ``via_half``: a float32 input is rounded through fp16 first (the tofp16 wrapper)."""
         lib = L.load()
         if not isinstance(x, torch.Tensor) or not x.is_cuda:
             raise L.BrtpeError("%s.forward needs a CUDA tensor (no CPU fallback); got %r"
@@ -608,9 +619,28 @@ class _PlanRunner:
             if sig != self._sig:
                 self._plans = {}
                 self._sig = sig
-        nb = min(self.chunk_size, n)
-        odt = torch.float16 if x.dtype == torch.float16 else torch.float32
         results = None
+        if flip_pair:
+            stem_mode = 2 | (4 if via_half and x.dtype == torch.float32 else 0)
+            nb = max(1, min(self.chunk_size, 2 * n) // 2)          # originals per plan replay
+            with torch.cuda.device(dev):
+                st = L.stream_ptr(dev)
+                for s0 in range(0, n, nb):
+                    cn = min(nb, n - s0)
+                    plan = self._get_plan(2 * cn, h, w, mode, dev, x.dtype, stem_mode)
+                    plan.in_buf.copy_(x[s0:s0 + cn])
+                    if self.use_cuda_graph:
+                        L.check(lib.brtpe_plan_graph_launch(plan.handle, st), "brtpe_plan_graph_launch")
+                    else:
+                        L.check(lib.brtpe_plan_run(plan.handle, st), "brtpe_plan_run")
+                    if results is None:
+                        results = [torch.empty((2 * n,) + tuple(o.shape[1:]), dtype=o.dtype, device=dev)
+                                   for o in plan.outs]
+                    for r, o in zip(results, plan.outs):
+                        r[s0:s0 + cn].copy_(o[:cn])
+                        r[n + s0:n + s0 + cn].copy_(o[cn:])
+            return results
+        nb = min(self.chunk_size, n)
         with torch.cuda.device(dev):
             st = L.stream_ptr(dev)
             for s0 in range(0, n, nb):
@@ -792,8 +822,9 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
         self.invalidate_plans()
 
     # ---------------------------------------------------------------- plan
-    def _record(self, n, h, w, mode, device, in_is_half, out_half):
+    def _record(self, n, h, w, mode, device, in_is_half, out_half, stem_mode=0):
         R = _Recorder(self, n, h, w, mode, self.conv_engine, device, in_is_half)
+        R.stem_mode = stem_mode
         par = self.parallel_branches
         if mode == "bf16" and self.conv_engine != L.ENGINE_FFMA:
             x = R.stem_tc(self.conv1, self.bn1)
@@ -908,3 +939,17 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
     def forward(self, x):
         """pose_higher_hrnet.py:637-686: (N,3,H,W) -> [(N,34,H/4,W/4), (N,17,H/2,W/2)]."""
         return self._run_plans(x, 32)
+
+    def supports_flip_pair(self, x):
+        """The fused flip-test batch needs the tensor-core stem (im2col) and N * H / 2 <= 65535 rows
+        per plan replay."""
+        return (self._mode() == "bf16" and self.conv_engine != L.ENGINE_FFMA and x.dim() == 4 and
+                min(self.chunk_size, 2 * x.shape[0]) * (x.shape[2] // 2) <= 65535)
+
+    def forward_flip_pair(self, x, via_half=False):
+        """``forward(torch.cat((x, torch.flip(x, [3])), 0))`` of the flip test (upstream
+        get_multi_stage_outputs callers, legacy/valid_ae_avg.py:176-185) without building that batch:
+        the stem's im2col reads the mirrored half straight from ``x``.  Not part of the reference
+        API (``TeacherPipeline`` uses it); bit-identical to the materialised batch.  ``via_half``:
+        ``x`` is the float32 input of a ``network_to_half`` wrapper (rounded through fp16 first)."""
+        return self._run_plans(x, 32, flip_pair=True, via_half=via_half)

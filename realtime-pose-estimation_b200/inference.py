@@ -118,6 +118,19 @@ class TeacherPipeline:
         self.mode = mode
         self.num_joints = parser.params.num_joints
 
+    def _forward_flip(self, x):
+        """network outputs of cat(x, flip(x)): through the fused flip-pair plan when the model is
+        this package's network (optionally inside ``network_to_half``'s Sequential), else by
+        materialising the batch."""
+        net, via_half = self.model, False
+        if isinstance(net, torch.nn.Sequential) and len(net) == 3 and hasattr(net[1], "forward_flip_pair"):
+            net, via_half = net[1], True                  # tofp16 -> net -> tofp32
+        if hasattr(net, "forward_flip_pair") and x.dtype in (torch.float32, torch.float16) and \
+                net.supports_flip_pair(x) and not os.environ.get("BRTPE_NO_FLIP_PAIR"):
+            y0, y1 = net.forward_flip_pair(x, via_half=via_half and x.dtype == torch.float32)
+            return y0.float(), y1.float()
+        return self.model(torch.cat((x, torch.flip(x, [3])), 0))
+
     @torch.no_grad()
     def forward_aggregate(self, x, after_forward=None):
         """x (N,3,H,W) CUDA -> det (N,J,Hb,Wb), tag (N,A,Hb,Wb,T).  ``after_forward`` (optional
@@ -130,8 +143,7 @@ class TeacherPipeline:
                 after_forward()
             return aggregate_intree(y0, y1, (hb, wb), self.num_joints)
         if self.flip_test:
-            both = torch.cat((x, torch.flip(x, [3])), 0)
-            y0, y1 = self.model(both)
+            y0, y1 = self._forward_flip(x)
             if after_forward is not None:
                 after_forward()
             det, tag = aggregate_scale(y0[:n], y1[:n], y0[n:], y1[n:], (hb, wb), self.num_joints)
@@ -157,7 +169,7 @@ class TeacherPipeline:
         for k, (scale, x) in enumerate(inputs_by_scale):
             n = x.shape[0]
             if self.flip_test:
-                y0, y1 = self.model(torch.cat((x, torch.flip(x, [3])), 0))
+                y0, y1 = self._forward_flip(x)
                 outs, outs_f = (y0[:n], y1[:n]), (y0[n:], y1[n:])
             else:
                 outs, outs_f = tuple(self.model(x)), (None, None)

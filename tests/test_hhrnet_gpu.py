@@ -84,3 +84,30 @@ def test_requires_cuda_and_eval(cuda_device):
         net.train().cuda()(torch.zeros(1, 3, 64, 64).cuda())
     with pytest.raises(ValueError):
         net.eval().cuda()(torch.zeros(1, 3, 70, 64).cuda())
+
+
+@pytest.mark.parametrize("chunk", [8, 3])
+def test_forward_flip_pair_equals_materialised_batch(cuda_device, chunk):
+    """the fused flip-test batch (the stem's im2col reads the mirrored half straight from x) gives the
+    outputs of forward(cat(x, flip(x))): identical for a float32 model input, and for the
+    network_to_half wrapper up to the fp16 output rounding the wrapper's half outputs carry."""
+    import rtpe_b200
+    from oracle.weights import fill_params_deterministic
+    net = rtpe_b200.PoseHigherResolutionNet()
+    fill_params_deterministic(net, 9)
+    model = rtpe_b200.network_to_half(net).cuda().eval()
+    model[1].chunk_size = chunk
+    x = torch.randn(5, 3, 64, 96, generator=torch.Generator().manual_seed(3)).cuda()
+    both = torch.cat((x, torch.flip(x, [3])), 0)
+    with torch.no_grad():
+        # (a) the half-precision network fed float32 directly: bit-identical
+        ya = model[1](both)
+        yb = model[1].forward_flip_pair(x)
+        for a, b in zip(ya, yb):
+            assert a.shape == b.shape and torch.equal(a, b)
+        # (b) the wrapper (input rounded through fp16, outputs through fp16 in the wrapper only)
+        yc = model(both)
+        yd = model[1].forward_flip_pair(x, via_half=True)
+        for c, d in zip(yc, yd):
+            assert c.shape == d.shape
+            assert (c - d.float()).abs().max().item() <= 1e-3 * c.abs().max().item()
