@@ -198,9 +198,9 @@ class TeacherPipeline:
         graph down by more than the copy takes (measured: profiles/r01e_halo_pair.md).
         ``early_images`` images of the next batch are released already when the network of batch i
         STARTS: aggregation + decode (2.3 ms) have become shorter than a 157 MB copy (3 ms), and a
-        partial copy under the graph costs less than exposing the rest (measured r01n, e2e / device
-        throughput: 0 early 0.977, half 0.99-1.00, all 0.988).  Default: half of the batch
-        (environment variable BRTPE_EARLY_IMAGES overrides).
+        partial copy under the graph costs less than exposing the rest (measured r01n/r01o, e2e /
+        device throughput with the fused flip batch: 16 of 32 early 0.985, 22 -> 0.992, 28 -> 0.999).
+        Default: 7/8 of the batch (environment variable BRTPE_EARLY_IMAGES overrides).
         Yields the device results ``(ans, count, scores)`` of every batch in order (see
         ``run_device``); the caller copies what it needs back."""
         L.load()
@@ -249,7 +249,7 @@ class TeacherPipeline:
                 xn = None
             if xn is not None:
                 kn = claim(xn)
-                ne = xn.shape[0] // 2 if early_images is None else int(early_images)
+                ne = (xn.shape[0] * 7) // 8 if early_images is None else int(early_images)
                 ne = min(max(ne, 0), xn.shape[0])
                 start = torch.cuda.Event()
                 start.record(main)             # after the previous step's last reader of bufs[kn]
