@@ -591,10 +591,13 @@ class _PlanRunner:
             self._plans[key] = plan
         return plan
 
-    def _run_plans(self, x, size_multiple, flip_pair=False, via_half=False):
+    def _run_plans(self, x, size_multiple, flip_pair=False, via_half=False, borrow=False):
         """``flip_pair``: run the network on cat(x, flip(x, [3])) without materialising the batch
         (rows [0:N] of every output belong to x, rows [N:2N] to the mirrored images);
-        ``via_half``: a float32 input is rounded through fp16 first (the tofp16 wrapper)."""
+        ``via_half``: a float32 input is rounded through fp16 first (the tofp16 wrapper);
+        ``borrow``: when one plan replay covers the whole batch, return the plan's own output
+        buffers instead of copies -- valid only until the next forward of this module (callers that
+        consume the outputs in stream order before that, like ``TeacherPipeline``)."""
         lib = L.load()
         if not isinstance(x, torch.Tensor) or not x.is_cuda:
             raise L.BrtpeError("%s.forward needs a CUDA tensor (no CPU fallback); got %r"
@@ -633,6 +636,8 @@ class _PlanRunner:
                         L.check(lib.brtpe_plan_graph_launch(plan.handle, st), "brtpe_plan_graph_launch")
                     else:
                         L.check(lib.brtpe_plan_run(plan.handle, st), "brtpe_plan_run")
+                    if borrow and cn == n:
+                        return list(plan.outs)
                     if results is None:
                         results = [torch.empty((2 * n,) + tuple(o.shape[1:]), dtype=o.dtype, device=dev)
                                    for o in plan.outs]
@@ -946,10 +951,11 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
         return (self._mode() == "bf16" and self.conv_engine != L.ENGINE_FFMA and x.dim() == 4 and
                 min(self.chunk_size, 2 * x.shape[0]) * (x.shape[2] // 2) <= 65535)
 
-    def forward_flip_pair(self, x, via_half=False):
+    def forward_flip_pair(self, x, via_half=False, borrow=False):
         """``forward(torch.cat((x, torch.flip(x, [3])), 0))`` of the flip test (upstream
         get_multi_stage_outputs callers, legacy/valid_ae_avg.py:176-185) without building that batch:
         the stem's im2col reads the mirrored half straight from ``x``.  Not part of the reference
         API (``TeacherPipeline`` uses it); bit-identical to the materialised batch.  ``via_half``:
-        ``x`` is the float32 input of a ``network_to_half`` wrapper (rounded through fp16 first)."""
-        return self._run_plans(x, 32, flip_pair=True, via_half=via_half)
+        ``x`` is the float32 input of a ``network_to_half`` wrapper (rounded through fp16 first);
+        ``borrow``: see ``_run_plans`` (outputs valid until the next forward of this module)."""
+        return self._run_plans(x, 32, flip_pair=True, via_half=via_half, borrow=borrow)

@@ -127,7 +127,9 @@ class TeacherPipeline:
             net, via_half = net[1], True                  # tofp16 -> net -> tofp32
         if hasattr(net, "forward_flip_pair") and x.dtype in (torch.float32, torch.float16) and \
                 net.supports_flip_pair(x) and not os.environ.get("BRTPE_NO_FLIP_PAIR"):
-            y0, y1 = net.forward_flip_pair(x, via_half=via_half and x.dtype == torch.float32)
+            # borrowed plan outputs: aggregation consumes them in stream order before the next forward
+            y0, y1 = net.forward_flip_pair(x, via_half=via_half and x.dtype == torch.float32,
+                                           borrow=True)
             return y0.float(), y1.float()
         return self.model(torch.cat((x, torch.flip(x, [3])), 0))
 
