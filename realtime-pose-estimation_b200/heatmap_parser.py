@@ -139,8 +139,10 @@ class HeatmapParser(object):
                 "val_k": val_k.cpu().numpy()}
 
     # ------------------------------------------------------------------ match
-    def match_device(self, val_k, ind_k, tag_k, width, pmax=None):
-        """Grouping on the device -> ans (N,Pmax,J,3+T) f32, count (N) i32, Pmax used."""
+    def match_device(self, val_k, ind_k, tag_k, width, pmax=None, defer_overflow=False):
+        """Grouping on the device -> ans (N,Pmax,J,3+T) f32, count (N) i32, Pmax used.
+        ``defer_overflow``: do not wait for the capacity flag; returns (ans, count, pmax, flag) with
+        flag = the device int32 the caller must read later (None when pmax is already the bound)."""
         lib = L.load()
         dev = val_k.device
         n, j, k = val_k.shape
@@ -164,6 +166,8 @@ class HeatmapParser(object):
                                            t, C.byref(prm), L.ptr(ans), L.ptr(count),
                                            L.ptr(overflow), pmax, L.ptr(ws), ws.numel(),
                                            L.stream_ptr(dev)), "brtpe_group_ae")
+                if defer_overflow:
+                    return ans, count, pmax, (overflow if pmax < pmax_full else None)
                 if pmax >= pmax_full or int(overflow.item()) == 0:
                     return ans, count, pmax
                 pmax = pmax_full
@@ -272,16 +276,23 @@ class HeatmapParser(object):
         dev = det.device
         n, j, h, w = det.shape
         val_k, ind_k, _, tag_k = self.top_k_device(det, tag)
-        ans, count, pmax = self.match_device(val_k, ind_k, tag_k, w)
-        if adjust:
-            self.adjust_device(ans, count, det)
-        scores = torch.empty((n, pmax), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            L.check(lib.brtpe_scores(L.ptr(ans), L.ptr(count), L.ptr(scores), n, j,
-                                     ans.shape[3] - 3, pmax, L.stream_ptr(dev)), "brtpe_scores")
-        if refine:
-            self.refine_device(det, tag, ans, count)
-        return ans, count, scores
+        # optimistic: everything is enqueued for the default person capacity and the capacity
+        # flag is read once at the end (one host sync per decode, after the last launch, instead
+        # of one in the middle that left the GPU waiting for the remaining launches)
+        ans, count, pmax, flag = self.match_device(val_k, ind_k, tag_k, w, defer_overflow=True)
+        while True:
+            if adjust:
+                self.adjust_device(ans, count, det)
+            scores = torch.empty((n, pmax), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                L.check(lib.brtpe_scores(L.ptr(ans), L.ptr(count), L.ptr(scores), n, j,
+                                         ans.shape[3] - 3, pmax, L.stream_ptr(dev)), "brtpe_scores")
+            if refine:
+                self.refine_device(det, tag, ans, count)
+            if flag is None or int(flag.item()) == 0:
+                return ans, count, scores
+            ans, count, pmax = self.match_device(val_k, ind_k, tag_k, w, pmax=self._pmax_full())
+            flag = None
 
     def parse_batch(self, det, tag, adjust=True, refine=True):
         """Reference ``parse`` applied to every image of the batch.

@@ -234,3 +234,29 @@ def test_refine_more_missing_persons_than_one_pass(cuda_device, t):
     assert want[0][0].shape[0] >= 40
     assert (np.asarray(want[0][0])[:, :3, 2] > 0).any()      # refine filled missing joints
     assert_people_equal(got, want)
+
+
+def test_person_capacity_overflow_retry(cuda_device):
+    """more persons than the optimistic person capacity: the decode is enqueued for the small
+    capacity, the flag read at the end triggers ONE retry at the J*K bound, same result."""
+    h = w = 160
+    det = torch.rand(2, 17, h, w, generator=torch.Generator().manual_seed(1)) * 0.01
+    tag = torch.zeros(2, 17, h, w, 1)
+    pid = 0
+    for y in range(10, 150, 20):
+        for x in range(10, 150, 20):
+            if pid >= 24:
+                break
+            for j in range(17):
+                yy, xx = y + (j % 4), x + (j // 4)
+                det[0, j, yy, xx] = 0.5 + 0.01 * ((pid + 7 * j) % 40) + 0.0001 * j
+                tag[0, j, yy - 2:yy + 3, xx - 2:xx + 3, 0] = 3.0 * pid
+            pid += 1
+    det[1], tag[1] = det[0].flip(-1), tag[0].flip(-2)
+    hp, p = make_parser()
+    want = G.parse_batch_ref(det.numpy().copy(), tag.numpy().copy(), p, True, True)
+    assert want[0][0].shape[0] >= 24
+    small = rtpe_b200.HeatmapParser(**PARSER_KW, person_capacity=8)
+    got = small.parse_batch(det.cuda(), tag.cuda(), True, True)
+    assert_people_equal(got, want)
+    assert_people_equal(hp.parse_batch(det.cuda(), tag.cuda(), True, True), want)
