@@ -772,7 +772,9 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
   // TMEM columns (BN > 128): the epilogue of item i then overlaps the MMAs of item i+1 again and
   // the work items are finer (better balance over the SMs); needs the fast epilogue
   const int cp0 = (d->Cout_store + 15) / 16 * 16;
-  p.tpc = (cp0 > 128 && cp0 <= HL_MAX_BN && epi_fast_ok(d) && (cp0 / 16) % 2 == 0) ? 1 : 2;
+  // (whole 64-channel rounds per epilogue group only: 192 and 256 channels, the widths this mode
+  // was built and verified for; 160 / 224 channels gave wrong results / no valid tiling)
+  p.tpc = (cp0 > 128 && cp0 <= HL_MAX_BN && epi_fast_ok(d) && cp0 % 64 == 0) ? 1 : 2;
   if (getenv("BRTPE_HALO_TPC")) {
     const int v = atoi(getenv("BRTPE_HALO_TPC"));
     if (v == 2 || (v == 1 && epi_fast_ok(d) && (cp0 / 16) % 2 == 0)) p.tpc = v;

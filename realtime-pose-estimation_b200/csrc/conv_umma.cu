@@ -287,9 +287,12 @@ bool umma_conv_supported(const brtpe_conv_desc* d, const char** why) {
   if (d->res_ld % 8 || d->res_coff % 8) return fail("res_ld / res_coff must be multiples of 8");
   if (d->in_stride != 1 && d->in_stride != 2) return fail("in_stride must be 1 or 2");
   if (d->in_stride == 2 && ((d->Hin | d->Win) & 1)) return fail("stride 2 needs even Hin/Win");
+  // stride 1: a tap is just a shifted TMA box (zero fill outside the map), so dilated 3x3
+  // convolutions run here too; stride 2 maps taps onto pixel parities and needs [-1, 1]
+  const int tmax = d->in_stride == 1 ? 64 : 1;
   for (int t = 0; t < d->ntaps; ++t)
-    if (d->tap_dy[t] < -1 || d->tap_dy[t] > 1 || d->tap_dx[t] < -1 || d->tap_dx[t] > 1)
-      return fail("tap offsets must be in [-1, 1]");
+    if (d->tap_dy[t] < -tmax || d->tap_dy[t] > tmax || d->tap_dx[t] < -tmax || d->tap_dx[t] > tmax)
+      return fail("tap offsets must be in [-1, 1] (stride 2) / [-64, 64] (stride 1)");
   int nt, bn;
   umma_n_tiling(d->Cout_store, &nt, &bn);
   if (nt * bn > UM_MAX_COUT_PAD) return fail("Cout too large");

@@ -244,8 +244,10 @@ class _Recorder:
 
     # -- ops
     def conv(self, x, conv, bn, relu, residual=None, out=None, out_coff=0, in_coff=0,
-             cin_store=None, cout_store=None, pad_cout=False):
-        """conv (+BN) (+residual) (+ReLU) over virtual tensor x -> virtual tensor."""
+             cin_store=None, cout_store=None, pad_cout=False, cin_index=None):
+        """conv (+BN) (+residual) (+ReLU) over virtual tensor x -> virtual tensor.
+        ``cin_index``: for every stored input channel the module's input channel it carries, or -1
+        for a pad channel (zero weights) -- inputs whose real channels sit in padded slots."""
         k = conv.kernel_size[0]
         s = conv.stride[0]
         dil = conv.dilation[0]                       # dilated 3x3 = the same taps, spread out
@@ -259,6 +261,10 @@ class _Recorder:
         w, b = self._fold(conv, bn)
         ktaps = _TAPS3 if k == 3 else [(0, 0)]
         wt = torch.stack([w[:, :, dy + (k // 2), dx + (k // 2)] for dy, dx in ktaps], 0)
+        if cin_index is not None:
+            idx = torch.as_tensor(list(cin_index), dtype=torch.long, device=wt.device)
+            wt = wt[:, :, idx.clamp(min=0)] * (idx >= 0).to(wt.dtype).view(1, 1, -1)
+            cin = cin_store = len(cin_index)
         if pad_cout and cout_store % 16 == 0 and cout < cout_store and self.mode == "bf16":
             # heads with 17 / 34 real channels: zero weights + zero bias for the pad channels, so
             # that the layer is a whole number of 16-channel chunks (vectorised epilogue; the pad

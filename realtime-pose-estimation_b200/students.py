@@ -196,12 +196,17 @@ class AttentionStudent(_PlanRunner, nn.Module):
         R.aux(AUX_SE_PARTIAL, [x], [], x, None, None, partial, [R.dt, x.n, hw, c, x.ld, chunks])
         R.aux(AUX_SE_GATE, [], [], partial, packed, None, gate, [R.dt, x.n, c, hid, chunks, hw])
         # hybrid dilated convolutions write channel slices of one buffer (the torch.cat)
+        # (every branch gets a 16-channel slot -- zero pad channels, zero weights for them in
+        # hdc_top -- so that the slices are chunk aligned and the branches, dilated ones included,
+        # run on the tcgen05 per-tap engine instead of the CUDA-core fallback)
         hc = cam.hdcs[0][0].out_channels
         nd = len(cam.hdcs)
-        cat = R.new(x.n, x.h, x.w, (hc * nd + 15) // 16 * 16)
+        slot = (hc + 15) // 16 * 16
+        cat = R.new(x.n, x.h, x.w, slot * nd)
         for i, hdc in enumerate(cam.hdcs):
-            R.conv(x, hdc[0], hdc[1], True, out=cat, out_coff=hc * i)
-        top = R.conv(cat, cam.hdc_top[0], cam.hdc_top[1], True)
+            R.conv(x, hdc[0], hdc[1], True, out=cat, out_coff=slot * i, cout_store=slot, pad_cout=True)
+        index = [(i * hc + j if j < hc else -1) for i in range(nd) for j in range(slot)]
+        top = R.conv(cat, cam.hdc_top[0], cam.hdc_top[1], True, cin_index=index)
         out = R.new(x.n, x.h, x.w, (c + 15) // 16 * 16)
         R.aux(AUX_CAM_MIX, [res, top], [out], res, top, gate, out,
               [R.dt, x.n, hw, c, res.ld, top.ld, out.ld])
@@ -227,8 +232,12 @@ class AttentionStudent(_PlanRunner, nn.Module):
             t = R.conv(x, blk.conv1, blk.bn1, True)
             t = R.conv(t, blk.conv2, blk.bn2, True)
             x = R.conv(t, blk.conv3, blk.bn3, True, residual=res)
-        x = R.conv(x, self.mid_stem[0], self.mid_stem[1], True)
-        s = R.conv(x, self.mid_stem[3], self.mid_stem[4], True)
+        # (mid-stem width 152 is stored as 160 channels: zero pad channels / zero weights keep the
+        # second conv on the tcgen05 halo engine)
+        mid = self.mid_stem[0].out_channels
+        mid16 = (mid + 15) // 16 * 16
+        x = R.conv(x, self.mid_stem[0], self.mid_stem[1], True, cout_store=mid16, pad_cout=True)
+        s = R.conv(x, self.mid_stem[3], self.mid_stem[4], True, cin_store=mid16)
         c = self.inplanes
 
         # attention pyramid (students.py:741-753): att = hi + 2 * nearest_x4(lo)

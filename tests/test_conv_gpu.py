@@ -60,6 +60,15 @@ HALO_SHAPES = [
     (2, 24, 40, 64, 64, 3, 1, True, False),
     (1, 17 * 2, 22, 48, 48, 3, 1, True, True),
     (5, 16, 8, 96, 96, 3, 1, True, True),
+    # widths outside the teacher's {48, 64, 96, 192, 384}: the students' 16-channel dilation
+    # branches, the 152 -> 160-channel mid stem, and odd multiples of 16
+    (2, 32, 32, 48, 16, 3, 1, True, False),
+    (2, 32, 32, 256, 160, 3, 1, True, False),
+    (2, 32, 32, 160, 48, 3, 1, True, False),
+    (1, 24, 24, 64, 224, 3, 1, True, True),
+    (1, 24, 24, 64, 256, 3, 1, True, True),
+    (1, 24, 24, 80, 144, 3, 1, False, False),
+    (2, 16, 16, 48, 1, 3, 1, False, False),
 ]
 
 
