@@ -278,6 +278,23 @@ int brtpe_plan_profile(brtpe_plan*, void* stream, float* ms_out, int32_t* kinds_
  *                                              iparams = {dtype, N, HW, C, ld0, ld1, ld_out}
  *  5 attention injection (students.py:752-753): a = sigmoid(in0[...,0] / 20); out = in1 + a;
  *    in2 = float att_out (N,H,W) written with a; iparams = {dtype, N, HW, C, ld_att, ld_in1, ld_out}
+ *  6 NHWC bilinear resize (MultistageStudent's out_hw, students.py:481-498): in0 (N,H,W,in_ld) ->
+ *    channels [coff, coff + C) of out (N,Ho,Wo,out_ld);
+ *                                  iparams = {dtype, N, H, W, C, in_ld, out_ld, Ho, Wo, align_corners, coff}
+ *  7 NCHW image -> NHWC slice (AttentionStudentSteps' alt image, students.py:980-988): in0 = float
+ *    (or half) image (N,C,H,W); s2d = 0: bilinear (align_corners=False) resize to (Ho,Wo) into channels
+ *    [coff, coff + C), zeros in [coff + C, coff + Cz); s2d = 1: space-to-depth by 2, channel
+ *    (ry*2+rx)*C + c of pixel (y,x) = img[c][2y+ry][2x+rx], zeros in [4C, Cz);
+ *                                  iparams = {dtype, N, H, W, C, img_is_half, out_ld, Ho, Wo, coff, Cz, s2d}
+ *  8 NHWC space-to-depth by 2: in0 (N,H,W,in_ld) -> out (N,H/2,W/2,out_ld), channel (ry*2+rx)*C + c;
+ *    with it a 5x5 / stride-2 conv (students.py:835-846) is a 3x3 / stride-1 conv over 4C channels;
+ *                                  iparams = {dtype, N, H, W, C, in_ld, out_ld}
+ *  9 attention product (students.py:1001-1018): a = sigmoid(in0[...,0] / div); out = in1 * a; in2 =
+ *    float att_out (N,H,W) written with a;
+ *                                  iparams = {dtype, N, HW, C, ld_att, ld_in1, ld_out, float bits of div}
+ * Kinds 3 and 4 take optional trailing parameters: 3 {..., Cin} = number of pooled (stored) channels
+ * when it differs from the gate's C; 4 {..., Cz} = zero-fill channels [C, Cz) of out.
+ * nparams <= 12.
  */
 int brtpe_aux_run(int kind, const void* in0, const void* in1, const void* in2, void* out,
                   const int32_t* iparams, int nparams, void* stream);

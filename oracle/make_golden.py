@@ -120,7 +120,61 @@ def refiner_student_fixture(ref_students, name, h, w, seed):
     print(name, tuple(pred.shape), tuple(pred_up.shape), float(pred.abs().max()))
 
 
+def build_reference_multistage(ref_students, **kw):
+    """The reference's MultistageStudent.__init__ first runs RefinerStudent.__init__ with ITS default
+    device "cuda" (students.py:405 -> :305-335), so the class cannot be built on a CPU-only host as
+    it stands: the harness swaps that one default for "cpu" while constructing (no file is touched)."""
+    init = ref_students.RefinerStudent.__init__
+    keep = init.__defaults__
+    init.__defaults__ = tuple("cpu" if d == "cuda" else d for d in keep)
+    try:
+        return ref_students.MultistageStudent(None, "cpu", half_precision=False, **kw).eval()
+    finally:
+        init.__defaults__ = keep
+
+
+def multistage_student_fixture(ref_students, name, h, w, seed):
+    """MultistageStudent (rtpe/students.py:389-499), default hyper-parameters, fp32."""
+    torch.manual_seed(0)
+    net = build_reference_multistage(ref_students)
+    fill_params_deterministic(net, seed)
+    x = torch.randn(2, 3, h, w, generator=torch.Generator().manual_seed(seed + 1))
+    with torch.no_grad():
+        outs = net(x)
+        outs_up = net(x, out_hw=(21, 35))
+    np.savez_compressed(os.path.join(OUT, name), x=x.numpy(), outs=np.stack([o.numpy() for o in outs]),
+                        outs_up=np.stack([o.numpy() for o in outs_up]),
+                        seed=np.int64(seed), entries=np.int64(len(net.state_dict())))
+    print(name, len(outs), tuple(outs[0].shape), tuple(outs_up[0].shape), float(outs[-1].abs().max()))
+
+
+def attention_steps_fixture(ref_students, name, h, w, seed, inplanes=48):
+    """AttentionStudentSteps (rtpe/students.py:786-1073), fp32, with and without att_divisor."""
+    import warnings
+    torch.manual_seed(0)
+    net = ref_students.AttentionStudentSteps(None, "cpu", inplanes, 17, 1, False).eval()
+    fill_params_deterministic(net, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(2, 3, h, w, generator=g)
+    alt = torch.randn(2, 3, h, w, generator=g)
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        att, det = net(x, alt=alt)
+        att20, det20 = net(x, alt=alt, att_divisor=20)
+    np.savez_compressed(os.path.join(OUT, name), x=x.numpy(), alt=alt.numpy(), att=att.numpy(),
+                        det=det.numpy(), att20=att20.numpy(), det20=det20.numpy(),
+                        inplanes=np.int64(inplanes), seed=np.int64(seed),
+                        entries=np.int64(len(net.state_dict())))
+    print(name, tuple(att.shape), tuple(det.shape), float(det.abs().max()), float(att.min()),
+          float(att.max()))
+
+
 def main():
+    if "--new-students" in sys.argv:
+        multistage_student_fixture(load_reference_students(), "multistage_student_64x96.npz", 64, 96,
+                                   seed=12)
+        attention_steps_fixture(load_reference_students(), "attention_steps_64x96.npz", 64, 96, seed=13)
+        return
     os.makedirs(OUT, exist_ok=True)
     ref_group, ref_model = load_reference()
     decode_fixture(ref_group, "decode_a.npz", 2, 56, 72, 1, 6, seed=21)
@@ -132,6 +186,8 @@ def main():
     student_fixture(load_reference_students(), "student_64x96.npz", 64, 96, seed=9)
     cam_student_fixture(load_reference_students(), "cam_student_64x96.npz", 64, 96, seed=10)
     refiner_student_fixture(load_reference_students(), "refiner_student_64x96.npz", 64, 96, seed=11)
+    multistage_student_fixture(load_reference_students(), "multistage_student_64x96.npz", 64, 96, seed=12)
+    attention_steps_fixture(load_reference_students(), "attention_steps_64x96.npz", 64, 96, seed=13)
 
 
 if __name__ == "__main__":

@@ -149,3 +149,59 @@ def refiner_student_forward_ref(state_dict, x, out_hw=None, dtype=torch.float32)
     if out_hw is not None:
         y = F.interpolate(y, out_hw, mode="bilinear", align_corners=True)
     return y
+
+
+@torch.no_grad()
+def multistage_student_forward_ref(state_dict, x, out_hw=None, dtype=torch.float32):
+    """``MultistageStudent.forward`` (students.py:473-499) -> list of stage outputs.  With
+    ``out_hw`` the stem output is resized first, the stages run at that size and the per-stage
+    resizes (same size, align_corners=True) are kept as the reference has them."""
+    sd = state_dict
+    s = stem_ref(sd, x.to(dtype))
+    if out_hw is not None:
+        s = F.interpolate(s, out_hw, mode="bilinear", align_corners=True)
+    n = 0
+    while ("stages.%d.convs.0.weight" % n) in sd:
+        n += 1
+    y = skip_conv_ref(sd, s, "stages.0")
+    if out_hw is not None:
+        y = F.interpolate(y, out_hw, mode="bilinear", align_corners=True)
+    outs = [y]
+    for i in range(1, n):
+        y = skip_conv_ref(sd, torch.cat([s, outs[-1]], dim=1), "stages.%d" % i)
+        if out_hw is not None:
+            y = F.interpolate(y, out_hw, mode="bilinear", align_corners=True)
+        outs.append(y)
+    return outs
+
+
+@torch.no_grad()
+def attention_student_steps_forward_ref(state_dict, x, alt, att_divisor=None, dtype=torch.float32):
+    """``AttentionStudentSteps.forward`` (students.py:966-1052) -> (att, det).  Quirks kept: ``mid``
+    and ``lo`` are the same up-sampled ``lo`` map (:993-996), the attention multiplies the
+    concatenated (stem, image) tensor (:1018), ``out_hw`` is unused."""
+    sd = state_dict
+    x, alt = x.to(dtype), alt.to(dtype)
+    s = stem_ref(sd, x)
+    s = F.relu(_bn(_conv(s, sd, "mid_stem.0", padding=1), sd, "mid_stem.1"))
+    s = F.relu(_bn(_conv(s, sd, "mid_stem.3", padding=1), sd, "mid_stem.4"))
+    a = F.relu(_bn(_conv(alt, sd, "alt_img_stem.0", stride=2, padding=2), sd, "alt_img_stem.1"))
+    a = F.relu(_bn(_conv(a, sd, "alt_img_stem.3", stride=2, padding=2), sd, "alt_img_stem.4"))
+    hw = s.shape[-2:]
+    s = torch.cat((s, F.interpolate(alt, hw, mode="bilinear")), dim=1)
+    dil4 = (1, 2, 3, 4)
+    hi = cam_ref(sd, s, "att_hi.0", dil4)
+    mid = cam_ref(sd, _pool(s), "att_mid.1", dil4)
+    lo = cam_ref(sd, _pool(mid), "att_lo.1", dil4)
+    lo_up = F.interpolate(lo, hw, mode="nearest")
+    att = _conv(hi + lo_up + lo_up, sd, "att_top.0", padding=1)
+    if att_divisor is not None:
+        att = att / att_divisor
+    att = torch.sigmoid(att)
+    y = torch.cat((s * att.expand(s.shape), a), dim=1)
+    i = 0
+    while ("steps.%d.residual.0.weight" % i) in sd:
+        y = cam_ref(sd, y, "steps.%d" % i, (1, 2, 3))
+        i += 1
+    det = _conv(y, sd, "steps.%d" % i, padding=1)
+    return att, det

@@ -11,8 +11,9 @@ from .hhrnet import PoseHigherResolutionNet, BasicBlock, Bottleneck, HighResolut
     NoOpModule  # noqa: F401
 from .precision import network_to_half, tofp16, tofp32, BN_convert_float, \
     get_hrnet_w48_teacher, W48_KWARGS  # noqa: F401
-from .students import AttentionStudent, CamStudent, ContextAwareModule, RefinerStudent, \
-    SELayer, SkipConv, StemHRNet  # noqa: F401
+from .students import AttentionStudent, AttentionStudentSteps, CamStudent, ContextAwareModule, \
+    MultistageStudent, RefinerStudent, SELayer, SkipConv, StemHRNet  # noqa: F401
+from .engine import eval_student  # noqa: F401
 from .teacher_dump import TeacherDumpWriter, TeacherDumper, load_teacher_data, \
     HEATMAPS_ORDER  # noqa: F401
 from . import preprocess  # noqa: F401

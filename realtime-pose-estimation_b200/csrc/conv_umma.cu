@@ -379,7 +379,10 @@ UmmaConvPrepared* umma_conv_prepare(const brtpe_conv_desc* d, const void* in, co
   p.epi.out = nullptr; p.epi.res = nullptr;
   p.epi.out_ld = d->out_ld; p.epi.out_coff = d->out_coff; p.epi.res_ld = d->res_ld;
   p.epi.res_coff = d->res_coff; p.epi.Cout = d->Cout; p.epi.Cout_store = d->Cout_store;
-  p.epi.relu = d->relu; p.epi.vec32 = epi_vec32_ok(d); p.epi.fast = epi_fast_ok(d);
+  p.epi.relu = d->relu; p.epi.vec32 = epi_vec32_ok(d);
+  // the fast epilogue walks whole 16-channel chunks of every Cout tile without a bound check: only
+  // for tilings that cover the channels exactly (176 = 2 x 96 would write 16 channels too many)
+  p.epi.fast = (epi_fast_ok(d) && p.n_tiles * p.BN == d->Cout) ? 1 : 0;
   p.fd_nt = make_fastdiv((uint32_t)p.n_tiles, (uint64_t)p.total_tiles + 1);
   p.fd_xy = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y), (uint64_t)p.total_tiles + 1);
   p.fd_x = make_fastdiv((uint32_t)p.tiles_x, (uint64_t)p.tiles_x * p.tiles_y);

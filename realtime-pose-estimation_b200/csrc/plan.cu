@@ -25,7 +25,7 @@ struct Op {
   UmmaConvPrepared* umma;  // non-null: tcgen05 per-tap path
   HaloConvPrepared* halo;  // non-null: tcgen05 halo-tile path
   // stem / tonchw / fuse
-  int i[12];
+  int i[16];
   const void* terms[4];
   int shifts[4], lds[4];
   const float* stem_w;
@@ -75,7 +75,7 @@ static int run_op(const Op& op, cudaStream_t st) {
     case OP_IM2COL:
       return stem_im2col_launch(op.in, op.i[0], op.i[1], op.i[2], op.i[3], op.out, st);
     case OP_AUX:
-      return aux_launch(op.i[8], op.terms[0], op.terms[1], op.terms[2], op.out, op.i, st);
+      return aux_launch(op.i[15], op.terms[0], op.terms[1], op.terms[2], op.out, op.i, st);
   }
   return BRTPE_EINVAL;
 }
@@ -237,14 +237,14 @@ extern "C" int brtpe_plan_add_stem_im2col(brtpe_plan* pl, const void* img, int i
 
 extern "C" int brtpe_plan_add_aux(brtpe_plan* pl, int kind, const void* in0, const void* in1,
                                   const void* in2, void* out, const int32_t* iparams, int nparams) {
-  BRTPE_CHECK_ARG(pl && in0 && out && iparams && nparams >= 4 && nparams <= 8,
+  BRTPE_CHECK_ARG(pl && in0 && out && iparams && nparams >= 4 && nparams <= 12,
                   "brtpe_plan_add_aux: bad arguments");
   Op op{};
   op.kind = OP_AUX;
   op.terms[0] = in0; op.terms[1] = in1; op.terms[2] = in2;
   op.out = out;
   for (int i = 0; i < nparams; ++i) op.i[i] = iparams[i];
-  op.i[8] = kind;
+  op.i[15] = kind;
   pl->ops.push_back(op);
   return BRTPE_OK;
 }

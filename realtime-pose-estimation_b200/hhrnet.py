@@ -577,9 +577,13 @@ class _PlanRunner:
     def _mode(self):
         return "fp32" if self._ref_param().dtype == torch.float32 else "bf16"
 
+    def _plan_extra_key(self):
+        """Forward arguments that change the recorded plan (e.g. a student's ``out_hw``)."""
+        return None
+
     def _get_plan(self, n, h, w, mode, device, in_dtype, stem_mode=0):
         key = (n, h, w, mode, str(device), in_dtype, self.conv_engine, self.parallel_branches,
-               stem_mode)
+               stem_mode, self._plan_extra_key())
         plan = self._plans.get(key)
         if plan is None:
             in_is_half = in_dtype == torch.float16
@@ -597,13 +601,16 @@ class _PlanRunner:
             self._plans[key] = plan
         return plan
 
-    def _run_plans(self, x, size_multiple, flip_pair=False, via_half=False, borrow=False):
+    def _run_plans(self, x, size_multiple, flip_pair=False, via_half=False, borrow=False,
+                   extra=None):
         """``flip_pair``: run the network on cat(x, flip(x, [3])) without materialising the batch
         (rows [0:N] of every output belong to x, rows [N:2N] to the mirrored images);
         ``via_half``: a float32 input is rounded through fp16 first (the tofp16 wrapper);
         ``borrow``: when one plan replay covers the whole batch, return the plan's own output
         buffers instead of copies -- valid only until the next forward of this module (callers that
-        consume the outputs in stream order before that, like ``TeacherPipeline``)."""
+        consume the outputs in stream order before that, like ``TeacherPipeline``);
+        ``extra``: second per-image input (N, ...) copied chunk by chunk into the buffer the
+        recorder exposes as ``extra_input`` (``AttentionStudentSteps``' ``alt`` image)."""
         lib = L.load()
         if not isinstance(x, torch.Tensor) or not x.is_cuda:
             raise L.BrtpeError("%s.forward needs a CUDA tensor (no CPU fallback); got %r"
@@ -658,6 +665,8 @@ class _PlanRunner:
                 cn = min(nb, n - s0)
                 plan = self._get_plan(cn, h, w, mode, dev, x.dtype)
                 plan.in_buf.copy_(x[s0:s0 + cn])
+                if extra is not None:
+                    plan.recorder.extra_input.copy_(extra[s0:s0 + cn])
                 if self.use_cuda_graph:
                     L.check(lib.brtpe_plan_graph_launch(plan.handle, st), "brtpe_plan_graph_launch")
                 else:

@@ -22,6 +22,11 @@ SHAPES = [
     (1, 16, 16, 256, 48, 3, 1, True, False),
     (3, 24, 40, 48, 34, 1, 1, False, False),
     (1, 16, 16, 384, 48, 1, 1, False, False),
+    # Cout tilings that do not cover the channels exactly (176 = 2 x 96, 208 = 2 x 112): the
+    # chunk-wise fast epilogue must not run over the end (AttentionStudentSteps, inplanes 80)
+    (2, 32, 32, 176, 176, 1, 1, True, False),
+    (1, 24, 24, 64, 208, 1, 1, True, True),
+    (1, 16, 24, 320, 32, 1, 1, True, True),
 ]
 
 
@@ -69,6 +74,18 @@ HALO_SHAPES = [
     (1, 24, 24, 64, 256, 3, 1, True, True),
     (1, 24, 24, 80, 144, 3, 1, False, False),
     (2, 16, 16, 48, 1, 3, 1, False, False),
+    # MultistageStudent (256 + 18 -> 288 / 320 stored channels) and AttentionStudentSteps
+    # (16-channel space-to-depth image, 4 x 64 space-to-depth planes, 64 / 96 / 112 / 176 wide concats)
+    (1, 16, 24, 320, 288, 3, 1, True, False),
+    (1, 16, 24, 288, 288, 3, 1, True, False),
+    (1, 16, 24, 288, 32, 3, 1, True, False),
+    (1, 21, 35, 256, 288, 3, 1, True, False),
+    (2, 32, 48, 16, 64, 3, 1, True, False),
+    (2, 16, 24, 256, 48, 3, 1, True, False),
+    (2, 16, 24, 64, 16, 3, 1, True, False),
+    (2, 16, 24, 112, 32, 3, 1, True, False),
+    (1, 12, 20, 176, 48, 3, 1, True, False),
+    (1, 12, 20, 176, 16, 3, 1, False, False),
 ]
 
 

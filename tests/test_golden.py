@@ -114,3 +114,39 @@ def test_refiner_student_oracle_matches_reference_fixture():
         want = torch.from_numpy(want)
         assert got.shape == want.shape
         assert ((got - want).abs().max() / want.abs().max()).item() <= 1e-5
+
+
+def test_multistage_student_oracle_matches_reference_fixture():
+    """MultistageStudent (students.py:389-499): every stage output, with and without out_hw."""
+    from rtpe_b200.students import MultistageStudent
+    from oracle.student_ref import multistage_student_forward_ref
+    z = np.load(os.path.join(GOLD, "multistage_student_64x96.npz"))
+    net = MultistageStudent(None, "cpu", half_precision=False)
+    assert len(net.state_dict()) == int(z["entries"])
+    fill_params_deterministic(net, int(z["seed"]))
+    x = torch.from_numpy(z["x"])
+    outs = multistage_student_forward_ref(net.state_dict(), x)
+    outs_up = multistage_student_forward_ref(net.state_dict(), x, out_hw=tuple(z["outs_up"].shape[3:]))
+    for got, want in ((outs, z["outs"]), (outs_up, z["outs_up"])):
+        assert len(got) == want.shape[0]
+        for g, w_ in zip(got, want):
+            w_ = torch.from_numpy(w_)
+            assert g.shape == w_.shape
+            assert ((g - w_).abs().max() / w_.abs().max()).item() <= 1e-5
+
+
+def test_attention_student_steps_oracle_matches_reference_fixture():
+    """AttentionStudentSteps (students.py:786-1073), with and without att_divisor."""
+    from rtpe_b200.students import AttentionStudentSteps
+    from oracle.student_ref import attention_student_steps_forward_ref
+    z = np.load(os.path.join(GOLD, "attention_steps_64x96.npz"))
+    net = AttentionStudentSteps(None, "cpu", int(z["inplanes"]), 17, 1, False)
+    assert len(net.state_dict()) == int(z["entries"])
+    fill_params_deterministic(net, int(z["seed"]))
+    x, alt = torch.from_numpy(z["x"]), torch.from_numpy(z["alt"])
+    att, det = attention_student_steps_forward_ref(net.state_dict(), x, alt)
+    att20, det20 = attention_student_steps_forward_ref(net.state_dict(), x, alt, att_divisor=20)
+    for got, key in ((att, "att"), (det, "det"), (att20, "att20"), (det20, "det20")):
+        want = torch.from_numpy(z[key])
+        assert got.shape == want.shape
+        assert ((got - want).abs().max() / want.abs().max()).item() <= 1e-5

@@ -140,3 +140,59 @@ def test_refiner_student_oracle_vs_reference_class():
     assert [(k, tuple(v.shape)) for k, v in mine.state_dict().items()] == \
         [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
     mine.load_state_dict(ref.state_dict(), strict=True)
+
+
+def test_multistage_student_oracle_vs_reference_class():
+    """oracle multistage_student_forward_ref against rtpe.students.MultistageStudent itself
+    (students.py:389-499; built through the harness's CPU construction workaround)."""
+    from oracle.ref_loader import load_reference_students
+    from oracle.make_golden import build_reference_multistage
+    from oracle.student_ref import multistage_student_forward_ref
+    from oracle.weights import fill_params_deterministic
+    from rtpe_b200.students import MultistageStudent
+    S = load_reference_students()
+    torch.manual_seed(0)
+    ref = build_reference_multistage(S, layers_per_stage=[2, 3])
+    fill_params_deterministic(ref, 7)
+    x = torch.randn(2, 3, 48, 80, generator=torch.Generator().manual_seed(8))
+    with torch.no_grad():
+        a = ref(x)
+        b = ref(x, out_hw=(30, 50))
+    a2 = multistage_student_forward_ref(ref.state_dict(), x)
+    b2 = multistage_student_forward_ref(ref.state_dict(), x, out_hw=(30, 50))
+    assert len(a) == len(a2) == 2 and all(torch.equal(p, q) for p, q in zip(a, a2))
+    assert all(torch.equal(p, q) for p, q in zip(b, b2))
+    mine = MultistageStudent(None, "cpu", layers_per_stage=[2, 3], half_precision=False)
+    assert [(k, tuple(v.shape)) for k, v in mine.state_dict().items()] == \
+        [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
+    mine.load_state_dict(ref.state_dict(), strict=True)
+
+
+def test_attention_student_steps_oracle_vs_reference_class():
+    """oracle attention_student_steps_forward_ref against rtpe.students.AttentionStudentSteps itself
+    (students.py:786-1073), eval_attention.py's inplanes = 80, with and without att_divisor."""
+    import warnings
+    from oracle.ref_loader import load_reference_students
+    from oracle.student_ref import attention_student_steps_forward_ref
+    from oracle.weights import fill_params_deterministic
+    from rtpe_b200.students import AttentionStudentSteps
+    S = load_reference_students()
+    torch.manual_seed(0)
+    ref = S.AttentionStudentSteps(None, "cpu", 80, 17, 0, False).eval()
+    fill_params_deterministic(ref, 7)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 3, 48, 80, generator=g)
+    alt = torch.randn(2, 3, 48, 80, generator=g)
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a, d = ref(x, alt=alt)
+        a20, d20 = ref(x, alt=alt, att_divisor=20)
+    a2, d2 = attention_student_steps_forward_ref(ref.state_dict(), x, alt)
+    a3, d3 = attention_student_steps_forward_ref(ref.state_dict(), x, alt, att_divisor=20)
+    assert torch.equal(a, a2) and torch.equal(d, d2) and torch.equal(a20, a3) and torch.equal(d20, d3)
+    mine = AttentionStudentSteps(None, "cpu", 80, 17, 0, False)
+    assert [(k, tuple(v.shape)) for k, v in mine.state_dict().items()] == \
+        [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    with pytest.raises(NotImplementedError):
+        mine(x)                                      # "ATM alt is expected" (students.py:983)

@@ -171,3 +171,166 @@ def test_refiner_student_bf16_vs_oracle(cuda_device):
     with torch.no_grad():
         pred = net(x.cuda())
     assert _rel(pred, ref) <= 2e-2
+
+
+# ---- MultistageStudent (rtpe/students.py:389-499)
+def _multistage_student(half, seed, **kw):
+    from rtpe_b200.students import MultistageStudent
+    net = MultistageStudent(None, "cpu", half_precision=half, **kw)
+    fill_params_deterministic(net, seed)
+    return net.eval()
+
+
+def test_multistage_student_fp32_vs_oracle_and_fixture(cuda_device):
+    from oracle.student_ref import multistage_student_forward_ref
+    net = _multistage_student(False, 41, layers_per_stage=[2, 3, 1, 2])
+    x = torch.randn(3, 3, 64, 96, generator=torch.Generator().manual_seed(42))
+    ref = multistage_student_forward_ref(net.state_dict(), x)
+    ref_up = multistage_student_forward_ref(net.state_dict(), x, out_hw=(50, 70))
+    net = net.cuda()
+    with torch.no_grad():
+        outs = net(x.cuda())
+        outs_up = net(x.cuda(), out_hw=(50, 70))
+        again = net(x.cuda())                                   # the out_hw plan did not replace it
+    assert len(outs) == len(ref) == 4 and outs[0].shape == ref[0].shape == (3, 18, 16, 24)
+    assert outs_up[0].shape == ref_up[0].shape == (3, 18, 50, 70)
+    for g, r in zip(outs + outs_up, ref + ref_up):
+        assert _rel(g, r) <= 1e-4
+    assert all(torch.equal(a, b) for a, b in zip(outs, again))
+    z = np.load(os.path.join(GOLD, "multistage_student_64x96.npz"))
+    net = _multistage_student(False, int(z["seed"])).cuda()
+    with torch.no_grad():
+        outs = net(torch.from_numpy(z["x"]).cuda())
+        outs_up = net(torch.from_numpy(z["x"]).cuda(), out_hw=tuple(z["outs_up"].shape[3:]))
+    for g, r in zip(outs, z["outs"]):
+        assert _rel(g, torch.from_numpy(r)) <= 1e-4
+    for g, r in zip(outs_up, z["outs_up"]):
+        assert _rel(g, torch.from_numpy(r)) <= 1e-4
+
+
+def test_multistage_student_bf16_vs_oracle(cuda_device):
+    from oracle.student_ref import multistage_student_forward_ref
+    net = _multistage_student(True, 43)
+    sd = {k: v.float() for k, v in net.state_dict().items()}
+    x = torch.randn(2, 3, 128, 128, generator=torch.Generator().manual_seed(44))
+    ref = multistage_student_forward_ref(sd, x)
+    ref_up = multistage_student_forward_ref(sd, x, out_hw=(40, 56))
+    net = net.cuda()
+    with torch.no_grad():
+        outs = net(x.cuda())
+        outs_up = net(x.cuda(), out_hw=(40, 56))
+    for g, r in zip(outs + outs_up, ref + ref_up):
+        assert torch.isfinite(g).all()
+        assert _rel(g, r) <= 2e-2
+
+
+# ---- AttentionStudentSteps (rtpe/students.py:786-1073, eval_attention.py:95-104)
+def _steps_student(half, seed, inplanes, ae_dims=1):
+    from rtpe_b200.students import AttentionStudentSteps
+    net = AttentionStudentSteps(None, "cpu", inplanes, 17, ae_dims, half)
+    fill_params_deterministic(net, seed)
+    return net.eval()
+
+
+def test_attention_student_steps_fp32_vs_oracle_and_fixture(cuda_device):
+    from oracle.student_ref import attention_student_steps_forward_ref
+    net = _steps_student(False, 51, 80, ae_dims=0)              # eval_attention.py's configuration
+    g = torch.Generator().manual_seed(52)
+    x = torch.randn(3, 3, 64, 96, generator=g)
+    alt = torch.randn(3, 3, 64, 96, generator=g)
+    ref = attention_student_steps_forward_ref(net.state_dict(), x, alt)
+    ref20 = attention_student_steps_forward_ref(net.state_dict(), x, alt, att_divisor=20)
+    net = net.cuda()
+    net.chunk_size = 2                                           # 3 images = chunks of 2 + 1
+    with torch.no_grad():
+        got = net(x.cuda(), alt=alt.cuda())
+        got20 = net(x.cuda(), alt=alt.cuda(), att_divisor=20)
+    assert got[0].shape == ref[0].shape == (3, 1, 16, 24) and got[1].shape == ref[1].shape == (3, 17, 16, 24)
+    for a, b in zip(got + got20, ref + ref20):
+        assert _rel(a, b) <= 1e-4
+    z = np.load(os.path.join(GOLD, "attention_steps_64x96.npz"))
+    net = _steps_student(False, int(z["seed"]), int(z["inplanes"])).cuda()
+    x, alt = torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["alt"]).cuda()
+    with torch.no_grad():
+        att, det = net(x, alt=alt)
+        att20, det20 = net(x, alt=alt, att_divisor=20)
+    for a, key in ((att, "att"), (det, "det"), (att20, "att20"), (det20, "det20")):
+        assert _rel(a, torch.from_numpy(z[key])) <= 1e-4
+    with pytest.raises(NotImplementedError):
+        net(x)
+
+
+@pytest.mark.parametrize("inplanes", [48, 80])
+def test_attention_student_steps_bf16_vs_oracle(cuda_device, inplanes):
+    from oracle.student_ref import attention_student_steps_forward_ref
+    net = _steps_student(True, 53, inplanes)
+    sd = {k: v.float() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(54)
+    x = torch.randn(2, 3, 128, 128, generator=g)
+    alt = torch.randn(2, 3, 128, 128, generator=g)
+    ref = attention_student_steps_forward_ref(sd, x, alt, att_divisor=20)
+    net = net.cuda()
+    with torch.no_grad():
+        got = net(x.cuda(), alt=alt.cuda(), att_divisor=20)
+    for a, b in zip(got, ref):
+        assert torch.isfinite(a).all()
+        assert _rel(a, b) <= 2e-2
+
+
+# ---- eval_student (rtpe/engine.py:21-75)
+class _FakeValSet:
+    def evaluate(self, preds, scores, out_dir, a, b):
+        self.got = (preds, scores, out_dir, a, b)
+        return {"AP": 0.5, "people": sum(len(p) for p in preds)}, 0.5
+
+
+class _FakeLoader:
+    def __init__(self, batches):
+        self.dataset = _FakeValSet()
+        self.batches = batches
+
+    def __iter__(self):
+        return iter(self.batches)
+
+
+class _BlobModel(torch.nn.Module):
+    """Stand-in student: returns the decode generator's maps, resized like a student's out_hw."""
+    def __init__(self, det, tag):
+        super().__init__()
+        self.pred = torch.cat((det, tag[..., 0]), dim=1)          # (N, 17 + 1, h, w)
+        self.at = 0
+
+    def forward(self, img, out_hw=None):
+        n = img.shape[0]
+        out = self.pred[self.at:self.at + n].to(img.device)
+        self.at += n
+        return out
+
+
+def test_eval_student_batched_equals_reference_loop(cuda_device):
+    """Batched decode of a whole loader batch == the reference's image-by-image ``parse`` loop
+    (rtpe/engine.py:38-51), and the evaluate() call gets the reference's arguments."""
+    det, tag = rtpe_b200.synth_decode_batch(5, height=64, width=80, max_people=5, seed=61,
+                                            tag_per_joint=False)
+    kw = dict(num_joints=17, max_num_people=30, detection_threshold=0.1, tag_threshold=1.0,
+              use_detection_val=True, ignore_too_much=False, tag_per_joint=False)
+    hp = rtpe_b200.HeatmapParser(**kw)
+    imgs = torch.zeros(5, 3, 64, 80)
+    mk = lambda sizes: _FakeLoader([(torch.arange(a, b), imgs[a:b], None, None, None, None)  # noqa: E731
+                                    for a, b in sizes])
+    one = mk([(i, i + 1) for i in range(5)])
+    many = mk([(0, 2), (2, 5)])
+    r1 = rtpe_b200.eval_student(_BlobModel(det, tag), hp, one, "cuda", batched=False, verbose=False)
+    r2 = rtpe_b200.eval_student(_BlobModel(det, tag), hp, many, "cuda", verbose=False)
+    assert r1 == r2 and r1["people"] > 0
+    assert one.dataset.got[2:] == (".", False, False)
+    want = G.parse_batch_ref(det.numpy().copy(), tag.numpy().copy(), G.DecodeParams(**kw), True, True)
+    for got in (one.dataset.got, many.dataset.got):
+        preds, scores = got[:2]
+        assert len(preds) == len(scores) == 5
+        for gp, gs, (wp, ws) in zip(preds, scores, want):
+            wp = [x for x in np.asarray(wp) if x.size > 0]
+            assert len(gp) == len(wp) and all(np.array_equal(a, b) for a, b in zip(gp, wp))
+            assert np.array_equal(np.asarray(gs, np.float32), np.asarray(ws, np.float32))
+    with pytest.raises(NotImplementedError):
+        rtpe_b200.eval_student(_BlobModel(det, tag), hp, one, "cuda", plot_every=1)
