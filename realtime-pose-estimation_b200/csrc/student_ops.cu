@@ -258,6 +258,155 @@ att_mul_kernel(const T* __restrict__ att, const T* __restrict__ x, T* __restrict
   }
 }
 
+// ---- bf16 fast paths: one thread = 8 consecutive channels (one 16-byte load / store) ---------
+struct BF8 {
+  uint4 u;
+};
+__device__ __forceinline__ void bf8_to_f32(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 v = __bfloat1622float2(h[i]);
+    f[2 * i] = v.x;
+    f[2 * i + 1] = v.y;
+  }
+}
+__device__ __forceinline__ uint4 f32_to_bf8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+__device__ __forceinline__ uint4 ld8(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const uint4& u) { *reinterpret_cast<uint4*>(p) = u; }
+
+__global__ void __launch_bounds__(256)
+avgpool3s2_bf8_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int N, int H,
+                      int W, int C8, int in_ld, int out_ld) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = (size_t)N * Ho * Wo * C8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    size_t p = i / C8;
+    const int xo = (int)(p % Wo);
+    p /= Wo;
+    const int yo = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int cnt = 0;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int y = 2 * yo + dy;
+      if (y < 0 || y >= H) continue;
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int x = 2 * xo + dx;
+        if (x < 0 || x >= W) continue;
+        float f[8];
+        bf8_to_f32(ld8(in + (((size_t)n * H + y) * W + x) * in_ld + c), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += f[j];
+        ++cnt;
+      }
+    }
+    const float inv = (float)cnt;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = s[j] / inv;
+    st8(out + (((size_t)n * Ho + yo) * Wo + xo) * out_ld + c, f32_to_bf8(s));
+  }
+}
+
+// partial[n][chunk][c]: thread = 8 channels of one pixel row slot; rows = 256 / C8 pixels in flight;
+// the per-row partial sums are reduced in a fixed order (deterministic)
+__global__ void __launch_bounds__(256)
+se_partial_bf8_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ partial, int HW, int C8,
+                      int ld, int chunks) {
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int per = (HW + chunks - 1) / chunks;
+  const int p0 = chunk * per, p1 = min(HW, p0 + per);
+  __shared__ float red[256 * 8];
+  const int rows = 256 / C8;
+  const int c8 = threadIdx.x % C8, r = threadIdx.x / C8;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (r < rows)
+    for (int p = p0 + r; p < p1; p += rows) {
+      float f[8];
+      bf8_to_f32(ld8(in + ((size_t)n * HW + p) * ld + c8 * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += f[j];
+    }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = (r < rows) ? s[j] : 0.0f;
+  __syncthreads();
+  const int C = C8 * 8;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float t = 0.0f;
+    for (int k = 0; k < rows; ++k) t += red[(k * C8 + c / 8) * 8 + (c & 7)];
+    partial[((size_t)n * chunks + chunk) * C + c] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cam_mix_bf8_kernel(const __nv_bfloat16* __restrict__ res, const __nv_bfloat16* __restrict__ hdc,
+                   const float* __restrict__ gate, __nv_bfloat16* __restrict__ out, int N, int HW, int C,
+                   int ld_res, int ld_hdc, int ld_out, int Cz8) {
+  const size_t total = (size_t)N * HW * Cz8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cz8) * 8;
+    const size_t p = i / Cz8;
+    const int n = (int)(p / HW);
+    float a[8], b[8], v[8];
+    bf8_to_f32(ld8(res + p * ld_res + c), a);
+    bf8_to_f32(ld8(hdc + p * ld_hdc + c), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] = (c + j < C) ? fmaxf(a[j] + b[j] * __ldg(gate + (size_t)n * C + c + j), 0.0f) : 0.0f;
+    st8(out + p * ld_out + c, f32_to_bf8(v));
+  }
+}
+
+// MUL = false: out = x + sigmoid(att / div)  (AttentionStudent); MUL = true: out = x * sigmoid(att / div)
+template <bool MUL>
+__global__ void __launch_bounds__(256)
+att_apply_bf8_kernel(const __nv_bfloat16* __restrict__ att, const __nv_bfloat16* __restrict__ x,
+                     __nv_bfloat16* __restrict__ out, float* __restrict__ att_out, size_t P, int C8,
+                     int ld_att, int ld_x, int ld_out, float div) {
+  const size_t total = P * C8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    const size_t p = i / C8;
+    const float a = 1.0f / (1.0f + expf(-(__bfloat162float(att[p * ld_att]) / div)));
+    if (c == 0) att_out[p] = a;
+    float f[8];
+    bf8_to_f32(ld8(x + p * ld_x + c), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = MUL ? f[j] * a : f[j] + a;
+    st8(out + p * ld_out + c, f32_to_bf8(f));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+s2d_bf8_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int N, int H, int W,
+               int C8, int in_ld, int out_ld) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = (size_t)N * Ho * Wo * 4 * C8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    size_t p = i / C8;
+    const int blk = (int)(p % 4);
+    p /= 4;
+    const int xo = (int)(p % Wo);
+    p /= Wo;
+    const int yo = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    st8(out + (((size_t)n * Ho + yo) * Wo + xo) * out_ld + blk * C8 * 8 + c,
+        ld8(in + (((size_t)n * H + 2 * yo + (blk >> 1)) * W + 2 * xo + (blk & 1)) * in_ld + c));
+  }
+}
+
 static int grid_for(size_t total) {
   size_t b = (total + 255) / 256;
   const size_t cap = (size_t)num_sms() * 16;
@@ -273,7 +422,9 @@ int aux_launch(int kind, const void* in0, const void* in1, const void* in2, void
       const int N = ip[1], H = ip[2], W = ip[3], C = ip[4], ild = ip[5], old = ip[6];
       BRTPE_CHECK_ARG(N > 0 && H >= 2 && W >= 2 && !(H & 1) && !(W & 1) && C > 0, "avgpool: bad shape");
       const int g = grid_for((size_t)N * (H / 2) * (W / 2) * C);
-      if (bf) avgpool3s2_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in0, (__nv_bfloat16*)out, N, H, W, C, ild, old);
+      if (bf && C % 8 == 0 && ild % 8 == 0 && old % 8 == 0)
+        avgpool3s2_bf8_kernel<<<grid_for((size_t)N * (H / 2) * (W / 2) * (C / 8)), 256, 0, st>>>((const __nv_bfloat16*)in0, (__nv_bfloat16*)out, N, H, W, C / 8, ild, old);
+      else if (bf) avgpool3s2_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in0, (__nv_bfloat16*)out, N, H, W, C, ild, old);
       else avgpool3s2_kernel<float><<<g, 256, 0, st>>>((const float*)in0, (float*)out, N, H, W, C, ild, old);
       break;
     }
@@ -281,7 +432,9 @@ int aux_launch(int kind, const void* in0, const void* in1, const void* in2, void
       const int N = ip[1], HW = ip[2], C = ip[3], ld = ip[4], chunks = ip[5];
       BRTPE_CHECK_ARG(N > 0 && HW > 0 && C > 0 && C <= 256 && chunks > 0, "se_partial: bad shape");
       dim3 grid(chunks, N);
-      if (bf) se_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in0, (float*)out, HW, C, ld, chunks);
+      if (bf && C % 8 == 0 && ld % 8 == 0)
+        se_partial_bf8_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)in0, (float*)out, HW, C / 8, ld, chunks);
+      else if (bf) se_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in0, (float*)out, HW, C, ld, chunks);
       else se_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)in0, (float*)out, HW, C, ld, chunks);
       break;
     }
@@ -297,7 +450,9 @@ int aux_launch(int kind, const void* in0, const void* in1, const void* in2, void
       const int Cz = ip[7] > C ? ip[7] : C;              // zero-fill the pad channels [C, Cz)
       BRTPE_CHECK_ARG(Cz <= ip[6], "cam_mix: zero fill beyond ld_out");
       const int g = grid_for((size_t)N * HW * Cz);
-      if (bf) cam_mix_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in0, (const __nv_bfloat16*)in1, (const float*)in2, (__nv_bfloat16*)out, N, HW, C, ip[4], ip[5], ip[6], Cz);
+      if (bf && Cz % 8 == 0 && ip[4] % 8 == 0 && ip[5] % 8 == 0 && ip[6] % 8 == 0 && ip[4] >= Cz && ip[5] >= Cz)
+        cam_mix_bf8_kernel<<<grid_for((size_t)N * HW * (Cz / 8)), 256, 0, st>>>((const __nv_bfloat16*)in0, (const __nv_bfloat16*)in1, (const float*)in2, (__nv_bfloat16*)out, N, HW, C, ip[4], ip[5], ip[6], Cz / 8);
+      else if (bf) cam_mix_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in0, (const __nv_bfloat16*)in1, (const float*)in2, (__nv_bfloat16*)out, N, HW, C, ip[4], ip[5], ip[6], Cz);
       else cam_mix_kernel<float><<<g, 256, 0, st>>>((const float*)in0, (const float*)in1, (const float*)in2, (float*)out, N, HW, C, ip[4], ip[5], ip[6], Cz);
       break;
     }
@@ -306,7 +461,9 @@ int aux_launch(int kind, const void* in0, const void* in1, const void* in2, void
       const int C = ip[3];
       const int g = grid_for(P * C);
       float* att_out = (float*)const_cast<void*>(in2);
-      if (bf) att_add_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in0, (const __nv_bfloat16*)in1, (__nv_bfloat16*)out, att_out, P, C, ip[4], ip[5], ip[6]);
+      if (bf && C % 8 == 0 && ip[5] % 8 == 0 && ip[6] % 8 == 0)
+        att_apply_bf8_kernel<false><<<grid_for(P * (C / 8)), 256, 0, st>>>((const __nv_bfloat16*)in0, (const __nv_bfloat16*)in1, (__nv_bfloat16*)out, att_out, P, C / 8, ip[4], ip[5], ip[6], 20.0f);
+      else if (bf) att_add_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in0, (const __nv_bfloat16*)in1, (__nv_bfloat16*)out, att_out, P, C, ip[4], ip[5], ip[6]);
       else att_add_kernel<float><<<g, 256, 0, st>>>((const float*)in0, (const float*)in1, (float*)out, att_out, P, C, ip[4], ip[5], ip[6]);
       break;
     }
@@ -344,7 +501,9 @@ int aux_launch(int kind, const void* in0, const void* in1, const void* in2, void
       BRTPE_CHECK_ARG(N > 0 && H >= 2 && W >= 2 && !(H & 1) && !(W & 1) && C > 0 && C <= ild &&
                       4 * C <= old, "space_to_depth: bad shape");
       const int g = grid_for((size_t)N * (H / 2) * (W / 2) * 4 * C);
-      if (bf) s2d_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in0, (__nv_bfloat16*)out, N, H, W, C, ild, old);
+      if (bf && C % 8 == 0 && ild % 8 == 0 && old % 8 == 0)
+        s2d_bf8_kernel<<<grid_for((size_t)N * (H / 2) * (W / 2) * 4 * (C / 8)), 256, 0, st>>>((const __nv_bfloat16*)in0, (__nv_bfloat16*)out, N, H, W, C / 8, ild, old);
+      else if (bf) s2d_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in0, (__nv_bfloat16*)out, N, H, W, C, ild, old);
       else s2d_kernel<float><<<g, 256, 0, st>>>((const float*)in0, (float*)out, N, H, W, C, ild, old);
       break;
     }
@@ -356,7 +515,9 @@ int aux_launch(int kind, const void* in0, const void* in1, const void* in2, void
       BRTPE_CHECK_ARG(P > 0 && C > 0 && in1 && in2 && div != 0.0f, "att_mul: bad arguments");
       const int g = grid_for(P * C);
       float* att_out = (float*)const_cast<void*>(in2);
-      if (bf) att_mul_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in0, (const __nv_bfloat16*)in1, (__nv_bfloat16*)out, att_out, P, C, ip[4], ip[5], ip[6], div);
+      if (bf && C % 8 == 0 && ip[5] % 8 == 0 && ip[6] % 8 == 0)
+        att_apply_bf8_kernel<true><<<grid_for(P * (C / 8)), 256, 0, st>>>((const __nv_bfloat16*)in0, (const __nv_bfloat16*)in1, (__nv_bfloat16*)out, att_out, P, C / 8, ip[4], ip[5], ip[6], div);
+      else if (bf) att_mul_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)in0, (const __nv_bfloat16*)in1, (__nv_bfloat16*)out, att_out, P, C, ip[4], ip[5], ip[6], div);
       else att_mul_kernel<float><<<g, 256, 0, st>>>((const float*)in0, (const float*)in1, (float*)out, att_out, P, C, ip[4], ip[5], ip[6], div);
       break;
     }
