@@ -273,6 +273,30 @@ static void umma_n_tiling(int cout_store, int* n_tiles, int* bn) {
   *bn = ((cp + *n_tiles - 1) / *n_tiles + 15) / 16 * 16;
 }
 
+// Per-layer Cout tiling.  Layers with a long reduction (taps x Cin >= 768: the 3x3 layers) are MMA
+// bound, not epilogue bound: tiles of up to 192 channels (one CTA per SM, 384 TMEM columns) re-load
+// the pixel operand fewer times -- 3x3 384 -> 384 on 20x20 maps: 2 x 192 instead of 3 x 128,
+// 0.0645 -> 0.0536 ms per 64 images (profiles/r01q_conv_384.md).  Only tilings that keep the packed
+// weight geometry of umma_n_tiling (brtpe_umma_weight_dims) are taken.  BRTPE_UMMA_WIDE=0 disables.
+static void umma_n_tiling_layer(const brtpe_conv_desc* d, int* n_tiles, int* bn) {
+  umma_n_tiling(d->Cout_store, n_tiles, bn);
+  static int wide = -1;
+  if (wide < 0) {
+    const char* e = getenv("BRTPE_UMMA_WIDE");
+    wide = e ? atoi(e) : 192;
+    if (wide == 1) wide = 192;
+    if (wide != 0 && (wide < 128 || wide > 256)) wide = 192;
+  }
+  if (!wide || d->ntaps * d->Cin < 768) return;
+  const int cp = (d->Cout_store + 15) / 16 * 16;
+  const int nt2 = (cp + wide - 1) / wide;
+  const int bn2 = ((cp + nt2 - 1) / nt2 + 15) / 16 * 16;
+  if (nt2 < *n_tiles && nt2 * bn2 == *n_tiles * *bn) {
+    *n_tiles = nt2;
+    *bn = bn2;
+  }
+}
+
 bool umma_conv_supported(const brtpe_conv_desc* d, const char** why) {
   static const char* msg = "";
   auto fail = [&](const char* m) {
@@ -329,7 +353,7 @@ UmmaConvPrepared* umma_conv_prepare(const brtpe_conv_desc* d, const void* in, co
       }
   p.TW = bw; p.TH = bh; p.TN = bnn;
   p.tiles_x = ceil_div(d->Wm, bw); p.tiles_y = ceil_div(d->Hm, bh); p.tiles_n = ceil_div(d->N, bnn);
-  umma_n_tiling(d->Cout_store, &p.n_tiles, &p.BN);
+  umma_n_tiling_layer(d, &p.n_tiles, &p.BN);
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
 
   p.ntaps = d->ntaps;

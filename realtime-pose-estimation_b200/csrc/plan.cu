@@ -44,9 +44,22 @@ static int choose_engine(const brtpe_conv_desc* d) {
     }
     return BRTPE_ENGINE_UMMA_HALO;
   }
-  if (d->engine == BRTPE_ENGINE_AUTO && halo_ok) return BRTPE_ENGINE_UMMA_HALO;
   const char* why = nullptr;
   const bool ok = umma_conv_supported(d, &why);
+  if (d->engine == BRTPE_ENGINE_AUTO && halo_ok) {
+    // The halo engine's 8 x 16 pixel tiles waste MMA rows on small maps (20 x 20 -> 24 x 32: 48 %);
+    // wide layers there are weight-operand bound anyway, so the per-tap engine with its free tile
+    // geometry (20 x 6 pixels) wins: 3x3 384 -> 384 @ 20x20, 64 images: 0.075 -> 0.054 ms
+    // (profiles/r01q_conv_384.md).  BRTPE_HALO_MIN_UTIL (percent, default 60; 0 = always halo).
+    static int min_util = -1;
+    if (min_util < 0) {
+      const char* e = getenv("BRTPE_HALO_MIN_UTIL");
+      min_util = e ? atoi(e) : 60;
+    }
+    const long covered = (long)((d->Hm + 7) / 8 * 8) * ((d->Wm + 15) / 16 * 16);
+    const bool wasteful = 100L * d->Hm * d->Wm < (long)min_util * covered;
+    if (!(wasteful && ok && d->Cin >= 256 && d->Cout_store >= 256)) return BRTPE_ENGINE_UMMA_HALO;
+  }
   if (d->engine == BRTPE_ENGINE_UMMA) {
     if (!ok) {
       set_error("conv: tcgen05 engine requested but unsupported: %s", why ? why : "?");
