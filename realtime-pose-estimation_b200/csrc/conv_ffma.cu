@@ -8,6 +8,7 @@
 // activations, a tap table (3x3 / 1x1 / stride 2 / one parity phase of the 4x4 s2
 // transposed conv), folded-BN bias, optional residual and ReLU in the epilogue.
 #include "conv_common.cuh"
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -319,6 +320,73 @@ __global__ void __launch_bounds__(256) fuse_sum_bf16x8_kernel(FuseArgs a) {
   *reinterpret_cast<uint4*>(op) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+
+// bf16 fast path, second version: block = (C/8 channel vectors) x (PX pixels) threads, grid =
+// (pixel blocks, rows, images): no integer division, the per-term row pointers are computed once
+// per thread, U pixels per thread with all their loads issued before the first add (the first
+// version spent ~280 instructions per 16 output bytes, most of them address arithmetic, and ran
+// at 41-58 % of the DRAM bandwidth with 62 % of the issue slots busy: gpurun_out/fuse_r01p.ncu-rep).
+// Same left-to-right fp32 summation order as the generic kernel.
+template <int U>
+__global__ void __launch_bounds__(256) fuse_sum_bf16x8_rows_kernel(FuseArgs a) {
+  const int px = blockDim.y;
+  const int c = threadIdx.x << 3;
+  const int y = blockIdx.y, n = blockIdx.z;
+  const __nv_bfloat16* rowp[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    rowp[k] = nullptr;
+    if (k < a.nterms) {
+      const int sh = a.shifts[k];
+      const int hk = a.H >> sh, wk = a.W >> sh;
+      rowp[k] = reinterpret_cast<const __nv_bfloat16*>(a.terms[k]) +
+                ((size_t)n * hk + (y >> sh)) * wk * a.ld[k] + c;
+    }
+  }
+  __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(a.out) +
+                        ((size_t)n * a.H + y) * a.W * a.out_ld + c;
+  const int x0 = blockIdx.x * (U * px) + threadIdx.y;
+  uint4 v[4][U];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < a.nterms) {
+      const int sh = a.shifts[k], ld = a.ld[k];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int x = x0 + j * px;
+        if (x < a.W) v[k][j] = __ldg(reinterpret_cast<const uint4*>(rowp[k] + (x >> sh) * ld));
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const int x = x0 + j * px;
+    if (x >= a.W) continue;
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < a.nterms) {
+        const uint32_t w[4] = {v[k][j].x, v[k][j].y, v[k][j].z, v[k][j].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+          s[2 * e] = (k == 0) ? lo : s[2 * e] + lo;
+          s[2 * e + 1] = (k == 0) ? hi : s[2 * e + 1] + hi;
+        }
+      }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float lo = s[2 * e], hi = s[2 * e + 1];
+      if (a.relu) { lo = fmaxf(lo, 0.0f); hi = fmaxf(hi, 0.0f); }
+      __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+      o[e] = *reinterpret_cast<uint32_t*>(&pk);
+    }
+    *reinterpret_cast<uint4*>(orow + (size_t)x * a.out_ld) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // NHWC (f32 | bf16) -> NCHW (f32 | f16) network outputs
 // ------------------------------------------------------------------------------------------
@@ -517,7 +585,23 @@ int fuse_sum_launch(int dtype, int nterms, const void* const* terms, const int32
               (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   for (int k = 0; k < nterms; ++k)
     fast = fast && (term_ld[k] % 8) == 0 && (reinterpret_cast<uintptr_t>(terms[k]) & 15) == 0;
-  if (fast) {
+  static int fuse_v2 = -1;
+  if (fuse_v2 < 0) {
+    const char* e = getenv("BRTPE_FUSE_V2");
+    fuse_v2 = e ? atoi(e) : 2;                 // 0: first version; 1 / 2 / 4: pixels per thread
+  }
+  const int cv = C / 8;
+  if (fast && fuse_v2 && cv <= 256 && H <= 65535 && N <= 65535) {
+    const int px = 256 / cv;
+    dim3 block(cv, px);
+    // pixels per thread, measured on the 23 fuse launches of a 64-forward plan: 1.66 ms (first
+    // version) -> 1.33 (U = 4) -> 1.24 (U = 2); U = 8: 2.6 ms (166 registers)
+    const int U = fuse_v2 == 1 ? 1 : fuse_v2 == 4 ? 4 : 2;
+    dim3 grid(ceil_div(W, U * px), H, N);
+    if (U == 1) fuse_sum_bf16x8_rows_kernel<1><<<grid, block, 0, st>>>(a);
+    else if (U == 4) fuse_sum_bf16x8_rows_kernel<4><<<grid, block, 0, st>>>(a);
+    else fuse_sum_bf16x8_rows_kernel<2><<<grid, block, 0, st>>>(a);
+  } else if (fast) {
     dim3 grid(ceil_div(W * (C / 8), 256), N * H);
     fuse_sum_bf16x8_kernel<<<grid, 256, 0, st>>>(a);
   } else if (dtype == BRTPE_DT_F32) {

@@ -141,3 +141,42 @@ def test_aux_rejects_bad_arguments(cuda_device):
     assert b"resize_nhwc" in lib.brtpe_last_error()
     unk = (C.c_int32 * 4)(L.DT_F32, 1, 1, 1)
     assert lib.brtpe_aux_run(42, L.ptr(x), None, None, L.ptr(x), unk, 4, L.stream_ptr()) < 0
+
+
+@pytest.mark.parametrize("c,h,w,shifts,relu", [
+    (48, 16, 160, (0, 1, 2, 3), True),      # HRNet branch 0: identity + three up-sampled terms
+    (96, 8, 40, (0, 0, 1), True),
+    (192, 4, 20, (0, 0), False),
+    (384, 2, 20, (0, 0, 0, 0), True),
+    (48, 6, 50, (0, 1), True),              # width that is not a multiple of the pixel block
+    (64, 3, 7, (0,), False),
+    (176, 5, 9, (0, 0), True),
+])
+def test_fuse_sum_bf16_bit_exact(cuda_device, c, h, w, shifts, relu):
+    """HighResolutionModule's cross-resolution sum (pose_higher_hrnet.py:245-254): nearest
+    up-sampling by 2^shift, fp32 left-to-right sum, ReLU, one bf16 rounding -- bit-exact."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(7)
+    n = 3
+    hh = h * 8                                                    # every shift divides H and W
+    ww = (w + 7) // 8 * 8 if max(shifts) > 0 else w
+    terms, ref = [], None
+    for k, sh in enumerate(shifts):
+        ld = c + 16 * (k % 2)                                     # padded leading dimensions too
+        t = torch.full((n, hh >> sh, ww >> sh, ld), float("nan"), dtype=torch.bfloat16, device="cuda")
+        t[..., :c] = torch.randn((n, hh >> sh, ww >> sh, c), generator=g).to("cuda", torch.bfloat16)
+        terms.append(t)
+        up = t[..., :c].float().repeat_interleave(1 << sh, 1).repeat_interleave(1 << sh, 2)
+        ref = up if ref is None else ref + up
+    if relu:
+        ref = torch.relu(ref)
+    out = torch.zeros((n, hh, ww, c + 16), dtype=torch.bfloat16, device="cuda")
+    nt = len(terms)
+    tp = (C.c_void_p * nt)(*[t.data_ptr() for t in terms])
+    sh = (C.c_int32 * nt)(*shifts)
+    ld = (C.c_int32 * nt)(*[t.shape[3] for t in terms])
+    L.check(lib.brtpe_fuse_sum(L.DT_BF16, nt, tp, sh, ld, n, hh, ww, c, L.ptr(out), out.shape[3],
+                               int(relu), L.stream_ptr()), "brtpe_fuse_sum")
+    torch.cuda.synchronize()
+    assert torch.equal(out[..., :c], ref.to(torch.bfloat16))
+    assert (out[..., c:] == 0).all()
