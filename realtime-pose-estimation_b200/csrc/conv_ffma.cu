@@ -581,7 +581,7 @@ int fuse_sum_launch(int dtype, int nterms, const void* const* terms, const int32
   const size_t total = (size_t)N * H * W * (C / 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
-  bool fast = dtype == BRTPE_DT_BF16 && (C % 8) == 0 && (out_ld % 8) == 0 && (long long)N * H <= 65535 &&
+  bool fast = dtype == BRTPE_DT_BF16 && (C % 8) == 0 && (out_ld % 8) == 0 &&
               (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   for (int k = 0; k < nterms; ++k)
     fast = fast && (term_ld[k] % 8) == 0 && (reinterpret_cast<uintptr_t>(terms[k]) & 15) == 0;
@@ -601,7 +601,7 @@ int fuse_sum_launch(int dtype, int nterms, const void* const* terms, const int32
     if (U == 1) fuse_sum_bf16x8_rows_kernel<1><<<grid, block, 0, st>>>(a);
     else if (U == 4) fuse_sum_bf16x8_rows_kernel<4><<<grid, block, 0, st>>>(a);
     else fuse_sum_bf16x8_rows_kernel<2><<<grid, block, 0, st>>>(a);
-  } else if (fast) {
+  } else if (fast && (long long)N * H <= 65535) {
     dim3 grid(ceil_div(W * (C / 8), 256), N * H);
     fuse_sum_bf16x8_kernel<<<grid, 256, 0, st>>>(a);
   } else if (dtype == BRTPE_DT_F32) {
