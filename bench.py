@@ -336,7 +336,7 @@ def run_ours(args, rank, world, local_rank):
         # CUDA-core FFMA kernel is the dominant one; the tensor peak is kept as denominator
         roofline = conv_roofline((1,), "conv_ffma_kernel (fp32 FFMA implicit GEMM)")
         roofline["note"] = "fp32 CUDA-core path; frac is against the bf16 tensor peak"
-    roofline_other = conv_roofline((0,), "conv_umma_kernel (tcgen05 implicit GEMM, 1x1 / s2 / deconv)")
+    roofline_other = conv_roofline((0,), "conv_umma_kernel (tcgen05 implicit GEMM, 1x1 / s2 / deconv / 3x3 384ch on 20x20 maps)")
     roofline["conv_share_of_forward"] = conv_ms / max(sum(ms_ops), 1e-9)
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.isfile(tpath):
