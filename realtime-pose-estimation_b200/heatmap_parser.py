@@ -56,6 +56,10 @@ class HeatmapParser(object):
         # first-try capacity of the per-image person list; the reference's list is
         # unbounded (<= J*K), so an overflow transparently re-runs with J*K.
         self.person_capacity = int(person_capacity)
+        # after an overflow the following decodes start at the J*K bound right away (a stream of
+        # crowded images -- e.g. an untrained student, ~170 "persons" per image -- would otherwise
+        # run the grouping twice per batch); results do not depend on the capacity
+        self._capacity_hint = 0
         self._ws = {}
 
     # ------------------------------------------------------------------ helpers
@@ -153,7 +157,8 @@ class HeatmapParser(object):
             raise ValueError("K mismatch: parser max_num_people %d, input %d"
                              % (self.params.max_num_people, k))
         pmax_full = self._pmax_full()
-        pmax = min(pmax_full, self.person_capacity) if pmax is None else int(pmax)
+        pmax = min(pmax_full, max(self.person_capacity, self._capacity_hint)) if pmax is None \
+            else int(pmax)
         prm = self._cparams()
         with torch.cuda.device(dev):
             while True:
@@ -170,7 +175,7 @@ class HeatmapParser(object):
                     return ans, count, pmax, (overflow if pmax < pmax_full else None)
                 if pmax >= pmax_full or int(overflow.item()) == 0:
                     return ans, count, pmax
-                pmax = pmax_full
+                pmax = self._capacity_hint = pmax_full
 
     def match(self, tag_k, loc_k, val_k):
         """group.py:140-142 -> list (one per image) of (P,J,3+T) float32 arrays."""
@@ -291,6 +296,7 @@ class HeatmapParser(object):
                 self.refine_device(det, tag, ans, count)
             if flag is None or int(flag.item()) == 0:
                 return ans, count, scores
+            self._capacity_hint = self._pmax_full()
             ans, count, pmax = self.match_device(val_k, ind_k, tag_k, w, pmax=self._pmax_full())
             flag = None
 

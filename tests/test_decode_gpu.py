@@ -260,3 +260,9 @@ def test_person_capacity_overflow_retry(cuda_device):
     got = small.parse_batch(det.cuda(), tag.cuda(), True, True)
     assert_people_equal(got, want)
     assert_people_equal(hp.parse_batch(det.cuda(), tag.cuda(), True, True), want)
+    # the overflow is remembered: the next decode starts at the J*K bound (no second grouping pass)
+    assert small._capacity_hint == small._pmax_full() and hp._capacity_hint == 0
+    val_k, ind_k, _, tag_k = small.top_k_device(det.cuda(), tag.cuda())
+    ans, count, pmax, flag = small.match_device(val_k, ind_k, tag_k, w, defer_overflow=True)
+    assert pmax == small._pmax_full() and flag is None
+    assert_people_equal(small.parse_batch(det.cuda(), tag.cuda(), True, True), want)
