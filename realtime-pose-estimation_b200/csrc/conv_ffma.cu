@@ -140,6 +140,167 @@ __global__ void __launch_bounds__(FTHREADS) conv_ffma_kernel(FfmaArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// fp32 mode, second version: 128 pixels x (64 | 128) output channels per CTA, 8 x (4 | 8) outputs
+// per thread, K chunks of 16 double-buffered in shared memory with the next chunk's global loads in
+// flight during the FMAs, 16-byte global loads where the layout allows.  Every output accumulates
+// its products in the same order as conv_ffma_kernel (taps, then channels ascending): bit-identical
+// results.  (The first version -- 64 x 64 tiles, 4 x 4 outputs per thread, two barriers per chunk --
+// runs at ~24 TFLOP/s, a third of the FP32 pipe.)
+// ------------------------------------------------------------------------------------------
+constexpr int GBM = 128, GBK = 16, GTHREADS = 256;
+
+template <int BN>
+__global__ void __launch_bounds__(GTHREADS, 2) conv_ffma_big_kernel(FfmaArgs a, int a_vec, int b_vec) {
+  constexpr int TN = BN / 16;                 // output channels per thread (4 or 8)
+  constexpr int NB4 = TN / 4;                 // float4 groups of output channels per thread
+  __shared__ __align__(16) float As[2][GBK][GBM + 4];
+  __shared__ __align__(16) float Bs[2][GBK][BN + 4];
+  __shared__ int s_pix_n[GBM], s_pix_y[GBM], s_pix_x[GBM];
+
+  const brtpe_conv_desc& d = a.d;
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * GBM;
+  const int n0 = blockIdx.y * BN;
+  const float* __restrict__ in = reinterpret_cast<const float*>(a.in);
+
+  if (tid < GBM) {
+    const int m = m0 + tid;
+    if (m < a.M) {
+      const int hw = d.Hm * d.Wm;
+      const int n = m / hw;
+      const int r = m - n * hw;
+      s_pix_n[tid] = n;
+      s_pix_y[tid] = r / d.Wm;
+      s_pix_x[tid] = r - (r / d.Wm) * d.Wm;
+    } else {
+      s_pix_n[tid] = -1;
+      s_pix_y[tid] = 0;
+      s_pix_x[tid] = 0;
+    }
+  }
+  __syncthreads();
+
+  const int tx = tid & 15;                    // output-channel group: channels tx*4 + g*64 + (0..3)
+  const int ty = tid >> 4;                    // pixel group: pixels ty*8 + (0..7)
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+
+  // A loader: thread -> (pixel = tid / 2, 8 channels from (tid % 2) * 8)
+  const int a_pix = tid >> 1;
+  const int a_k = (tid & 1) * 8;
+  const int pn = s_pix_n[a_pix];
+  const int py = s_pix_y[a_pix] * d.in_stride, px = s_pix_x[a_pix] * d.in_stride;
+  // B loader: thread -> (k = tid / 16, TN output channels: group g at n0 + g*64 + (tid % 16) * 4)
+  const int b_k = tid >> 4;
+  const int b_c = (tid & 15) * 4;
+
+  const int kchunks = (d.Cin + GBK - 1) / GBK;
+  const int total = d.ntaps * kchunks;
+  float av[8], bv[TN];
+
+  auto load = [&](int it) {
+    const int tap = it / kchunks;
+    const int c0 = (it - tap * kchunks) * GBK;
+    const int iy = py + d.tap_dy[tap], ix = px + d.tap_dx[tap];
+    const bool pvalid = (pn >= 0) && iy >= 0 && iy < d.Hin && ix >= 0 && ix < d.Win;
+    const float* __restrict__ prow =
+        in + (((size_t)(pn < 0 ? 0 : pn) * d.Hin + (pvalid ? iy : 0)) * d.Win + (pvalid ? ix : 0)) *
+                 (size_t)d.in_ld + d.in_coff;
+    const int ca = c0 + a_k;
+    if (a_vec) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pvalid && ca + 4 * h < d.Cin) v = __ldg(reinterpret_cast<const float4*>(prow + ca + 4 * h));
+        av[4 * h] = v.x; av[4 * h + 1] = v.y; av[4 * h + 2] = v.z; av[4 * h + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) av[e] = (pvalid && ca + e < d.Cin) ? __ldg(prow + ca + e) : 0.0f;
+    }
+    const int cb = c0 + b_k;
+    const float* __restrict__ wrow = a.w + ((size_t)tap * d.Cin + cb) * d.Cout;
+#pragma unroll
+    for (int g = 0; g < NB4; ++g) {
+      const int co = n0 + g * 64 + b_c;
+      if (b_vec) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cb < d.Cin && co < d.Cout) v = __ldg(reinterpret_cast<const float4*>(wrow + co));
+        bv[4 * g] = v.x; bv[4 * g + 1] = v.y; bv[4 * g + 2] = v.z; bv[4 * g + 3] = v.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          bv[4 * g + e] = (cb < d.Cin && co + e < d.Cout) ? __ldg(wrow + co + e) : 0.0f;
+      }
+    }
+  };
+  auto store = [&](int buf) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) As[buf][a_k + e][a_pix] = av[e];
+#pragma unroll
+    for (int g = 0; g < NB4; ++g)
+      *reinterpret_cast<float4*>(&Bs[buf][b_k][g * 64 + b_c]) =
+          make_float4(bv[4 * g], bv[4 * g + 1], bv[4 * g + 2], bv[4 * g + 3]);
+  };
+
+  load(0);
+  store(0);
+  __syncthreads();
+  for (int it = 0; it < total; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < total) load(it + 1);
+#pragma unroll
+    for (int k = 0; k < GBK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+      const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float br[TN];
+#pragma unroll
+      for (int g = 0; g < NB4; ++g) {
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][g * 64 + tx * 4]);
+        br[4 * g] = b4.x; br[4 * g + 1] = b4.y; br[4 * g + 2] = b4.z; br[4 * g + 3] = b4.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    if (it + 1 < total) store(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---- epilogue
+  float* __restrict__ out = reinterpret_cast<float*>(a.out);
+  const float* __restrict__ res = reinterpret_cast<const float*>(a.res);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int pl = ty * 8 + i;
+    const int qn = s_pix_n[pl];
+    if (qn < 0) continue;
+    const int oy = s_pix_y[pl] * d.out_scale + d.out_oy;
+    const int ox = s_pix_x[pl] * d.out_scale + d.out_ox;
+    const size_t opix = ((size_t)qn * d.Hout + oy) * d.Wout + ox;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int co = n0 + (j >> 2) * 64 + tx * 4 + (j & 3);
+      if (co >= d.Cout_store) continue;
+      float v = 0.0f;
+      if (co < d.Cout) {
+        v = acc[i][j];
+        if (a.bias) v += __ldg(a.bias + co);
+        if (res) v += res[opix * d.res_ld + d.res_coff + co];
+        if (d.relu) v = fmaxf(v, 0.0f);
+      }
+      out[opix * d.out_ld + d.out_coff + co] = v;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // stem conv1: NCHW float/half image -> 3x3 s2 p1 conv (3 -> Cout) + bias + ReLU -> NHWC
 // ------------------------------------------------------------------------------------------
@@ -489,6 +650,25 @@ int conv_ffma_launch(const brtpe_conv_desc* d, const void* in, const void* weigh
   a.res = residual;
   a.out = out;
   a.M = d->N * d->Hm * d->Wm;
+  static int big = -1;
+  if (big < 0) {
+    const char* e = getenv("BRTPE_FFMA_BIG");
+    big = e ? atoi(e) : 1;
+  }
+  if (big && d->dtype == BRTPE_DT_F32) {
+    const int a_vec = (d->Cin % 4 == 0 && d->in_ld % 4 == 0 && d->in_coff % 4 == 0 &&
+                       (reinterpret_cast<uintptr_t>(in) & 15) == 0) ? 1 : 0;
+    const int b_vec = (d->Cout % 4 == 0 && (reinterpret_cast<uintptr_t>(weights) & 15) == 0) ? 1 : 0;
+    if (d->Cout_store > 64) {
+      dim3 g2(ceil_div(a.M, GBM), ceil_div(d->Cout_store, 128));
+      conv_ffma_big_kernel<128><<<g2, GTHREADS, 0, st>>>(a, a_vec, b_vec);
+    } else {
+      dim3 g2(ceil_div(a.M, GBM), 1);
+      conv_ffma_big_kernel<64><<<g2, GTHREADS, 0, st>>>(a, a_vec, b_vec);
+    }
+    BRTPE_LAUNCH_CHECK();
+    return BRTPE_OK;
+  }
   dim3 grid(ceil_div(a.M, FBM), ceil_div(d->Cout_store, FBN));
   if (d->dtype == BRTPE_DT_F32)
     conv_ffma_kernel<float><<<grid, FTHREADS, 0, st>>>(a);
