@@ -14,7 +14,7 @@ from rtpe_b200 import inference  # noqa: E402
 
 def main():
     shard = int(os.environ.get("SHARD", "32"))
-    sub = int(os.environ.get("SUB", "8"))          # images per multi-scale pass (1280^2 activations are 4x)
+    sub = int(os.environ.get("SUB", "32"))         # images per multi-scale pass (1280^2 activations are 4x)
     reps = int(os.environ.get("REPS", "3"))
     torch.manual_seed(0)
     model = rtpe_b200.get_hrnet_w48_teacher(None).cuda()
