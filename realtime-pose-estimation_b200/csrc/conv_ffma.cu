@@ -265,10 +265,17 @@ __global__ void __launch_bounds__(GTHREADS, 2) conv_ffma_big_kernel(FfmaArgs a, 
         const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][g * 64 + tx * 4]);
         br[4 * g] = b4.x; br[4 * g + 1] = b4.y; br[4 * g + 2] = b4.z; br[4 * g + 3] = b4.w;
       }
+      // packed FFMA2 (two IEEE fmas per instruction, sm_100): pairs of neighbouring output channels
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i) {
+        const float2 a2 = make_float2(ar[i], ar[i]);
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        for (int j = 0; j < TN; j += 2) {
+          const float2 r = __ffma2_rn(a2, make_float2(br[j], br[j + 1]), make_float2(acc[i][j], acc[i][j + 1]));
+          acc[i][j] = r.x;
+          acc[i][j + 1] = r.y;
+        }
+      }
     }
     if (it + 1 < total) store(buf ^ 1);
     __syncthreads();
