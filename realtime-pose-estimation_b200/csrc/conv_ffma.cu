@@ -530,23 +530,22 @@ __global__ void __launch_bounds__(256) fuse_sum_bf16x8_rows_kernel(FuseArgs a) {
   for (int j = 0; j < U; ++j) {
     const int x = x0 + j * px;
     if (x >= a.W) continue;
-    float s[8];
+    float2 s[4];                              // (even, odd) channel pairs, packed FADD2 adds
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (k < a.nterms) {
         const uint32_t w[4] = {v[k][j].x, v[k][j].y, v[k][j].z, v[k][j].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
-          s[2 * e] = (k == 0) ? lo : s[2 * e] + lo;
-          s[2 * e + 1] = (k == 0) ? hi : s[2 * e + 1] + hi;
+          const float2 t = make_float2(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
+          s[e] = (k == 0) ? t : __fadd2_rn(s[e], t);
         }
       }
     }
     uint32_t o[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      float lo = s[2 * e], hi = s[2 * e + 1];
+      float lo = s[e].x, hi = s[e].y;
       if (a.relu) { lo = fmaxf(lo, 0.0f); hi = fmaxf(hi, 0.0f); }
       __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
       o[e] = *reinterpret_cast<uint32_t*>(&pk);
