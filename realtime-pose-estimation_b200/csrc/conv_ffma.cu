@@ -368,37 +368,62 @@ stem_conv1_kernel(const TI* __restrict__ img, int N, int H, int W, const float* 
 // mirrored in x -- the flip-test batch cat(x, flip(x)) without materialising it.  mode bit 2: a
 // float32 image is rounded through fp16 first, like the reference's network_to_half wrapper
 // (tofp16) does before the network sees it.
+template <typename TI> struct Pair2;
+template <> struct Pair2<float> { using type = float2; };
+template <> struct Pair2<__half> { using type = __half2; };
+__device__ __forceinline__ float2 pair_to_f32(float2 v) { return v; }
+__device__ __forceinline__ float2 pair_to_f32(__half2 v) { return __half22float2(v); }
+
+// One thread = one output pixel.  The three input columns 2*ox-1, 2*ox, 2*ox+1 of a tap row come
+// from ONE aligned 2-pixel load per thread (columns 2*ox, 2*ox+1: a warp reads 64 consecutive
+// pixels) plus the neighbouring lane's second pixel through a shuffle (column 2*ox-1); only lane 0
+// loads that pixel itself.  (The first version issued 27 scalar loads per thread at a stride of two
+// pixels between lanes.)
 template <typename TI>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 stem_im2col_kernel(const TI* __restrict__ img, int N, int H, int W, __nv_bfloat16* __restrict__ out,
                    int mode) {
+  using P2 = typename Pair2<TI>::type;
   const int Ho = H >> 1, Wo = W >> 1;
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ox >= Wo) return;
+  const bool live = ox < Wo;                  // no early return: the shuffles need whole warps
   const int row = blockIdx.y;                 // n * Ho + oy
   const int n = row / Ho, oy = row - n * Ho;
   const bool mirror = (mode & 2) && n >= (N >> 1);
   const int ns = mirror ? n - (N >> 1) : n;
   const bool via_half = (mode & 4) != 0;
+  const int lane = threadIdx.x & 31;
   float v[32];
 #pragma unroll
   for (int k = 27; k < 32; ++k) v[k] = 0.0f;
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int iy = oy * 2 + ky - 1;
+    const bool yok = iy >= 0 && iy < H;
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int ix = ox * 2 + kx - 1;
-      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
-      const int sx = mirror ? W - 1 - ix : ix;
+    for (int ci = 0; ci < 3; ++ci) {
+      const TI* __restrict__ r = img + (((size_t)ns * 3 + ci) * H + (yok ? iy : 0)) * W;
+      // columns 2*ox (c0) and 2*ox+1 (c1): source pixels (2ox, 2ox+1), mirrored (W-1-2ox, W-2-2ox)
+      float2 p = make_float2(0.0f, 0.0f);
+      if (live && yok)
+        p = pair_to_f32(*reinterpret_cast<const P2*>(r + (mirror ? W - 2 - 2 * ox : 2 * ox)));
+      const float c0 = mirror ? p.y : p.x, c1 = mirror ? p.x : p.y;
+      // column 2*ox-1 = the previous output pixel's column 2*(ox-1)+1
+      float cm = __shfl_up_sync(0xffffffffu, c1, 1);
+      if (lane == 0) {
+        const int ix = 2 * ox - 1;
+        cm = (live && yok && ix >= 0) ? to_f32(r[mirror ? W - 1 - ix : ix]) : 0.0f;
+      }
+      float t[3] = {cm, c0, c1};
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
-        float t = ok ? to_f32(img[(((size_t)ns * 3 + ci) * H + iy) * W + sx]) : 0.0f;
-        if (via_half) t = __half2float(__float2half_rn(t));
-        v[(ky * 3 + kx) * 3 + ci] = t;
+      for (int kx = 0; kx < 3; ++kx) {
+        float tv = t[kx];
+        if (via_half) tv = __half2float(__float2half_rn(tv));
+        v[(ky * 3 + kx) * 3 + ci] = tv;
       }
     }
   }
+  if (!live) return;
   uint4* o = reinterpret_cast<uint4*>(out + ((size_t)row * Wo + ox) * 32);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -717,6 +742,8 @@ int stem_im2col_launch(const void* img, int img_mode, int N, int H, int W, void*
   BRTPE_CHECK_ARG((H % 2) == 0 && (W % 2) == 0, "stem_im2col: H and W must be even");
   BRTPE_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "stem_im2col: out must be 16-byte aligned");
   BRTPE_CHECK_ARG(!(kmode & 2) || (N % 2) == 0, "stem_im2col: flip-pair mode needs an even N");
+  BRTPE_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & (img_is_half ? 3 : 7)) == 0,
+                  "stem_im2col: the image must be aligned to two pixels (8 bytes float32, 4 bytes half)");
   const int rows = N * (H / 2);
   dim3 grid(ceil_div(W / 2, 128), rows);
   if (rows > 65535) {
