@@ -1,6 +1,7 @@
-"""Context-aware-module student -- drop-in for ``rtpe.students.AttentionStudent``
-(rtpe/students.py:595-771) and its building blocks ``SELayer`` (:118-142),
-``ContextAwareModule`` (:145-201) and ``StemHRNet`` (:206-282), executed by libbrtpe.so.
+"""The students of rtpe/students.py, executed by libbrtpe.so: ``AttentionStudent`` (:595-771, BASELINE
+config 4) with its building blocks ``SELayer`` (:118-142), ``ContextAwareModule`` (:145-201) and
+``StemHRNet`` (:206-282); ``CamStudent`` (:502-592); ``SkipConv`` (:37-112) with ``RefinerStudent``
+(:302-386) and ``MultistageStudent`` (:389-499); ``AttentionStudentSteps`` (:786-1073).
 
 Module tree and parameter names are the reference's (``stem.1.conv1.weight``,
 ``att_lo.1.hdcs.3.0.weight``, ``det_top.0.bias`` ...), so ``load_state_dicts`` snapshots and
