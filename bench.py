@@ -72,7 +72,7 @@ class ClockSampler:
     # only the samples whose timestamp falls inside the timed region are used
     FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.limit")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
@@ -107,7 +107,7 @@ class ClockSampler:
             self.proc.kill()
         self.tmp.flush()
         self.tmp.seek(0)
-        sm, smax, reasons = [], [], set()
+        sm, smax, reasons, watts, wlimit, mask = [], [], set(), [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.tmp.read().splitlines():
             parts = [p.strip() for p in line.split(",")]
@@ -124,6 +124,15 @@ class ClockSampler:
             for nme, val in zip(names, parts[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(nme)
+            # context for a clock below the maximum: board power against its limit and the raw
+            # bit mask of active clock-event reasons (0x4 = sw_power_cap)
+            try:
+                watts.append(float(parts[3]))
+                if len(parts) > 9:
+                    wlimit.append(float(parts[9]))
+            except ValueError:
+                pass
+            mask.add(parts[4])
         try:
             os.unlink(self.tmp.name)
         except OSError:
@@ -132,6 +141,12 @@ class ClockSampler:
             out["sm_mhz"] = float(np.median(sm))
             out["sm_max_mhz"] = float(max(smax))
             out["samples"] = len(sm)
+        if watts:
+            out["power_w"] = float(np.median(watts))
+        if wlimit:
+            out["power_limit_w"] = float(np.median(wlimit))
+        if mask:
+            out["reason_masks"] = sorted(mask)
         out["reasons"] = sorted(reasons)
         return out
 
