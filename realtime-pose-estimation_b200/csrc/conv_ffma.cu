@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(256) fuse_sum_bf16x8_kernel(FuseArgs a) {
 // version spent ~280 instructions per 16 output bytes, most of them address arithmetic, and ran
 // at 41-58 % of the DRAM bandwidth with 62 % of the issue slots busy: gpurun_out/fuse_r01p.ncu-rep).
 // Same left-to-right fp32 summation order as the generic kernel.
-template <int U>
+template <int U, int NT>
 __global__ void __launch_bounds__(256) fuse_sum_bf16x8_rows_kernel(FuseArgs a) {
   const int px = blockDim.y;
   const int c = threadIdx.x << 3;
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(256) fuse_sum_bf16x8_rows_kernel(FuseArgs a) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     rowp[k] = nullptr;
-    if (k < a.nterms) {
+    if (k < NT) {
       const int sh = a.shifts[k];
       const int hk = a.H >> sh, wk = a.W >> sh;
       rowp[k] = reinterpret_cast<const __nv_bfloat16*>(a.terms[k]) +
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(256) fuse_sum_bf16x8_rows_kernel(FuseArgs a) {
   uint4 v[4][U];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    if (k < a.nterms) {
+    if (k < NT) {
       const int sh = a.shifts[k], ld = a.ld[k];
 #pragma unroll
       for (int j = 0; j < U; ++j) {
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(256) fuse_sum_bf16x8_rows_kernel(FuseArgs a) {
     float2 s[4];                              // (even, odd) channel pairs, packed FADD2 adds
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (k < a.nterms) {
+      if (k < NT) {
         const uint32_t w[4] = {v[k][j].x, v[k][j].y, v[k][j].z, v[k][j].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -811,9 +811,17 @@ int fuse_sum_launch(int dtype, int nterms, const void* const* terms, const int32
     // version) -> 1.33 (U = 4) -> 1.24 (U = 2); U = 8: 2.6 ms (166 registers)
     const int U = fuse_v2 == 1 ? 1 : fuse_v2 == 4 ? 4 : 2;
     dim3 grid(ceil_div(W, U * px), H, N);
-    if (U == 1) fuse_sum_bf16x8_rows_kernel<1><<<grid, block, 0, st>>>(a);
-    else if (U == 4) fuse_sum_bf16x8_rows_kernel<4><<<grid, block, 0, st>>>(a);
-    else fuse_sum_bf16x8_rows_kernel<2><<<grid, block, 0, st>>>(a);
+#define BRTPE_FUSE(UU)                                                                         \
+  switch (nterms) {                                                                            \
+    case 1: fuse_sum_bf16x8_rows_kernel<UU, 1><<<grid, block, 0, st>>>(a); break;              \
+    case 2: fuse_sum_bf16x8_rows_kernel<UU, 2><<<grid, block, 0, st>>>(a); break;              \
+    case 3: fuse_sum_bf16x8_rows_kernel<UU, 3><<<grid, block, 0, st>>>(a); break;              \
+    default: fuse_sum_bf16x8_rows_kernel<UU, 4><<<grid, block, 0, st>>>(a); break;             \
+  }
+    if (U == 1) { BRTPE_FUSE(1) }
+    else if (U == 4) { BRTPE_FUSE(4) }
+    else { BRTPE_FUSE(2) }
+#undef BRTPE_FUSE
   } else if (fast && (long long)N * H <= 65535) {
     dim3 grid(ceil_div(W * (C / 8), 256), N * H);
     fuse_sum_bf16x8_kernel<<<grid, 256, 0, st>>>(a);
