@@ -17,4 +17,5 @@ from .engine import eval_student  # noqa: F401
 from .teacher_dump import TeacherDumpWriter, TeacherDumper, load_teacher_data, \
     HEATMAPS_ORDER  # noqa: F401
 from . import preprocess  # noqa: F401
+from . import coco_results  # noqa: F401
 from ._lib import BrtpeError, LIB_PATH  # noqa: F401
