@@ -2,6 +2,7 @@
 list, FLOP count, arena packing) without launching anything."""
 import ctypes as C
 
+import pytest
 import torch
 
 import rtpe_b200
@@ -52,3 +53,19 @@ def test_invalid_configurations_raise():
         rtpe_b200.PoseHigherResolutionNet(s2_block_type="BOTTLENECK")
     with pytest.raises(ValueError):
         rtpe_b200.HeatmapParser(17, 30, 0.1, 1.0, True, False, munkres_start_rule="nope")
+
+
+def test_eval_student_prediction_selection():
+    """rtpe/engine.py:41 expects one tensor from ``model(img, out_hw)``; the drop-in students return a
+    tensor (RefinerStudent), a list of stage outputs (CamStudent / MultistageStudent: last stage) or
+    ``(att, det)`` (attention students: det)."""
+    import torch
+    from rtpe_b200.engine import _student_prediction
+    a, b = torch.zeros(1, 18, 4, 4), torch.ones(1, 18, 4, 4)
+    img = torch.zeros(1, 3, 16, 16)
+    assert _student_prediction(lambda x, hw: b, img, (16, 16)) is b
+    assert _student_prediction(lambda x, hw: [a, b], img, (16, 16)) is b
+    assert _student_prediction(lambda x, hw: (a, b), img, (16, 16)) is b
+    with pytest.raises(NotImplementedError):
+        from rtpe_b200 import eval_student
+        eval_student(torch.nn.Identity(), None, [], "cpu", plot_every=1)
