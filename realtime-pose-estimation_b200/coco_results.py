@@ -52,25 +52,14 @@ def build_keypoint_results(preds, scores, image_ids, dataset_with_center=False,
                                               "tags": kpt[:, 3], "image": int(image_ids[idx]),
                                               "area": area})
     results = []
-    for img in kpts.keys():
-        img_kpts = kpts[img]
-        if len(img_kpts) == 0:
-            continue
-        _key_points = np.array([p["keypoints"] for p in img_kpts])
-        key_points = np.zeros((_key_points.shape[0], NUM_JOINTS * 3), dtype=float)
-        for ipt in range(NUM_JOINTS):
-            key_points[:, ipt * 3 + 0] = _key_points[:, ipt, 0]
-            key_points[:, ipt * 3 + 1] = _key_points[:, ipt, 1]
-            key_points[:, ipt * 3 + 2] = _key_points[:, ipt, 2]
-        for k in range(len(img_kpts)):
-            kpt = key_points[k].reshape((NUM_JOINTS, 3))
-            left_top = np.amin(kpt, axis=0)
-            right_bottom = np.amax(kpt, axis=0)
-            w = right_bottom[0] - left_top[0]
-            h = right_bottom[1] - left_top[1]
-            results.append({"image_id": img_kpts[k]["image"], "category_id": category_id,
-                            "keypoints": list(key_points[k]), "score": img_kpts[k]["score"],
-                            "bbox": list([left_top[0], left_top[1], w, h])})
+    for people in kpts.values():                       # images in first-seen order, every detection kept
+        kp = np.stack([p["keypoints"] for p in people]).astype(np.float64)      # (P, 17, 3)
+        lo, hi = kp.min(axis=1), kp.max(axis=1)                                 # tight keypoint box
+        flat = kp.reshape(len(people), NUM_JOINTS * 3)
+        for k, p in enumerate(people):
+            results.append({"image_id": p["image"], "category_id": category_id,
+                            "keypoints": list(flat[k]), "score": p["score"],
+                            "bbox": [lo[k, 0], lo[k, 1], hi[k, 0] - lo[k, 0], hi[k, 1] - lo[k, 1]]})
     return results
 
 
