@@ -308,6 +308,129 @@ __global__ void __launch_bounds__(GTHREADS, 2) conv_ffma_big_kernel(FfmaArgs a, 
   }
 }
 
+
+// Thin layers (Cout_store <= 16: the students' 12-channel dilation branches, 1- and 17/18-channel
+// heads take 81-98 % padding in a 64-channel tile): 256 pixels x 16 output channels per CTA, 4 x 4
+// outputs per thread, otherwise the scheme of conv_ffma_big_kernel (double-buffered K chunks, same
+// accumulation order, bit-identical results).
+constexpr int HBM_ = 256;
+__global__ void __launch_bounds__(GTHREADS, 2) conv_ffma_thin_kernel(FfmaArgs a, int a_vec) {
+  __shared__ __align__(16) float As[2][GBK][HBM_ + 4];
+  __shared__ __align__(16) float Bs[2][GBK][16 + 4];
+  __shared__ int s_pix_n[HBM_], s_pix_y[HBM_], s_pix_x[HBM_];
+
+  const brtpe_conv_desc& d = a.d;
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * HBM_;
+  const float* __restrict__ in = reinterpret_cast<const float*>(a.in);
+  {
+    const int m = m0 + tid;
+    if (m < a.M) {
+      const int hw = d.Hm * d.Wm;
+      const int n = m / hw;
+      const int r = m - n * hw;
+      s_pix_n[tid] = n;
+      s_pix_y[tid] = r / d.Wm;
+      s_pix_x[tid] = r - (r / d.Wm) * d.Wm;
+    } else {
+      s_pix_n[tid] = -1;
+      s_pix_y[tid] = 0;
+      s_pix_x[tid] = 0;
+    }
+  }
+  __syncthreads();
+
+  const int tx = tid & 3;                     // output channels tx*4 + (0..3)
+  const int ty = tid >> 2;                    // pixels ty*4 + (0..3)
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  // A loader: thread -> pixel tid, all 16 channels of the chunk; B loader: (k = tid / 16, co = tid % 16)
+  const int pn = s_pix_n[tid];
+  const int py = s_pix_y[tid] * d.in_stride, px = s_pix_x[tid] * d.in_stride;
+  const int b_k = tid >> 4, b_c = tid & 15;
+  const int kchunks = (d.Cin + GBK - 1) / GBK;
+  const int total = d.ntaps * kchunks;
+  float av[16], bv;
+
+  auto load = [&](int it) {
+    const int tap = it / kchunks;
+    const int c0 = (it - tap * kchunks) * GBK;
+    const int iy = py + d.tap_dy[tap], ix = px + d.tap_dx[tap];
+    const bool pvalid = (pn >= 0) && iy >= 0 && iy < d.Hin && ix >= 0 && ix < d.Win;
+    const float* __restrict__ prow =
+        in + (((size_t)(pn < 0 ? 0 : pn) * d.Hin + (pvalid ? iy : 0)) * d.Win + (pvalid ? ix : 0)) *
+                 (size_t)d.in_ld + d.in_coff;
+    if (a_vec) {
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pvalid && c0 + 4 * h < d.Cin) v = __ldg(reinterpret_cast<const float4*>(prow + c0 + 4 * h));
+        av[4 * h] = v.x; av[4 * h + 1] = v.y; av[4 * h + 2] = v.z; av[4 * h + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) av[e] = (pvalid && c0 + e < d.Cin) ? __ldg(prow + c0 + e) : 0.0f;
+    }
+    const int cb = c0 + b_k;
+    bv = (cb < d.Cin && b_c < d.Cout) ? __ldg(a.w + ((size_t)tap * d.Cin + cb) * d.Cout + b_c) : 0.0f;
+  };
+  auto store = [&](int buf) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) As[buf][e][tid] = av[e];
+    Bs[buf][b_k][b_c] = bv;
+  };
+
+  load(0);
+  store(0);
+  __syncthreads();
+  for (int it = 0; it < total; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < total) load(it + 1);
+#pragma unroll
+    for (int k = 0; k < GBK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float ar[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float br[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    if (it + 1 < total) store(buf ^ 1);
+    __syncthreads();
+  }
+
+  float* __restrict__ out = reinterpret_cast<float*>(a.out);
+  const float* __restrict__ res = reinterpret_cast<const float*>(a.res);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pl = ty * 4 + i;
+    const int qn = s_pix_n[pl];
+    if (qn < 0) continue;
+    const int oy = s_pix_y[pl] * d.out_scale + d.out_oy;
+    const int ox = s_pix_x[pl] * d.out_scale + d.out_ox;
+    const size_t opix = ((size_t)qn * d.Hout + oy) * d.Wout + ox;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = tx * 4 + j;
+      if (co >= d.Cout_store) continue;
+      float v = 0.0f;
+      if (co < d.Cout) {
+        v = acc[i][j];
+        if (a.bias) v += __ldg(a.bias + co);
+        if (res) v += res[opix * d.res_ld + d.res_coff + co];
+        if (d.relu) v = fmaxf(v, 0.0f);
+      }
+      out[opix * d.out_ld + d.out_coff + co] = v;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // stem conv1: NCHW float/half image -> 3x3 s2 p1 conv (3 -> Cout) + bias + ReLU -> NHWC
 // ------------------------------------------------------------------------------------------
@@ -690,7 +813,9 @@ int conv_ffma_launch(const brtpe_conv_desc* d, const void* in, const void* weigh
     const int a_vec = (d->Cin % 4 == 0 && d->in_ld % 4 == 0 && d->in_coff % 4 == 0 &&
                        (reinterpret_cast<uintptr_t>(in) & 15) == 0) ? 1 : 0;
     const int b_vec = (d->Cout % 4 == 0 && (reinterpret_cast<uintptr_t>(weights) & 15) == 0) ? 1 : 0;
-    if (d->Cout_store > 64) {
+    if (d->Cout_store <= 16 && big != 2) {
+      conv_ffma_thin_kernel<<<ceil_div(a.M, HBM_), GTHREADS, 0, st>>>(a, a_vec);
+    } else if (d->Cout_store > 64) {
       dim3 g2(ceil_div(a.M, GBM), ceil_div(d->Cout_store, 128));
       conv_ffma_big_kernel<128><<<g2, GTHREADS, 0, st>>>(a, a_vec, b_vec);
     } else {

@@ -41,6 +41,24 @@ def test_ffma_fp32(cuda_device, shape):
     assert _err(got, ref) <= 1e-5
 
 
+THIN_SHAPES = [
+    # Cout <= 16: conv_ffma_thin_kernel (256 pixels x 16 channels per CTA) in fp32 mode
+    (2, 32, 40, 48, 12, 3, 1, True, False),
+    (1, 24, 24, 51, 16, 3, 1, True, True),      # Cin not a multiple of 4: scalar loads
+    (3, 17, 23, 48, 1, 3, 1, False, False),
+    (2, 16, 16, 96, 8, 1, 1, True, False),
+    (1, 32, 32, 64, 16, 3, 2, True, False),
+]
+
+
+@pytest.mark.parametrize("shape", THIN_SHAPES)
+def test_ffma_fp32_thin_layers(cuda_device, shape):
+    got, ref, eng = run_conv(L.ENGINE_FFMA, "fp32", *shape)
+    assert eng == L.ENGINE_FFMA
+    assert torch.isfinite(got).all()
+    assert _err(got, ref) <= 1e-5
+
+
 @pytest.mark.parametrize("shape", SHAPES)
 def test_ffma_bf16(cuda_device, shape):
     got, ref, eng = run_conv(L.ENGINE_FFMA, "bf16", *shape)
