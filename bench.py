@@ -152,30 +152,93 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-# CPU implementation of the path (the oracle port; the reference is pure Python/torch-CPU and
-# /root/reference does not exist on the GPU box)
+# CPU implementation of the path.  When the UNMODIFIED reference is importable ($RTPE_REF,
+# /root/reference in the build container, or baseline/_ref -- the copy __graft_entry__.build()
+# installs, which travels to the GPU box) its own PoseHigherResolutionNet and HeatmapParser are
+# timed ("kind": "reference"); otherwise the oracle port ("kind": "port").  The flip-test
+# aggregation is upstream HigherHRNet code that the reference imports but does not vendor
+# (legacy/valid_ae_avg.py:32-33): both kinds use its restatement oracle/aggregate_ref.py, and
+# ``munkres`` (un-vendored, absent) is oracle/munkres_ref.py in both.
 # ------------------------------------------------------------------------------------------
 class CpuPath:
-    def __init__(self, size):
+    def __init__(self, size, mode="auto"):
         import rtpe_b200
         from oracle import group_ref as G
+        from oracle import ref_loader
         from oracle.aggregate_ref import aggregate_flip_multiscale_ref
         from oracle.hhrnet_ref import hhrnet_forward_ref
-        self.G, self.agg, self.fwd = G, aggregate_flip_multiscale_ref, hhrnet_forward_ref
+        self.G, self.agg = G, aggregate_flip_multiscale_ref
         self.cores = os.cpu_count() or 1
         torch.set_num_threads(self.cores)
-        torch.manual_seed(0)
-        self.sd = rtpe_b200.PoseHigherResolutionNet().state_dict()   # default init, seed 0
         self.params = G.DecodeParams(**PARSER_KW)
         self.size = size
+        self.kind = "port"
+        use_ref = mode in ("auto", "reference") and ref_loader.reference_available()
+        if use_ref:
+            ref_group, ref_model = ref_loader.load_reference()
+            torch.manual_seed(0)
+            self.net = ref_model.PoseHigherResolutionNet().eval()   # default init, seed 0
+            self.parser = ref_group.HeatmapParser(**PARSER_KW)
+            self.kind = "reference"
+            self.ref_root = ref_loader.REF_ROOT
+        else:
+            torch.manual_seed(0)
+            self.sd = rtpe_b200.PoseHigherResolutionNet().state_dict()   # default init, seed 0
+            self.fwd = hhrnet_forward_ref
+
+    def describe(self):
+        if self.kind == "reference":
+            return ("the UNMODIFIED reference (rtpe.third_party.pose_higher_hrnet + group.HeatmapParser "
+                    "from %s) on the CPU; flip aggregation = oracle restatement of the un-vendored "
+                    "upstream code, munkres = oracle/munkres_ref.py" % self.ref_root)
+        return "oracle port of the reference's per-image loop (no reference tree found)"
 
     @torch.no_grad()
-    def one_image(self, x1):
+    def forward(self, x1):
+        if self.kind == "reference":
+            return [t.float() for t in self.net(x1)]
+        return self.fwd(self.sd, x1)
+
+    def decode(self, det, tag):
+        """-> (people (P,J,3+T) float32, scores float32[P]) of one image."""
+        if self.kind == "reference":
+            grouped, scores = self.parser.parse(det, tag, adjust=True, refine=True)
+            return np.asarray(grouped[0], np.float32), np.asarray(scores, np.float32)
+        people, scores = self.G.parse_image_ref(det.numpy(), tag.numpy(), self.params, True, True)
+        return np.asarray(people, np.float32), np.asarray(scores, np.float32)
+
+    @torch.no_grad()
+    def one_image(self, x1, keep=False):
         """the reference's per-image loop body: 2 forwards (flip test), aggregation, parse."""
-        y = self.fwd(self.sd, x1)
-        yf = self.fwd(self.sd, torch.flip(x1, [3]))
+        y = self.forward(x1)
+        yf = self.forward(torch.flip(x1, [3]))
         det, tag = self.agg([(1.0, y, yf)], (self.size, self.size))
-        return self.G.parse_image_ref(det.numpy(), tag.numpy(), self.params, True, True)
+        people, scores = self.decode(det, tag)
+        if keep:
+            return {"y": y, "yf": yf, "det": det, "tag": tag, "people": people, "scores": scores}
+        return people, scores
+
+
+def parity_check(cpu, ref, gpu, tol):
+    """One image of the timed batch, GPU path against the CPU leg: network outputs and aggregated
+    maps within ``tol`` (max|d| / max|ref| per tensor), and the GPU decode of the DEVICE maps
+    bit-exact against the oracle decode of the same maps."""
+    def rel(got, want):
+        return float((got.double().cpu() - want.double()).abs().max() / want.double().abs().max())
+    out = {"image": 0, "tolerance": tol, "against": cpu.kind}
+    errs = {"y0": rel(gpu["y0"], ref["y"][0]), "y1": rel(gpu["y1"], ref["y"][1]),
+            "y0_flip": rel(gpu["y0f"], ref["yf"][0]), "y1_flip": rel(gpu["y1f"], ref["yf"][1]),
+            "det": rel(gpu["det"], ref["det"]), "tag": rel(gpu["tag"], ref["tag"])}
+    out["max_rel_err"] = errs
+    out["float_ok"] = bool(all(v <= tol for v in errs.values()))
+    wp, ws = cpu.G.parse_image_ref(gpu["det"].cpu().numpy().copy(), gpu["tag"].cpu().numpy().copy(),
+                                   cpu.params, True, True)
+    wp = np.asarray(wp, np.float32)
+    out["decode_bit_exact"] = bool(gpu["people"].shape == wp.shape and np.array_equal(gpu["people"], wp)
+                                   and np.array_equal(gpu["scores"], np.asarray(ws, np.float32)))
+    out["people"] = int(wp.shape[0]) if wp.ndim == 3 else 0
+    out["people_cpu_leg"] = int(ref["people"].shape[0]) if ref["people"].ndim == 3 else 0
+    return out
 
 
 def run_reference_arm(args, rank):
@@ -199,8 +262,9 @@ def run_reference_arm(args, rank):
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cpu.cores, "kind": "port",
-                         "torch_threads": torch.get_num_threads(), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cpu.cores, "kind": cpu.kind,
+                         "torch_threads": torch.get_num_threads(), "sample": sample,
+                         "what": cpu.describe()},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -418,18 +482,29 @@ def run_ours(args, rank, world, local_rank):
     n_chunks = -(-2 * args.batch // args.chunk)
     gpu_launches = (n_chunks * plan_ops + 1 + 9) * args.steps
 
-    cpu_baseline = None
+    cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = CpuPath(args.size)
-        xs = make_input(1, args.size)
+        xs = x_host[:1].clone()                       # image 0 of the timed batch
         t0 = time.perf_counter()
-        cpu.one_image(xs)
+        ref = cpu.one_image(xs, keep=True)
         dt = time.perf_counter() - t0
-        cpu_baseline = {"value": 1.0 / dt, "unit": "images/s", "cores": cpu.cores, "kind": "port",
+        cpu_baseline = {"value": 1.0 / dt, "unit": "images/s", "cores": cpu.cores, "kind": cpu.kind,
                         "torch_threads": torch.get_num_threads(), "seconds": dt,
-                        "sample": "1 image of the batch: 2 fp32 CPU forwards (flip test) + "
-                                  "aggregation + parse(adjust, refine), oracle port of the "
-                                  "reference's per-image loop"}
+                        "sample": "image 0 of the timed batch: 2 fp32 CPU forwards (flip test) + "
+                                  "aggregation + parse(adjust, refine)", "what": cpu.describe()}
+        # the same image through the GPU path, exactly as the timed step runs it (whole batch)
+        nimg = x_dev.shape[0]
+        with torch.no_grad():
+            gy0, gy1 = pipe._forward_flip(x_dev)
+            gpu = {"y0": gy0[0:1].clone(), "y1": gy1[0:1].clone(), "y0f": gy0[nimg:nimg + 1].clone(),
+                   "y1f": gy1[nimg:nimg + 1].clone()}
+            gdet, gtag = pipe.forward_aggregate(x_dev)
+            gans, gcount, gscores = parser.decode_device(gdet, gtag, True, True)
+        c0 = int(gcount[0])
+        gpu.update(det=gdet[0:1], tag=gtag[0:1], people=gans[0, :c0].cpu().numpy(),
+                   scores=gscores[0, :c0].cpu().numpy())
+        parity = parity_check(cpu, ref, gpu, 2e-2 if args.mode == "bf16" else 1e-4)
 
     if rank == 0:
         h2d = x_host.numel() * x_host.element_size()
@@ -444,6 +519,8 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline,
             "roofline_other_convs": roofline_other,
             "roofline_decode": roofline_decode, "cpu_baseline": cpu_baseline,
+            "parity_checked": bool(parity and parity["float_ok"] and parity["decode_bit_exact"]),
+            "parity": parity,
             "forward_tflops_effective": 2 * args.batch * world * args.steps *
             FLOP_PER_FORWARD_640 * (args.size / 640.0) ** 2 / (ms_dev * 1e-3) / 1e12,
             "people_per_image": people_mean,

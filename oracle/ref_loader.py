@@ -1,9 +1,12 @@
-"""ORACLE helper: import the REAL reference modules in-process (this container only).
+"""ORACLE helper: import the REAL reference modules in-process.
 
-/root/reference is read-only and does not exist on the GPU box, so this is used
-solely by oracle/make_golden.py and by the CPU tests that pin the restatement
-(they skip when the tree is absent).  ``munkres`` (PyPI, un-vendored, absent here)
-is satisfied by injecting oracle/munkres_ref.py under that module name BEFORE
+Search order: ``$RTPE_REF``, ``/root/reference`` (this container; read-only, absent on the GPU
+box), ``baseline/_ref`` (a git-ignored copy of the reference's ``rtpe`` package that
+``__graft_entry__.build()`` makes when /root/reference is present, so that the reference arm
+of ``bench.py`` can time the UNMODIFIED reference on the GPU box's host cores).  Used by
+oracle/make_golden*.py, by the CPU tests that pin the restatement (they skip when no tree is
+found) and by ``bench.py``'s CPU legs.  ``munkres`` (PyPI, un-vendored, absent here) is
+satisfied by injecting oracle/munkres_ref.py under that module name BEFORE
 ``rtpe.third_party.group`` is imported (group.py:14).
 """
 from __future__ import annotations
@@ -12,11 +15,26 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("RTPE_REF", "/root/reference")
+_HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INSTALLED_REF = os.path.join(_HERE, "baseline", "_ref")
+
+
+def _has_reference(root) -> bool:
+    return bool(root) and os.path.isfile(os.path.join(root, "rtpe", "third_party", "group.py"))
+
+
+def _find_root():
+    for cand in (os.environ.get("RTPE_REF"), "/root/reference", INSTALLED_REF):
+        if _has_reference(cand):
+            return cand
+    return os.environ.get("RTPE_REF", "/root/reference")
+
+
+REF_ROOT = _find_root()
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REF_ROOT, "rtpe", "third_party", "group.py"))
+    return _has_reference(REF_ROOT)
 
 
 def load_reference():

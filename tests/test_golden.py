@@ -150,3 +150,45 @@ def test_attention_student_steps_oracle_matches_reference_fixture():
         want = torch.from_numpy(z[key])
         assert got.shape == want.shape
         assert ((got - want).abs().max() / want.abs().max()).item() <= 1e-5
+
+
+def test_config1_oracle_pipeline_matches_reference_fixture():
+    """BASELINE.json configs[0] (validate_hhrnet.py:84-105 on a bundled JPEG, default init under seed
+    0): JPEG bytes -> oracle pre-processing -> oracle forward -> in-tree aggregation -> oracle parse,
+    against what the UNMODIFIED reference produced (oracle/make_golden_config1.py).  Float maps to
+    1e-5 of the tensor max (conv algorithm choice), the decode result exactly when the maps are
+    bit-identical, else to the quarter-pixel."""
+    import io
+    import rtpe_b200
+    from PIL import Image
+    from oracle import preprocess_ref
+    from oracle.aggregate_ref import aggregate_intree_ref
+    z = np.load(os.path.join(GOLD, "config1_bundled.npz"))
+    st, stb = int(z["stride"]), int(z["stride_big"])
+    torch.manual_seed(0)
+    sd = rtpe_b200.PoseHigherResolutionNet().state_dict()
+    p = "img1_"                                    # 555 x 640 -> 640 x 768 (the smaller of the two)
+    img = np.array(Image.open(io.BytesIO(z[p + "jpeg"].tobytes())).convert("RGB"))
+    h, w = int(z[p + "hw"][0]), int(z[p + "hw"][1])
+    assert img.shape[:2] == (h, w)
+    u8, center, scale = preprocess_ref.resize_align_multi_scale(img, 640, 1, 1)
+    t = torch.from_numpy(preprocess_ref.to_tensor_normalize(u8))[None]
+    assert tuple(t.shape) == tuple(int(v) for v in z[p + "input_shape"])
+    assert torch.equal(t[:, :, ::stb, ::stb], torch.from_numpy(z[p + "input_s"]))
+    with torch.no_grad():
+        y0, y1 = hhrnet_forward_ref(sd, t)
+    for got, key in ((y0, "y0"), (y1, "y1")):
+        want = torch.from_numpy(z[p + key + "_s"])
+        assert (got[:, :, ::st, ::st] - want).abs().max().item() <= 1e-5 * float(z[p + key + "_absmax"])
+    det, tag = aggregate_intree_ref(y0, y1, (h, w), 17)
+    exact = True
+    for got, key in ((det, "hms"), (tag[..., 0], "aes")):
+        want = torch.from_numpy(z[p + key + "_s"])
+        assert (got[:, :, ::stb, ::stb] - want).abs().max().item() <= 1e-5 * float(z[p + key + "_absmax"])
+        exact = exact and torch.equal(got[:, :, ::stb, ::stb], want)
+    people, scores = G.parse_image_ref(det.numpy(), tag.numpy(), G.DecodeParams(), True, True)
+    people = np.asarray(people, np.float32)
+    assert people.shape == z[p + "people"].shape
+    if exact:
+        assert np.array_equal(people, z[p + "people"])
+        assert np.array_equal(np.asarray(scores, np.float32), z[p + "scores"])
