@@ -199,6 +199,39 @@ int brtpe_conv_select_engine(const brtpe_conv_desc* d);
 /* Packed-weight geometry of the tcgen05 path: bf16 [ntaps][*cout_pad][*cin_pad]. */
 int brtpe_umma_weight_dims(int Cin, int Cout_store, int* cin_pad, int* cout_pad);
 
+/* ---- weight pre-packing: eval BatchNorm folded into its convolution + engine layout, one launch
+ * per layer (pose_higher_hrnet.py conv + bn pairs, e.g. :57-64, :96-106, :202-229, :514-521;
+ * replaces nn.BatchNorm2d.forward in eval mode).  float32 arithmetic, identical to
+ *   scale = gamma / sqrt(var + eps);  w' = w * scale[co];  b' = beta - mean * scale (+ bias * scale)
+ * evaluated with separate IEEE operations. */
+enum { BRTPE_WT_F32 = 0, BRTPE_WT_BF16 = 1, BRTPE_WT_F16 = 2 };
+enum { BRTPE_PACK_CIN_COUT_F32 = 0,   /* float32 [ntaps][Cin_store][Cout_pack] (CUDA-core engine)   */
+       BRTPE_PACK_KMAJOR_BF16 = 1 };  /* bf16 [ntaps][cout_pad][cin_pad] (tcgen05 engines)           */
+typedef struct brtpe_prepack_desc {
+  int32_t w_dtype;          /* BRTPE_WT_*: storage type of w and conv_bias                       */
+  int32_t transposed;       /* 0: w (Cout, Cin, KH, KW) nn.Conv2d; 1: w (Cin, Cout, KH, KW)
+                               nn.ConvTranspose2d                                                */
+  int32_t Cout, Cin, KH, KW;
+  int32_t ntaps;            /* packed taps (<= 9)                                                */
+  int32_t tap_kh[9], tap_kw[9];   /* kernel position packed tap t takes its weights from         */
+  int32_t im2col;           /* 1 (ntaps == 1): stored input channel k = (kh*KW + kw)*Cin + c, the
+                               operand of brtpe_stem_im2col                                      */
+  int32_t Cin_store;        /* stored input channels per tap (K); channels >= Cin get zeros      */
+  int32_t layout;           /* BRTPE_PACK_*                                                      */
+  int32_t Cout_pack;        /* layout 0: row length (>= Cout; the extra columns are zero)        */
+  int32_t cin_pad, cout_pad;      /* layout 1: brtpe_umma_weight_dims                            */
+  int32_t round_bf16;       /* layout 0: values rounded to bf16 (the operand rounding of tcgen05) */
+  float bn_eps;
+} brtpe_prepack_desc;
+/* w, conv_bias (NULL: none): device, d->w_dtype.  bn_* (all NULL: no BatchNorm): device float32
+ * [Cout].  cin_index (NULL: identity): device int32 [Cin_store], module input channel carried by
+ * stored channel k, or -1 for a zero (pad) channel.  packed: device, every element is written.
+ * bias_out (may be NULL): device float32 [bias_len], entries >= Cout are zero. */
+int brtpe_prepack_weights(const brtpe_prepack_desc* d, const void* w, const void* conv_bias,
+                          const float* bn_gamma, const float* bn_beta, const float* bn_mean,
+                          const float* bn_var, const int32_t* cin_index, void* packed,
+                          float* bias_out, int bias_len, void* stream);
+
 /* Stem conv1 (pose_higher_hrnet.py:363-365,:638-640): NCHW float32/half image ->
  * 3x3 s2 conv(3->Cout) + folded BN + ReLU -> NHWC (f32 or bf16).  w: float32 [27][Cout]
  * ordered (ky, kx, cin). */

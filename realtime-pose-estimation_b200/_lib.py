@@ -50,6 +50,19 @@ class ConvDesc(C.Structure):
                 ("relu", C.c_int32), ("Cout_store", C.c_int32)]
 
 
+class PrepackDesc(C.Structure):
+    """struct brtpe_prepack_desc (include/brtpe.h)."""
+    _fields_ = [("w_dtype", C.c_int32), ("transposed", C.c_int32),
+                ("Cout", C.c_int32), ("Cin", C.c_int32), ("KH", C.c_int32), ("KW", C.c_int32),
+                ("ntaps", C.c_int32), ("tap_kh", C.c_int32 * 9), ("tap_kw", C.c_int32 * 9),
+                ("im2col", C.c_int32), ("Cin_store", C.c_int32), ("layout", C.c_int32),
+                ("Cout_pack", C.c_int32), ("cin_pad", C.c_int32), ("cout_pad", C.c_int32),
+                ("round_bf16", C.c_int32), ("bn_eps", C.c_float)]
+
+
+WT_F32, WT_BF16, WT_F16 = 0, 1, 2
+PACK_CIN_COUT_F32, PACK_KMAJOR_BF16 = 0, 1
+
 _lib = None
 
 _P = C.c_void_p
@@ -77,6 +90,7 @@ _SIGS = {
     "brtpe_conv_run": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
     "brtpe_conv_select_engine": (_I, [C.POINTER(ConvDesc)]),
     "brtpe_umma_weight_dims": (_I, [_I, _I, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "brtpe_prepack_weights": (_I, [C.POINTER(PrepackDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "brtpe_stem_conv1": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P]),
     "brtpe_fuse_sum": (_I, [_I, _I, C.POINTER(_P), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                             _I, _I, _I, _I, _P, _I, _I, _P]),

@@ -201,46 +201,76 @@ class _Recorder:
         self.op_lane.append(self.lane)
         self.op_rw.append(([t for t in reads if t is not None], list(writes), group))
 
-    # -- weights
-    def _fold(self, conv, bn):
-        """-> (w (Cout,Cin,kh,kw) f32, bias (Cout,) f32) with eval BN folded in."""
-        w = conv.weight.detach().to(self.device, torch.float32)
-        if bn is None:
-            b = conv.bias.detach().to(self.device, torch.float32) if conv.bias is not None \
-                else torch.zeros(w.shape[0], device=self.device)
-            return w, b
-        g = bn.weight.detach().to(self.device, torch.float32)
-        beta = bn.bias.detach().to(self.device, torch.float32)
-        mu = bn.running_mean.detach().to(self.device, torch.float32)
-        var = bn.running_var.detach().to(self.device, torch.float32)
-        scale = g / torch.sqrt(var + bn.eps)
-        w = w * scale.view(-1, 1, 1, 1)
-        b = beta - mu * scale
-        if conv.bias is not None:
-            b = b + conv.bias.detach().to(self.device, torch.float32) * scale
-        return w, b
+    # -- weights: BN fold + engine layout in ONE launch per layer (brtpe_prepack_weights)
+    _WT = {torch.float32: L.WT_F32, torch.bfloat16: L.WT_BF16, torch.float16: L.WT_F16}
 
-    def _pack(self, wt, desc, cin_store):
-        """wt: (ntaps, Cout, Cin) f32 -> packed weight tensor for the chosen engine."""
+    def _dev(self, t, dtype=None):
+        """parameter / buffer -> contiguous device tensor (no launch when it already is one)"""
+        t = t.detach()
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        if t.device != torch.device(self.device):
+            t = t.to(self.device)
+        return t.contiguous()
+
+    def _prepack(self, d, weight, transposed, bn, conv_bias, khkw, cin_store, cout_module,
+                 cin_index=None, im2col=False):
+        """Folded, packed weights + bias of one conv launch.  ``weight``: the module's weight
+        ((Cout,Cin,KH,KW), or (Cin,Cout,KH,KW) if ``transposed``); ``khkw``: kernel position of every
+        packed tap; ``cin_index``: see ``conv``.  -> (packed, bias float32 [d.Cout])."""
         lib = L.load(require_cuda=False)
-        ntaps, cout, cin = wt.shape
-        if cin_store > cin:                                   # zero weights for pad channels
-            wt = torch.cat((wt, wt.new_zeros(ntaps, cout, cin_store - cin)), dim=2)
-        eng = lib.brtpe_conv_select_engine(C.byref(desc))
+        w = self._dev(weight)
+        if w.dtype not in self._WT:
+            w = w.float()
+        pd = L.PrepackDesc()
+        pd.w_dtype = self._WT[w.dtype]
+        pd.transposed = int(bool(transposed))
+        pd.Cout = cout_module
+        pd.Cin = w.shape[0] if transposed else w.shape[1]
+        pd.KH, pd.KW = w.shape[2], w.shape[3]
+        pd.ntaps = len(khkw)
+        for i, (kh, kw) in enumerate(khkw):
+            pd.tap_kh[i], pd.tap_kw[i] = kh, kw
+        pd.im2col = int(bool(im2col))
+        pd.Cin_store = cin_store
+        pd.bn_eps = float(bn.eps) if bn is not None else 0.0
+        eng = lib.brtpe_conv_select_engine(C.byref(d)) if d is not None else L.ENGINE_FFMA
         if eng < 0:
             L.check(eng, "brtpe_conv_select_engine")
+        cout = d.Cout if d is not None else cout_module
         if eng in (L.ENGINE_UMMA, L.ENGINE_UMMA_HALO):
             cin_pad, cout_pad = C.c_int(0), C.c_int(0)
-            lib.brtpe_umma_weight_dims(cin_store, desc.Cout_store, C.byref(cin_pad),
-                                       C.byref(cout_pad))
-            packed = torch.zeros((ntaps, cout_pad.value, cin_pad.value), dtype=torch.bfloat16,
+            lib.brtpe_umma_weight_dims(cin_store, d.Cout_store, C.byref(cin_pad), C.byref(cout_pad))
+            pd.layout = L.PACK_KMAJOR_BF16
+            pd.cin_pad, pd.cout_pad = cin_pad.value, cout_pad.value
+            packed = torch.empty((pd.ntaps, cout_pad.value, cin_pad.value), dtype=torch.bfloat16,
                                  device=self.device)
-            packed[:, :cout, :cin_store] = wt.to(torch.bfloat16)
         else:
-            if self.mode == "bf16":                            # same operand rounding as tcgen05
-                wt = wt.to(torch.bfloat16).to(torch.float32)
-            packed = wt.permute(0, 2, 1).contiguous()          # (ntaps, Cin, Cout) f32
-        return packed
+            pd.layout = L.PACK_CIN_COUT_F32
+            pd.Cout_pack = cout
+            pd.round_bf16 = int(self.mode == "bf16" and d is not None)   # tcgen05's operand rounding
+            packed = torch.empty((pd.ntaps, cin_store, cout), dtype=torch.float32,
+                                 device=self.device)
+        bias = torch.empty((cout,), dtype=torch.float32, device=self.device)
+        cb = None
+        if conv_bias is not None:
+            cb = self._dev(conv_bias, w.dtype)
+        g = beta = mu = var = None
+        if bn is not None:
+            g, beta = self._dev(bn.weight, torch.float32), self._dev(bn.bias, torch.float32)
+            mu = self._dev(bn.running_mean, torch.float32)
+            var = self._dev(bn.running_var, torch.float32)
+        ci = None
+        if cin_index is not None:
+            ci = torch.as_tensor(list(cin_index), dtype=torch.int32).to(self.device)
+        with torch.cuda.device(self.device):
+            L.check(lib.brtpe_prepack_weights(
+                C.byref(pd), L.ptr(w), L.ptr(cb), L.ptr(g), L.ptr(beta), L.ptr(mu), L.ptr(var),
+                L.ptr(ci), L.ptr(packed), L.ptr(bias), cout, L.stream_ptr(self.device)),
+                "brtpe_prepack_weights")
+        # the launch is asynchronous: its inputs must outlive it
+        self.keepalive += [w, cb, g, beta, mu, var, ci]
+        return packed, bias
 
     # -- ops
     def conv(self, x, conv, bn, relu, residual=None, out=None, out_coff=0, in_coff=0,
@@ -258,51 +288,44 @@ class _Recorder:
         if out is None:
             out = self.new(x.n, ho, wo, (cout_store + 15) // 16 * 16)
         taps = [(dy * dil, dx * dil) for dy, dx in _TAPS3] if k == 3 else [(0, 0)]
-        w, b = self._fold(conv, bn)
         ktaps = _TAPS3 if k == 3 else [(0, 0)]
-        wt = torch.stack([w[:, :, dy + (k // 2), dx + (k // 2)] for dy, dx in ktaps], 0)
+        khkw = [(dy + k // 2, dx + k // 2) for dy, dx in ktaps]
         if cin_index is not None:
-            idx = torch.as_tensor(list(cin_index), dtype=torch.long, device=wt.device)
-            wt = wt[:, :, idx.clamp(min=0)] * (idx >= 0).to(wt.dtype).view(1, 1, -1)
             cin = cin_store = len(cin_index)
+        dcout = cout
         if pad_cout and cout_store % 16 == 0 and cout < cout_store and self.mode == "bf16":
             # heads with 17 / 34 real channels: zero weights + zero bias for the pad channels, so
             # that the layer is a whole number of 16-channel chunks (vectorised epilogue; the pad
             # channels were written as zeros before, too)
-            wt = torch.cat((wt, wt.new_zeros(wt.shape[0], cout_store - cout, wt.shape[2])), dim=1)
-            b = torch.cat((b, b.new_zeros(cout_store - cout)))
-            cout = cout_store
-        d = self._desc(x, in_coff, cin_store, taps, s, ho, wo, out, 1, 0, 0, cout, cout_store,
+            dcout = cout_store
+        d = self._desc(x, in_coff, cin_store, taps, s, ho, wo, out, 1, 0, 0, dcout, cout_store,
                        out_coff, residual, relu)
-        self._emit_conv(d, x, wt, b, residual, out, cin_store)
+        packed, b = self._prepack(d, conv.weight, False, bn, conv.bias, khkw, cin_store, cout,
+                                  cin_index=cin_index)
+        self._emit_conv(d, x, packed, b, residual, out)
         return out
 
     def deconv4x4s2(self, x, deconv, bn, cin_store, lanes=(0, 1, 2, 3)):
         """ConvTranspose2d(k4,s2,p1)+BN+ReLU as four output-parity 2x2 convs (independent:
         they write disjoint pixels of the output, one lane each)."""
-        cin, cout = deconv.in_channels, deconv.out_channels
+        cout = deconv.out_channels
         out = self.new(x.n, 2 * x.h, 2 * x.w, cout)
-        w = deconv.weight.detach().to(self.device, torch.float32)          # (Cin,Cout,4,4)
-        g = bn.weight.detach().to(self.device, torch.float32)
-        scale = g / torch.sqrt(bn.running_var.detach().to(self.device, torch.float32) + bn.eps)
-        b = bn.bias.detach().to(self.device, torch.float32) - \
-            bn.running_mean.detach().to(self.device, torch.float32) * scale
-        w = w * scale.view(1, -1, 1, 1)
         for a in (0, 1):
             ysel = [(0, 1), (-1, 3)] if a == 0 else [(1, 0), (0, 2)]       # (dy, kh)
             for bb in (0, 1):
                 xsel = [(0, 1), (-1, 3)] if bb == 0 else [(1, 0), (0, 2)]
-                taps, mats = [], []
+                taps, khkw = [], []
                 for dy, kh in ysel:
                     for dx, kw in xsel:
                         taps.append((dy, dx))
-                        mats.append(w[:, :, kh, kw].t())                   # (Cout, Cin)
-                wt = torch.stack(mats, 0)
+                        khkw.append((kh, kw))
                 d = self._desc(x, 0, cin_store, taps, 1, x.h, x.w, out, 2, a, bb, cout, cout, 0,
                                None, True)
+                packed, b = self._prepack(d, deconv.weight, True, bn, deconv.bias, khkw, cin_store,
+                                          cout)
                 keep = self.lane
                 self.lane = lanes[(2 * a + bb) % len(lanes)]
-                self._emit_conv(d, x, wt, b, None, out, cin_store, group=("deconv", id(out)))
+                self._emit_conv(d, x, packed, b, None, out, group=("deconv", id(out)))
                 self.lane = keep
         return out
 
@@ -326,9 +349,7 @@ class _Recorder:
         d.Cout_store = cout_store
         return d
 
-    def _emit_conv(self, d, x, wt, bias, residual, out, cin_store, group=None):
-        packed = self._pack(wt, d, cin_store)
-        bias = bias.contiguous()
+    def _emit_conv(self, d, x, packed, bias, residual, out, group=None):
         self.keepalive += [packed, bias]
         idx = len(self.ops)
         self.ops.append(("conv", d, x, packed, bias, residual, out))
@@ -339,12 +360,15 @@ class _Recorder:
         self._touch(out, idx)
 
     def stem(self, conv, bn):
-        w, b = self._fold(conv, bn)                                        # (64,3,3,3)
-        wp = w.permute(2, 3, 1, 0).reshape(27, w.shape[0]).contiguous()    # (ky,kx,ci) x Cout
-        out = self.new(self.n, self.h // 2, self.w // 2, w.shape[0])
+        cout = conv.out_channels                                           # (64,3,3,3)
+        # (ky,kx,ci) x Cout float32: the im2col ordering with one 27-channel "tap"
+        wp, b = self._prepack(None, conv.weight, False, bn, conv.bias, [(0, 0)], 27, cout,
+                              im2col=True)
+        wp = wp.view(27, cout)
+        out = self.new(self.n, self.h // 2, self.w // 2, cout)
         self.keepalive += [wp, b]
         idx = len(self.ops)
-        self.ops.append(("stem", wp, b.contiguous(), out))
+        self.ops.append(("stem", wp, b, out))
         self._sched([], [out])
         self._touch(out, idx)
         return out
@@ -352,19 +376,18 @@ class _Recorder:
     def stem_tc(self, conv, bn):
         """conv1 + BN + ReLU on the tensor cores: im2col (27 -> 32 channels per output pixel)
         followed by a 1x1 tcgen05 conv with K = 32."""
-        w, b = self._fold(conv, bn)                                        # (64,3,3,3)
-        cout = w.shape[0]
+        cout = conv.out_channels
         cols = self.new(self.n, self.h // 2, self.w // 2, 32)
         idx = len(self.ops)
         self.ops.append(("im2col", cols))
         self._sched([], [cols])
         self._touch(cols, idx)
-        wt = w.new_zeros((1, cout, 32))
-        wt[0, :, :27] = w.permute(0, 2, 3, 1).reshape(cout, 27)            # k = (ky, kx, ci)
         out = self.new(self.n, self.h // 2, self.w // 2, cout)
         d = self._desc(cols, 0, 32, [(0, 0)], 1, cols.h, cols.w, out, 1, 0, 0, cout, cout, 0,
                        None, True)
-        self._emit_conv(d, cols, wt, b, None, out, 32)
+        packed, b = self._prepack(d, conv.weight, False, bn, conv.bias, [(0, 0)], 32, cout,
+                                  im2col=True)                             # k = (ky, kx, ci)
+        self._emit_conv(d, cols, packed, b, None, out)
         return out
 
     def fuse(self, terms, shifts, c, relu, out=None):
