@@ -154,7 +154,13 @@ int brtpe_aggregate_scale(const float* y0, const float* y1, const float* y0f, co
  * Convolution engine: PoseHigherResolutionNet.forward (pose_higher_hrnet.py:637-686)
  * ---------------------------------------------------------------------------------- */
 
-enum { BRTPE_DT_F32 = 0, BRTPE_DT_BF16 = 1 };
+/* BRTPE_DT_BF16X2 ("split fp32", the float32 mode of the tcgen05 engines): every activation value v
+ * is stored as TWO bf16 numbers hi = bf16(v), lo = bf16(v - hi) (16 significant bits together).  A
+ * pixel of stride ld bf16 elements holds the hi parts in channels [0, ld/2) and the lo parts in
+ * [ld/2, ld): all channel offsets / counts of a descriptor index the hi half, the lo part of channel
+ * c sits at c + ld/2.  Convolutions accumulate hi*w_hi + lo*w_hi + hi*w_lo in float32 (three bf16
+ * MMAs per product, relative error ~1e-5 against float32: fp32 mode <= 1e-4). */
+enum { BRTPE_DT_F32 = 0, BRTPE_DT_BF16 = 1, BRTPE_DT_BF16X2 = 2 };
 /* FFMA: CUDA-core fp32-accurate path.  UMMA: tcgen05, one TMA box per tap (any tap table).
  * UMMA_HALO: tcgen05, 3x3/stride-1 only, one halo tile per channel block + cluster-multicast
  * weights.  AUTO picks HALO, then UMMA, then FFMA, by what the layer allows. */
@@ -222,6 +228,9 @@ typedef struct brtpe_prepack_desc {
   int32_t cin_pad, cout_pad;      /* layout 1: brtpe_umma_weight_dims                            */
   int32_t round_bf16;       /* layout 0: values rounded to bf16 (the operand rounding of tcgen05) */
   float bn_eps;
+  int32_t split;            /* layout 1, BRTPE_DT_BF16X2 layers: K = three segments of
+                               roundup(Cin_store, 64) channels [w_hi | w_hi | w_lo] (cin_pad = 3x),
+                               w_hi = bf16(w'), w_lo = bf16(w' - w_hi)                            */
 } brtpe_prepack_desc;
 /* w, conv_bias (NULL: none): device, d->w_dtype.  bn_* (all NULL: no BatchNorm): device float32
  * [Cout].  cin_index (NULL: identity): device int32 [Cin_store], module input channel carried by

@@ -19,7 +19,7 @@ MAX_TOPK = 64
 MAX_GROUP_K = 32
 MAX_JOINTS = 32
 
-DT_F32, DT_BF16 = 0, 1
+DT_F32, DT_BF16, DT_BF16X2 = 0, 1, 2
 ENGINE_AUTO, ENGINE_FFMA, ENGINE_UMMA, ENGINE_UMMA_HALO = 0, 1, 2, 3
 
 
@@ -57,7 +57,7 @@ class PrepackDesc(C.Structure):
                 ("ntaps", C.c_int32), ("tap_kh", C.c_int32 * 9), ("tap_kw", C.c_int32 * 9),
                 ("im2col", C.c_int32), ("Cin_store", C.c_int32), ("layout", C.c_int32),
                 ("Cout_pack", C.c_int32), ("cin_pad", C.c_int32), ("cout_pad", C.c_int32),
-                ("round_bf16", C.c_int32), ("bn_eps", C.c_float)]
+                ("round_bf16", C.c_int32), ("bn_eps", C.c_float), ("split", C.c_int32)]
 
 
 WT_F32, WT_BF16, WT_F16 = 0, 1, 2

@@ -26,6 +26,8 @@ struct EpiParams {
   int out_ld, out_coff, res_ld, res_coff, Cout, Cout_store, relu;
   int vec32;                      // 1: every 16-channel chunk is 32-byte aligned in out and res
   int fast;                       // 1: vec32 and Cout == Cout_store is a multiple of 16
+  int split;                      // 1: BRTPE_DT_BF16X2 activations (hi / lo bf16 pairs)
+  int out_lo, res_lo;             // split: element offset of the lo half inside a pixel (ld / 2)
 };
 
 // q = x / d for 0 <= x < 2^32 / d  (mul = floor(2^32 / d) + 1; mul == 0 selects plain division)
@@ -215,6 +217,84 @@ __device__ __forceinline__ void epi_fast(const EpiParams& e, const float* __rest
   }
 }
 
+// ---- split (BRTPE_DT_BF16X2) epilogue: the float32 result v is stored as hi = bf16(v) and
+// lo = bf16(v - hi); the residual is read back as hi + lo (exact in float32).
+template <bool RES, bool RELU, int OFF>
+__device__ __forceinline__ void epi_split_chunk(const uint32_t (&a)[32], uint32_t bias16_smem,
+                                                const Chunk32& rh, const Chunk32& rl,
+                                                __nv_bfloat16* op_hi, __nv_bfloat16* op_lo) {
+  Chunk32 oh, ol;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float4 b;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+        : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "r"(bias16_smem + 16u * q));
+    float v[4] = {__uint_as_float(a[OFF + 4 * q]) + b.x, __uint_as_float(a[OFF + 4 * q + 1]) + b.y,
+                  __uint_as_float(a[OFF + 4 * q + 2]) + b.z, __uint_as_float(a[OFF + 4 * q + 3]) + b.w};
+    if (RES) {
+      v[0] += bf16lo(rh.w[2 * q]) + bf16lo(rl.w[2 * q]);
+      v[1] += bf16hi(rh.w[2 * q]) + bf16hi(rl.w[2 * q]);
+      v[2] += bf16lo(rh.w[2 * q + 1]) + bf16lo(rl.w[2 * q + 1]);
+      v[3] += bf16hi(rh.w[2 * q + 1]) + bf16hi(rl.w[2 * q + 1]);
+    }
+    if (RELU) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.0f);
+    }
+    const uint32_t h0 = pack_bf16x2(v[0], v[1]), h1 = pack_bf16x2(v[2], v[3]);
+    oh.w[2 * q] = h0;
+    oh.w[2 * q + 1] = h1;
+    ol.w[2 * q] = pack_bf16x2(v[0] - bf16lo(h0), v[1] - bf16hi(h0));
+    ol.w[2 * q + 1] = pack_bf16x2(v[2] - bf16lo(h1), v[3] - bf16hi(h1));
+  }
+  st_chunk32(op_hi, oh, true);
+  st_chunk32(op_lo, ol, true);
+}
+
+template <bool RES, bool RELU>
+__device__ __forceinline__ void epi_split(const EpiParams& e, const float* __restrict__ bias_s,
+                                          uint32_t t_addr, int nchunks, int co0, bool valid,
+                                          size_t opix, uint32_t tfull_bar, uint32_t tfull_parity,
+                                          uint32_t arrive_bar, int lane) {
+  const __nv_bfloat16* rp = RES ? e.res + opix * e.res_ld + e.res_coff + co0 : nullptr;
+  __nv_bfloat16* op = e.out + opix * e.out_ld + e.out_coff + co0;
+  const uint32_t bias_u32 = smem_u32(bias_s);
+  mbar_wait(tfull_bar, tfull_parity);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < nchunks; c += 2) {
+    const bool two = c + 1 < nchunks;
+    Chunk32 rh0, rl0, rh1, rl1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rh0.w[i] = rl0.w[i] = rh1.w[i] = rl1.w[i] = 0u;
+    if (RES && valid) {
+      rh0 = ld_chunk32(rp + c * 16, true);
+      rl0 = ld_chunk32(rp + e.res_lo + c * 16, true);
+      if (two) {
+        rh1 = ld_chunk32(rp + c * 16 + 16, true);
+        rl1 = ld_chunk32(rp + e.res_lo + c * 16 + 16, true);
+      }
+    }
+    uint32_t a[32];
+    if (two) tmem_ld32(t_addr + (uint32_t)(c * 16), a);
+    else tmem_ld16_lo(t_addr + (uint32_t)(c * 16), a);
+    tmem_ld_wait();
+    if (c + 2 >= nchunks) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(arrive_bar);
+    }
+    if (valid) {
+      const uint32_t bs = bias_u32 + (uint32_t)((co0 + c * 16) * 4);
+      epi_split_chunk<RES, RELU, 0>(a, bs, rh0, rl0, op + c * 16, op + e.out_lo + c * 16);
+      if (two)
+        epi_split_chunk<RES, RELU, 16>(a, bs + 64u, rh1, rl1, op + c * 16 + 16,
+                                       op + e.out_lo + c * 16 + 16);
+    }
+  }
+}
+
 struct ResPrefetch {
   Chunk32 c[EPI_PRE];
 };
@@ -318,6 +398,21 @@ __device__ __forceinline__ void epi_tile(const EpiParams& e, const float* __rest
   }
 }
 
+// Dispatch of the split (BRTPE_DT_BF16X2) kernels: split layers always satisfy the fast-path
+// conditions (checked at prepare).
+__device__ __forceinline__ void epi_tile_split(const EpiParams& e, const float* __restrict__ bias_s,
+                                               uint32_t t_addr, int nchunks, int co0, bool valid,
+                                               size_t opix, uint32_t tfull_bar, uint32_t tfull_parity,
+                                               uint32_t arrive_bar, int lane) {
+  if (e.res != nullptr) {
+    if (e.relu) epi_split<true, true>(e, bias_s, t_addr, nchunks, co0, valid, opix, tfull_bar, tfull_parity, arrive_bar, lane);
+    else epi_split<true, false>(e, bias_s, t_addr, nchunks, co0, valid, opix, tfull_bar, tfull_parity, arrive_bar, lane);
+  } else {
+    if (e.relu) epi_split<false, true>(e, bias_s, t_addr, nchunks, co0, valid, opix, tfull_bar, tfull_parity, arrive_bar, lane);
+    else epi_split<false, false>(e, bias_s, t_addr, nchunks, co0, valid, opix, tfull_bar, tfull_parity, arrive_bar, lane);
+  }
+}
+
 static inline int epi_vec32_ok(const brtpe_conv_desc* d) {
   const bool out_ok = (d->out_ld % 16 == 0) && (d->out_coff % 16 == 0);
   const bool res_ok = (d->res_ld % 16 == 0) && (d->res_coff % 16 == 0);
@@ -325,6 +420,17 @@ static inline int epi_vec32_ok(const brtpe_conv_desc* d) {
 }
 static inline int epi_fast_ok(const brtpe_conv_desc* d) {
   return (epi_vec32_ok(d) && d->Cout % 16 == 0 && d->Cout_store == d->Cout) ? 1 : 0;
+}
+// split (BRTPE_DT_BF16X2) layers: the lo halves (offset ld / 2) must be 32-byte aligned as well
+static inline bool conv_is_split(const brtpe_conv_desc* d) { return d->dtype == BRTPE_DT_BF16X2; }
+static inline int epi_split_ok(const brtpe_conv_desc* d) {
+  return (epi_fast_ok(d) && d->out_ld % 32 == 0 && d->res_ld % 32 == 0 && d->in_ld % 32 == 0 &&
+          d->in_coff % 8 == 0) ? 1 : 0;
+}
+static inline void epi_set_split(EpiParams* e, const brtpe_conv_desc* d) {
+  e->split = conv_is_split(d) ? 1 : 0;
+  e->out_lo = d->out_ld / 2;
+  e->res_lo = d->res_ld / 2;
 }
 
 }  // namespace brtpe

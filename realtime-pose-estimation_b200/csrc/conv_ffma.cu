@@ -502,7 +502,7 @@ __device__ __forceinline__ float2 pair_to_f32(__half2 v) { return __half22float2
 // pixels) plus the neighbouring lane's second pixel through a shuffle (column 2*ox-1); only lane 0
 // loads that pixel itself.  (The first version issued 27 scalar loads per thread at a stride of two
 // pixels between lanes.)
-template <typename TI>
+template <typename TI, bool SPLIT>
 __global__ void __launch_bounds__(128)
 stem_im2col_kernel(const TI* __restrict__ img, int N, int H, int W, __nv_bfloat16* __restrict__ out,
                    int mode) {
@@ -547,16 +547,24 @@ stem_im2col_kernel(const TI* __restrict__ img, int N, int H, int W, __nv_bfloat1
     }
   }
   if (!live) return;
-  uint4* o = reinterpret_cast<uint4*>(out + ((size_t)row * Wo + ox) * 32);
+  // SPLIT (BRTPE_DT_BF16X2): 64 stored channels per pixel, hi parts in [0, 32), lo parts in [32, 64)
+  uint4* o = reinterpret_cast<uint4*>(out + ((size_t)row * Wo + ox) * (SPLIT ? 64 : 32));
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    uint32_t w[4];
+    uint32_t w[4], wl[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      __nv_bfloat162 pk = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+      const float a0 = v[q * 8 + 2 * e], a1 = v[q * 8 + 2 * e + 1];
+      __nv_bfloat162 pk = __floats2bfloat162_rn(a0, a1);
       w[e] = *reinterpret_cast<uint32_t*>(&pk);
+      if (SPLIT) {
+        __nv_bfloat162 pl = __floats2bfloat162_rn(a0 - __uint_as_float(w[e] << 16),
+                                                  a1 - __uint_as_float(w[e] & 0xffff0000u));
+        wl[e] = *reinterpret_cast<uint32_t*>(&pl);
+      }
     }
     o[q] = make_uint4(w[0], w[1], w[2], w[3]);
+    if (SPLIT) o[4 + q] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
   }
 }
 
@@ -637,6 +645,53 @@ __global__ void __launch_bounds__(256) fuse_sum_bf16x8_kernel(FuseArgs a) {
 }
 
 
+// split (BRTPE_DT_BF16X2) activations: every value is hi + lo (two bf16, the lo half ld / 2 elements
+// into the pixel); one thread = 8 channels of one output pixel, rows walked with a grid stride.
+// Same left-to-right fp32 summation order as the generic kernel.
+__global__ void __launch_bounds__(256) fuse_sum_split_kernel(FuseArgs a) {
+  const int cv = a.C >> 3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.W * cv) return;
+  const int x = i / cv, c = (i - x * cv) << 3;
+  for (int row = blockIdx.y; row < a.N * a.H; row += gridDim.y) {
+    const int n = row / a.H, y = row - n * a.H;
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < a.nterms) {
+        const int sh = a.shifts[k];
+        const int hk = a.H >> sh, wk = a.W >> sh;
+        const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(a.terms[k]) +
+                                 (((size_t)n * hk + (y >> sh)) * wk + (x >> sh)) * a.ld[k] + c;
+        const uint4 vh = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint4 vl = __ldg(reinterpret_cast<const uint4*>(p + (a.ld[k] >> 1)));
+        const uint32_t wh[4] = {vh.x, vh.y, vh.z, vh.w}, wl[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float v0 = __uint_as_float(wh[e] << 16) + __uint_as_float(wl[e] << 16);
+          const float v1 = __uint_as_float(wh[e] & 0xffff0000u) + __uint_as_float(wl[e] & 0xffff0000u);
+          s[2 * e] = (k == 0) ? v0 : s[2 * e] + v0;
+          s[2 * e + 1] = (k == 0) ? v1 : s[2 * e + 1] + v1;
+        }
+      }
+    }
+    uint32_t oh[4], ol[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v0 = s[2 * e], v1 = s[2 * e + 1];
+      if (a.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+      __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
+      oh[e] = *reinterpret_cast<uint32_t*>(&pk);
+      __nv_bfloat162 pl = __floats2bfloat162_rn(v0 - __uint_as_float(oh[e] << 16),
+                                                v1 - __uint_as_float(oh[e] & 0xffff0000u));
+      ol[e] = *reinterpret_cast<uint32_t*>(&pl);
+    }
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + ((size_t)row * a.W + x) * a.out_ld + c;
+    *reinterpret_cast<uint4*>(op) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    *reinterpret_cast<uint4*>(op + (a.out_ld >> 1)) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+  }
+}
+
 // bf16 fast path, second version: block = (C/8 channel vectors) x (PX pixels) threads, grid =
 // (pixel blocks, rows, images): no integer division, the per-term row pointers are computed once
 // per thread, U pixels per thread with all their loads issued before the first add (the first
@@ -705,7 +760,7 @@ __global__ void __launch_bounds__(256) fuse_sum_bf16x8_rows_kernel(FuseArgs a) {
 // ------------------------------------------------------------------------------------------
 // NHWC (f32 | bf16) -> NCHW (f32 | f16) network outputs
 // ------------------------------------------------------------------------------------------
-template <typename TS, typename TD>
+template <typename TS, typename TD, bool SPLIT = false>
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const TS* __restrict__ src, int N, int HW, int C, int ld, int coff,
                     TD* __restrict__ dst) {
@@ -716,7 +771,13 @@ nhwc_to_nchw_kernel(const TS* __restrict__ src, int N, int HW, int C, int ld, in
   for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
     const int pl = i / 64, cl = i % 64;
     const int p = p0 + pl, c = c0 + cl;
-    tile[pl][cl] = (p < HW && c < C) ? to_f32(src[((size_t)n * HW + p) * ld + coff + c]) : 0.0f;
+    float v = 0.0f;
+    if (p < HW && c < C) {
+      const TS* sp = src + ((size_t)n * HW + p) * ld + coff + c;
+      v = to_f32(sp[0]);
+      if (SPLIT) v += to_f32(sp[ld >> 1]);           // hi + lo of a split (bf16x2) value
+    }
+    tile[pl][cl] = v;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
@@ -771,8 +832,8 @@ nhwc_to_nchw_bf16_vec_kernel(const __nv_bfloat16* __restrict__ src, int HW, int 
 // ------------------------------------------------------------------------------------------
 int conv_validate(const brtpe_conv_desc* d) {
   BRTPE_CHECK_ARG(d != nullptr, "conv: null descriptor");
-  BRTPE_CHECK_ARG(d->dtype == BRTPE_DT_F32 || d->dtype == BRTPE_DT_BF16, "conv: bad dtype %d",
-                  d->dtype);
+  BRTPE_CHECK_ARG(d->dtype == BRTPE_DT_F32 || d->dtype == BRTPE_DT_BF16 ||
+                      d->dtype == BRTPE_DT_BF16X2, "conv: bad dtype %d", d->dtype);
   BRTPE_CHECK_ARG(d->N > 0 && d->Hin > 0 && d->Win > 0 && d->Cin > 0 && d->Cout > 0,
                   "conv: bad tensor sizes");
   BRTPE_CHECK_ARG(d->Hm > 0 && d->Wm > 0 && d->in_stride >= 1 && d->out_scale >= 1,
@@ -860,9 +921,11 @@ int stem_conv1_launch(const void* img, int img_is_half, int N, int H, int W, con
 
 int stem_im2col_launch(const void* img, int img_mode, int N, int H, int W, void* out,
                        cudaStream_t st) {
-  // img_mode: bit 0 = half input, bit 1 = flip pair, bit 2 = round float32 through fp16
+  // img_mode: bit 0 = half input, bit 1 = flip pair, bit 2 = round float32 through fp16,
+  // bit 3 = split (bf16x2) output: 64 stored channels per pixel
   const int img_is_half = img_mode & 1;
   const int kmode = img_mode & 6;
+  const bool split = (img_mode & 8) != 0;
   BRTPE_CHECK_ARG(img && out && N > 0 && H > 0 && W > 0, "stem_im2col: bad arguments");
   BRTPE_CHECK_ARG((H % 2) == 0 && (W % 2) == 0, "stem_im2col: H and W must be even");
   BRTPE_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "stem_im2col: out must be 16-byte aligned");
@@ -881,18 +944,23 @@ int stem_im2col_launch(const void* img, int img_mode, int N, int H, int W, void*
       const int nn = std::min(per, N - n0);
       int rc = stem_im2col_launch(reinterpret_cast<const char*>(img) + (size_t)n0 * 3 * H * W * isz,
                                   img_mode, nn, H, W,
-                                  reinterpret_cast<__nv_bfloat16*>(out) + (size_t)n0 * (H / 2) * (W / 2) * 32,
+                                  reinterpret_cast<__nv_bfloat16*>(out) +
+                                      (size_t)n0 * (H / 2) * (W / 2) * (split ? 64 : 32),
                                   st);
       if (rc) return rc;
     }
     return BRTPE_OK;
   }
-  if (img_is_half)
-    stem_im2col_kernel<__half><<<grid, 128, 0, st>>>(reinterpret_cast<const __half*>(img), N, H, W,
-                                                     reinterpret_cast<__nv_bfloat16*>(out), kmode & 2);
-  else
-    stem_im2col_kernel<float><<<grid, 128, 0, st>>>(reinterpret_cast<const float*>(img), N, H, W,
-                                                    reinterpret_cast<__nv_bfloat16*>(out), kmode);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (img_is_half) {
+    const __half* im = reinterpret_cast<const __half*>(img);
+    if (split) stem_im2col_kernel<__half, true><<<grid, 128, 0, st>>>(im, N, H, W, o, kmode & 2);
+    else stem_im2col_kernel<__half, false><<<grid, 128, 0, st>>>(im, N, H, W, o, kmode & 2);
+  } else {
+    const float* im = reinterpret_cast<const float*>(img);
+    if (split) stem_im2col_kernel<float, true><<<grid, 128, 0, st>>>(im, N, H, W, o, kmode);
+    else stem_im2col_kernel<float, false><<<grid, 128, 0, st>>>(im, N, H, W, o, kmode);
+  }
   BRTPE_LAUNCH_CHECK();
   return BRTPE_OK;
 }
@@ -916,6 +984,19 @@ int fuse_sum_launch(int dtype, int nterms, const void* const* terms, const int32
   }
   a.nterms = nterms; a.N = N; a.H = H; a.W = W; a.C = C; a.out_ld = out_ld; a.relu = relu;
   a.out = out;
+  if (dtype == BRTPE_DT_BF16X2) {
+    bool ok = (C % 8) == 0 && (out_ld % 16) == 0 && out_ld / 2 >= C &&
+              (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    for (int k = 0; k < nterms; ++k)
+      ok = ok && (term_ld[k] % 16) == 0 && term_ld[k] / 2 >= C &&
+           (reinterpret_cast<uintptr_t>(terms[k]) & 15) == 0;
+    BRTPE_CHECK_ARG(ok, "fuse_sum: split (bf16x2) tensors need C %% 8 == 0, strides %% 16 == 0 and "
+                        "16-byte aligned pointers");
+    dim3 grid(ceil_div(W * (C / 8), 256), std::min(N * H, 65535));
+    fuse_sum_split_kernel<<<grid, 256, 0, st>>>(a);
+    BRTPE_LAUNCH_CHECK();
+    return BRTPE_OK;
+  }
   const size_t total = (size_t)N * H * W * (C / 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
@@ -963,6 +1044,18 @@ int nhwc_to_nchw_launch(int dtype, const void* src, int N, int H, int W, int C, 
                         void* dst, int dst_is_half, cudaStream_t st) {
   BRTPE_CHECK_ARG(src && dst && N > 0 && H > 0 && W > 0 && C > 0 && ld >= coff + C,
                   "nhwc_to_nchw: bad arguments");
+  if (dtype == BRTPE_DT_BF16X2) {
+    BRTPE_CHECK_ARG((ld % 2) == 0 && ld / 2 >= coff + C, "nhwc_to_nchw: split tensor needs ld / 2 >= coff + C");
+    dim3 sgrid(ceil_div(H * W, 64), ceil_div(C, 64), N);
+    if (dst_is_half)
+      nhwc_to_nchw_kernel<__nv_bfloat16, __half, true><<<sgrid, 256, 0, st>>>(
+          reinterpret_cast<const __nv_bfloat16*>(src), N, H * W, C, ld, coff, reinterpret_cast<__half*>(dst));
+    else
+      nhwc_to_nchw_kernel<__nv_bfloat16, float, true><<<sgrid, 256, 0, st>>>(
+          reinterpret_cast<const __nv_bfloat16*>(src), N, H * W, C, ld, coff, reinterpret_cast<float*>(dst));
+    BRTPE_LAUNCH_CHECK();
+    return BRTPE_OK;
+  }
   if (dtype == BRTPE_DT_BF16 && C <= 64 && (ld % 8) == 0 && (coff % 8) == 0 && N <= 65535 &&
       (reinterpret_cast<uintptr_t>(src) & 15) == 0 && coff + ((C + 7) / 8) * 8 <= ld) {
     dim3 vgrid(ceil_div(H * W, dst_is_half ? 256 : 128), N);

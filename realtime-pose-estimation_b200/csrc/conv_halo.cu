@@ -18,7 +18,10 @@ int halo_conv_launch_cg2(const HaloConvPrepared* P, const float* bias, const voi
                          cudaStream_t st);
 
 bool halo_conv_supported(const brtpe_conv_desc* d) {
-  if (d->dtype != BRTPE_DT_BF16 || d->ntaps != 9 || d->in_stride != 1 || d->out_scale != 1) return false;
+  if ((d->dtype != BRTPE_DT_BF16 && d->dtype != BRTPE_DT_BF16X2) || d->ntaps != 9 ||
+      d->in_stride != 1 || d->out_scale != 1)
+    return false;
+  if (conv_is_split(d) && (!epi_split_ok(d) || d->in_ld / 2 < d->in_coff + d->Cin)) return false;
   if (d->out_oy || d->out_ox || d->Hm != d->Hin || d->Wm != d->Win || d->Hout != d->Hin ||
       d->Wout != d->Win)
     return false;

@@ -56,6 +56,8 @@ struct alignas(64) HaloParams {
   int N, H, W;
   int tiles_x, tiles_y, m_tiles, n_tiles, BN, num_items;
   int num_kb, last_k16, in_coff;
+  int nkb_seg, lo_off;          // split (BRTPE_DT_BF16X2): num_kb = 3 segments [hi | lo | hi] of
+                                // nkb_seg 64-channel blocks; the lo half starts lo_off channels in
   int a_stages, b_stages, b_stage_bytes;
   int tps, b_groups;            // taps per weight stage, stages per channel block (tps*b_groups = 9)
   int resident;                 // 1: all weights stay in smem for the whole kernel
@@ -289,6 +291,76 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const fl
   __syncwarp();
 }
 
+// ---- split (BRTPE_DT_BF16X2) epilogue: float32 result -> (hi, lo) bf16 pair, residual = hi + lo.
+// The MMAs of a split layer take three times as long per tile, so the plain form (residual loads
+// issued right before the TMEM read, direct 32-byte stores) stays off the critical path.
+template <bool RES, bool RELU>
+__device__ __forceinline__ void halo_epilogue_split(const HaloParams& p, const float* bias_s,
+                                                    uint32_t tmem_base, uint64_t* tfull,
+                                                    uint32_t tempty_addr, int group, int lg,
+                                                    int lane, int rank, int item0, int istep) {
+  const EpiParams& e = p.epi;
+  const int m = lg * 32 + lane;
+  const int BN = p.BN, n_tiles = p.n_tiles, num_items = p.num_items;
+  const int tile_sel = (p.tpc == 2) ? group : 0;
+  const int allchunks = BN >> 4;
+  const int cbeg = (p.tpc == 2) ? 0 : group * (allchunks >> 1);
+  const int nchunks = (p.tpc == 2) ? allchunks : cbeg + (group == 0 ? (allchunks >> 1) : allchunks - (allchunks >> 1));
+  const int acc_stages = p.acc_stages;
+  const int acc_cols = p.tpc * BN;
+  const uint32_t bias_u32 = smem_u32(bias_s);
+  constexpr bool remote = (HL_CG == 2);
+  int it = 0;
+  for (int item = item0; item < num_items; item += istep, ++it) {
+    const EpiPix px = epi_pixel(p, item, tile_sel, m, rank);
+    const int nt = item - (int)fdiv((uint32_t)item, p.fd_nt) * n_tiles;
+    const int co0 = nt * BN;
+    const __nv_bfloat16* rp = RES ? e.res + px.opix * e.res_ld + e.res_coff + co0 : nullptr;
+    __nv_bfloat16* op = e.out + px.opix * e.out_ld + e.out_coff + co0;
+    const int acc = (acc_stages == 2) ? (it & 1) : 0;
+    const uint32_t accph = (acc_stages == 2) ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
+    const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) +
+                            (uint32_t)(acc * acc_cols + tile_sel * BN);
+    mbar_wait(smem_u32(&tfull[acc]), accph);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = cbeg; c < nchunks; c += 2) {
+      const bool two = c + 1 < nchunks;
+      Chunk32 rh0, rl0, rh1, rl1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rh0.w[i] = rl0.w[i] = rh1.w[i] = rl1.w[i] = 0u;
+      if (RES && px.valid) {
+        rh0 = ld_chunk32(rp + c * 16, true);
+        rl0 = ld_chunk32(rp + e.res_lo + c * 16, true);
+        if (two) {
+          rh1 = ld_chunk32(rp + c * 16 + 16, true);
+          rl1 = ld_chunk32(rp + e.res_lo + c * 16 + 16, true);
+        }
+      }
+      uint32_t a[32];
+      if (two) tmem_ld32(t_addr + (uint32_t)(c * 16), a);
+      else tmem_ld16_lo(t_addr + (uint32_t)(c * 16), a);
+      tmem_ld_wait();
+      if (c + 2 >= nchunks) {                    // last TMEM read of this tile
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (remote) mbar_arrive_cluster(tempty_addr + 8u * acc);
+          else mbar_arrive(tempty_addr + 8u * acc);
+        }
+      }
+      if (px.valid) {
+        const uint32_t bs = bias_u32 + (uint32_t)((co0 + c * 16) * 4);
+        epi_split_chunk<RES, RELU, 0>(a, bs, rh0, rl0, op + c * 16, op + e.out_lo + c * 16);
+        if (two)
+          epi_split_chunk<RES, RELU, 16>(a, bs + 64u, rh1, rl1, op + c * 16 + 16,
+                                         op + e.out_lo + c * 16 + 16);
+      }
+    }
+  }
+}
+
+template <bool SPLIT>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
   const bool PROF = p.prof != nullptr;   // debug counters (brtpe_debug_halo_prof), warp-uniform
@@ -302,6 +374,7 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
   // hoist everything the hot loops need out of the constant bank
   const int a_stages = p.a_stages, b_stages = p.b_stages, b_stage_bytes = p.b_stage_bytes;
   const int num_kb = p.num_kb, last_k16 = p.last_k16, num_items = p.num_items;
+  const int nkb_seg = p.nkb_seg, lo_off = p.lo_off;
   const int n_tiles = p.n_tiles, BN = p.BN;
   const int tps = p.tps, b_groups = p.b_groups, acc_stages = p.acc_stages;
   const bool resident = p.resident != 0;
@@ -409,6 +482,9 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
       const int unit = (int)fdiv((uint32_t)nx_item, p.fd_nt);
       const TileOrg o0 = tile_origin(p, unit * tpi + rank * tpc);
       const TileOrg o1 = tile_origin(p, unit * tpi + rank * tpc + 1);      // unused when tpc == 1
+      // channel block nx_kb of the reduction: segment (hi, lo, hi again) and block inside it
+      const int seg = (nx_kb >= nkb_seg) + (nx_kb >= 2 * nkb_seg);
+      const int ch0 = in_coff + (nx_kb - seg * nkb_seg) * 64 + (seg == 1 ? lo_off : 0);
       if (elect_one()) {
         if (res_prefetch && nx_kb == 0) {
           // the residual tiles of this item will be read by the epilogue one to two items from
@@ -425,15 +501,13 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
           if (leader) mbar_expect_tx(fa, (uint32_t)(tpi * HL_A_BYTES));
           if (cg2) {
             const uint32_t fas = sig(&full_a[as_]);
-            tma_load_5d_cg2(dst, &p.tmap_a, fas, in_coff + nx_kb * 64, o0.x0 - 1, 0, o0.y0 - 1, o0.n);
+            tma_load_5d_cg2(dst, &p.tmap_a, fas, ch0, o0.x0 - 1, 0, o0.y0 - 1, o0.n);
             if (tpc == 2)
-              tma_load_5d_cg2(dst + HL_A_TILE, &p.tmap_a, fas, in_coff + nx_kb * 64, o1.x0 - 1, 0,
-                              o1.y0 - 1, o1.n);
+              tma_load_5d_cg2(dst + HL_A_TILE, &p.tmap_a, fas, ch0, o1.x0 - 1, 0, o1.y0 - 1, o1.n);
           } else {
-            tma_load_5d(dst, &p.tmap_a, fa, in_coff + nx_kb * 64, o0.x0 - 1, 0, o0.y0 - 1, o0.n);
+            tma_load_5d(dst, &p.tmap_a, fa, ch0, o0.x0 - 1, 0, o0.y0 - 1, o0.n);
             if (tpc == 2)
-              tma_load_5d(dst + HL_A_TILE, &p.tmap_a, fa, in_coff + nx_kb * 64, o1.x0 - 1, 0,
-                          o1.y0 - 1, o1.n);
+              tma_load_5d(dst + HL_A_TILE, &p.tmap_a, fa, ch0, o1.x0 - 1, 0, o1.y0 - 1, o1.n);
           }
         }
       }
@@ -510,7 +584,8 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
           HL_TIMED(6, mbar_wait(smem_u32(&full_a[as_]), aph));
           const uint32_t a0 = a_ring_lo + (uint32_t)as_ * a_stage_lo;
           const uint32_t a1 = a0 + a_tile_lo;
-          const int k16 = (kb == num_kb - 1) ? last_k16 : 4;
+          const int seg = (kb >= nkb_seg) + (kb >= 2 * nkb_seg);
+          const int k16 = (kb - seg * nkb_seg == nkb_seg - 1) ? last_k16 : 4;
 #pragma unroll 1
           for (int g = 0; g < b_groups; ++g) {
             uint32_t b_lo;
@@ -608,6 +683,14 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
           if (cg2) mbar_arrive_cluster(tempty_addr + 8u * acc);
           else mbar_arrive(tempty_addr + 8u * acc);
         }
+      }
+    } else if (SPLIT) {
+      if (e.res != nullptr) {
+        if (e.relu) halo_epilogue_split<true, true>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep);
+        else halo_epilogue_split<true, false>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep);
+      } else {
+        if (e.relu) halo_epilogue_split<false, true>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep);
+        else halo_epilogue_split<false, false>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep);
       }
     } else if (e.fast) {
       if (e.res != nullptr) {
@@ -792,8 +875,11 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
   }
   p.num_items = pairs * p.n_tiles;
 
-  p.num_kb = ceil_div(d->Cin, 64);
-  p.last_k16 = (d->Cin - (p.num_kb - 1) * 64) / 16;
+  const bool split = conv_is_split(d);
+  p.nkb_seg = ceil_div(d->Cin, 64);
+  p.num_kb = split ? 3 * p.nkb_seg : p.nkb_seg;
+  p.last_k16 = (d->Cin - (p.nkb_seg - 1) * 64) / 16;
+  p.lo_off = d->in_ld / 2;
   p.in_coff = d->in_coff;
   p.dbg = getenv("BRTPE_HALO_DBG") ? atoi(getenv("BRTPE_HALO_DBG")) : 0;
   if (p.tpc == 1 && (p.BN / 16) % 2 != 0) {        // the two epilogue groups split the chunks evenly
@@ -813,6 +899,7 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
   // their output through shared memory costs more than it saves there: direct 32-byte stores.
   p.tma_out = (p.BN >= 96) ? 1 : 0;
   if (getenv("BRTPE_HALO_TMA_OUT")) p.tma_out = atoi(getenv("BRTPE_HALO_TMA_OUT")) ? 1 : 0;
+  if (split) p.tma_out = 0;                         // the split epilogue stores directly
   // two output slabs per epilogue warp unless that would push resident weights out / leave the
   // weight ring with fewer than two stages
   p.out_slabs = 2;
@@ -865,6 +952,12 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
   p.epi.relu = d->relu; p.epi.vec32 = epi_vec32_ok(d);
   // the fast epilogue walks whole 16-channel chunks of real channels
   p.epi.fast = (epi_fast_ok(d) && p.n_tiles * p.BN == d->Cout) ? 1 : 0;
+  epi_set_split(&p.epi, d);
+  if (split && !p.epi.fast) {
+    set_error("halo conv: split layers need Cout = n_tiles * BN (Cout %d, %d x %d)", d->Cout, p.n_tiles, p.BN);
+    delete P;
+    return nullptr;
+  }
   if (p.tpc == 1 && !p.epi.fast) {
     set_error("halo conv: one-tile mode needs Cout = n_tiles * BN (Cout %d, %d x %d)", d->Cout, p.n_tiles, p.BN);
     delete P;
@@ -881,7 +974,7 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
 
   auto encode = halo_encode_fn();
   const cuuint64_t ld_b = (cuuint64_t)d->in_ld * 2;
-  cuuint64_t gdim[5] = {(cuuint64_t)(d->in_coff + d->Cin), (cuuint64_t)d->Win, 1,
+  cuuint64_t gdim[5] = {(cuuint64_t)(split ? d->in_ld : d->in_coff + d->Cin), (cuuint64_t)d->Win, 1,
                         (cuuint64_t)d->Hin, (cuuint64_t)d->N};
   cuuint64_t gstr[4] = {ld_b, ld_b * d->Win, ld_b * d->Win, ld_b * d->Win * d->Hin};
   cuuint32_t box[5] = {64, (cuuint32_t)HL_PITCH, 1, (cuuint32_t)(HL_TH + 2), 1};
@@ -898,6 +991,7 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
   // (when n_tiles*BN rounds up past it) are out of bounds and read as zeros
   int cin_pad = 0, cout_pad = 0;
   brtpe_umma_weight_dims(d->Cin, d->Cout_store, &cin_pad, &cout_pad);
+  if (split) cin_pad *= 3;                          // [w_hi | w_hi | w_lo] segments
   cuuint64_t wdim[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, 9};
   cuuint64_t wstr[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)cin_pad * 2 * cout_pad};
   cuuint32_t wbox[3] = {64, (cuuint32_t)(p.BN / p.cg), (cuuint32_t)p.tps};
@@ -918,7 +1012,9 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
     P->out_encoded = out;
   }
   if (!HL_NAME(g_halo_attr_set)) {
-    if (cudaFuncSetAttribute(HL_NAME(conv_halo_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(HL_NAME(conv_halo_kernel)<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             HL_SMEM_MAX) != cudaSuccess ||
+        cudaFuncSetAttribute(HL_NAME(conv_halo_kernel)<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              HL_SMEM_MAX) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(HL_NAME(conv_halo_kernel)) failed");
       delete P;
@@ -965,7 +1061,8 @@ int HL_NAME(halo_conv_launch)(const HaloConvPrepared* P, const float* bias, cons
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, HL_NAME(conv_halo_kernel), p);
+  cudaError_t e = p.epi.split ? cudaLaunchKernelEx(&cfg, HL_NAME(conv_halo_kernel)<true>, p)
+                              : cudaLaunchKernelEx(&cfg, HL_NAME(conv_halo_kernel)<false>, p);
   if (e != cudaSuccess) {
     set_error("HL_NAME(conv_halo_kernel) launch failed: %s", cudaGetErrorString(e));
     return BRTPE_ECUDA;

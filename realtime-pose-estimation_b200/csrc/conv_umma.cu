@@ -44,6 +44,8 @@ struct alignas(64) UmmaParams {
   int TW, TH, TN, tiles_x, tiles_y, tiles_n;
   int n_tiles, BN, total_tiles;
   int ntaps, num_kb, last_k16;
+  int nkb_seg, lo_off;    // split (BRTPE_DT_BF16X2): num_kb = 3 segments [hi | lo | hi] of nkb_seg
+                          // 64-channel blocks, the lo half starts lo_off channels into the pixel
   int tap_c[9], tap_x[9], tap_p[9], tap_y[9];
   int stages, b_stage_bytes, tmem_cols, acc_cols;
   uint32_t idesc;
@@ -67,12 +69,14 @@ __device__ __forceinline__ uint32_t um_desc_lo(uint32_t smem_addr) {
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
+template <bool SPLIT>
 __global__ void __launch_bounds__(UM_THREADS)
 conv_umma_kernel(const __grid_constant__ UmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int stages = p.stages, ntaps = p.ntaps, num_kb = p.num_kb, last_k16 = p.last_k16;
+  const int nkb_seg = p.nkb_seg, lo_off = p.lo_off;
   const int total_tiles = p.total_tiles, n_tiles = p.n_tiles, BN = p.BN;
   const int tiles_x = p.tiles_x, tiles_xy = p.tiles_x * p.tiles_y;
   const int TW = p.TW, TH = p.TH, TN = p.TN;
@@ -130,12 +134,15 @@ conv_umma_kernel(const __grid_constant__ UmmaParams p) {
         const int tc = p.tap_c[tap], tx = x0 + p.tap_x[tap], tp = p.tap_p[tap], ty = y0 + p.tap_y[tap];
 #pragma unroll 1
         for (int kb = 0; kb < num_kb; ++kb) {
+          // channel block kb of the reduction: segment (hi, lo, hi again) and block inside it
+          const int seg = (kb >= nkb_seg) + (kb >= 2 * nkb_seg);
+          const int coff = (kb - seg * nkb_seg) * 64 + (seg == 1 ? lo_off : 0);
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
           if (elect_one()) {
             const uint32_t fb = smem_u32(&full_bar[stage]);
             mbar_expect_tx(fb, tx_bytes);
             const uint32_t a_dst = smem_u32(smem + (size_t)stage * stage_bytes);
-            tma_load_5d(a_dst, &p.tmap_a, fb, tc + kb * 64, tx, tp, ty, n0);
+            tma_load_5d(a_dst, &p.tmap_a, fb, tc + coff, tx, tp, ty, n0);
             tma_load_3d(a_dst + UM_A_BYTES, &p.tmap_b, fb, kb * 64, nt * BN, tap);
           }
           __syncwarp();
@@ -166,7 +173,8 @@ conv_umma_kernel(const __grid_constant__ UmmaParams p) {
           tc_fence_after();
           const uint32_t a_lo = ring_lo + (uint32_t)stage * stage_lo;
           const uint32_t b_lo = a_lo + (uint32_t)(UM_A_BYTES >> 4);
-          const int k16 = (kb == num_kb - 1) ? last_k16 : 4;
+          const int seg = (kb >= nkb_seg) + (kb >= 2 * nkb_seg);
+          const int k16 = (kb - seg * nkb_seg == nkb_seg - 1) ? last_k16 : 4;
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -230,8 +238,12 @@ conv_umma_kernel(const __grid_constant__ UmmaParams p) {
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * acc_cols);
-      epi_tile(e, bias_s, t_addr, nchunks, co0, valid, opix, smem_u32(&tfull_bar[as]), aphase,
-               smem_u32(&tempty_bar[as]), lane);
+      if (SPLIT)
+        epi_tile_split(e, bias_s, t_addr, nchunks, co0, valid, opix, smem_u32(&tfull_bar[as]), aphase,
+                       smem_u32(&tempty_bar[as]), lane);
+      else
+        epi_tile(e, bias_s, t_addr, nchunks, co0, valid, opix, smem_u32(&tfull_bar[as]), aphase,
+                 smem_u32(&tempty_bar[as]), lane);
     }
   }
 
@@ -304,7 +316,12 @@ bool umma_conv_supported(const brtpe_conv_desc* d, const char** why) {
     if (why) *why = msg;
     return false;
   };
-  if (d->dtype != BRTPE_DT_BF16) return fail("tcgen05 path needs bf16 activations");
+  if (d->dtype != BRTPE_DT_BF16 && d->dtype != BRTPE_DT_BF16X2)
+    return fail("tcgen05 path needs bf16 (or split bf16x2) activations");
+  if (conv_is_split(d) && !epi_split_ok(d))
+    return fail("split (bf16x2) layers need Cout == Cout_store, a multiple of 16, and pixel strides "
+                "that are multiples of 32");
+  if (conv_is_split(d) && d->in_ld / 2 < d->in_coff + d->Cin) return fail("split: in_ld / 2 < in_coff + Cin");
   if (d->Cin % 16) return fail("Cin must be a multiple of 16");
   if (d->in_ld % 8 || d->in_coff % 8) return fail("in_ld / in_coff must be multiples of 8");
   if (d->out_ld % 8 || d->out_coff % 8) return fail("out_ld / out_coff must be multiples of 8");
@@ -357,8 +374,11 @@ UmmaConvPrepared* umma_conv_prepare(const brtpe_conv_desc* d, const void* in, co
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
 
   p.ntaps = d->ntaps;
-  p.num_kb = ceil_div(d->Cin, 64);
-  p.last_k16 = (d->Cin - (p.num_kb - 1) * 64) / 16;
+  const bool split = conv_is_split(d);
+  p.nkb_seg = ceil_div(d->Cin, 64);
+  p.num_kb = split ? 3 * p.nkb_seg : p.nkb_seg;
+  p.last_k16 = (d->Cin - (p.nkb_seg - 1) * 64) / 16;
+  p.lo_off = d->in_ld / 2;
   const int s = d->in_stride;
   for (int t = 0; t < d->ntaps; ++t) {
     const int dy = d->tap_dy[t], dx = d->tap_dx[t];
@@ -407,6 +427,13 @@ UmmaConvPrepared* umma_conv_prepare(const brtpe_conv_desc* d, const void* in, co
   // the fast epilogue walks whole 16-channel chunks of every Cout tile without a bound check: only
   // for tilings that cover the channels exactly (176 = 2 x 96 would write 16 channels too many)
   p.epi.fast = (epi_fast_ok(d) && p.n_tiles * p.BN == d->Cout) ? 1 : 0;
+  epi_set_split(&p.epi, d);
+  if (split && !p.epi.fast) {
+    set_error("tcgen05 conv: split layers need a Cout tiling that covers the channels exactly "
+              "(Cout %d, %d x %d)", d->Cout, p.n_tiles, p.BN);
+    delete P;
+    return nullptr;
+  }
   p.fd_nt = make_fastdiv((uint32_t)p.n_tiles, (uint64_t)p.total_tiles + 1);
   p.fd_xy = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y), (uint64_t)p.total_tiles + 1);
   p.fd_x = make_fastdiv((uint32_t)p.tiles_x, (uint64_t)p.tiles_x * p.tiles_y);
@@ -418,12 +445,14 @@ UmmaConvPrepared* umma_conv_prepare(const brtpe_conv_desc* d, const void* in, co
   const cuuint64_t ld_b = (cuuint64_t)d->in_ld * 2;
   cuuint64_t gdim[5], gstr[4];
   if (s == 1) {
-    gdim[0] = (cuuint64_t)(d->in_coff + d->Cin); gdim[1] = d->Win; gdim[2] = 1; gdim[3] = d->Hin;
+    gdim[0] = (cuuint64_t)(split ? d->in_ld : d->in_coff + d->Cin); gdim[1] = d->Win; gdim[2] = 1;
+    gdim[3] = d->Hin;
     gdim[4] = d->N;
     gstr[0] = ld_b; gstr[1] = ld_b * d->Win; gstr[2] = ld_b * d->Win;
     gstr[3] = ld_b * d->Win * d->Hin;
   } else {
-    gdim[0] = (cuuint64_t)(d->in_ld + d->in_coff + d->Cin); gdim[1] = d->Win / 2; gdim[2] = 2;
+    gdim[0] = (cuuint64_t)(split ? 2 * d->in_ld : d->in_ld + d->in_coff + d->Cin);
+    gdim[1] = d->Win / 2; gdim[2] = 2;
     gdim[3] = d->Hin / 2; gdim[4] = d->N;
     gstr[0] = 2 * ld_b; gstr[1] = ld_b * d->Win; gstr[2] = 2 * ld_b * d->Win;
     gstr[3] = ld_b * d->Win * d->Hin;
@@ -455,7 +484,9 @@ UmmaConvPrepared* umma_conv_prepare(const brtpe_conv_desc* d, const void* in, co
     return nullptr;
   }
   if (!g_attr_set) {
-    if (cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              227 * 1024) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(conv_umma_kernel) failed: %s",
                 cudaGetErrorString(cudaGetLastError()));
@@ -475,7 +506,8 @@ int umma_conv_launch(const UmmaConvPrepared* P, const float* bias, const void* r
   p.bias = bias;
   p.epi.res = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.epi.out = reinterpret_cast<__nv_bfloat16*>(out);
-  conv_umma_kernel<<<P->grid, UM_THREADS, P->smem, st>>>(p);
+  if (p.epi.split) conv_umma_kernel<true><<<P->grid, UM_THREADS, P->smem, st>>>(p);
+  else conv_umma_kernel<false><<<P->grid, UM_THREADS, P->smem, st>>>(p);
   BRTPE_LAUNCH_CHECK();
   return BRTPE_OK;
 }

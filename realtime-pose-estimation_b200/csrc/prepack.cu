@@ -70,6 +70,13 @@ __global__ void __launch_bounds__(256) prepack_weights_kernel(const PrepackParam
     ci = (int)(r % d.Cin_store);
     t = (int)(r / d.Cin_store);
   }
+  // split (BRTPE_DT_BF16X2) layers: K = [w_hi | w_hi | w_lo], each segment padded to 64 channels
+  int seg = 0;
+  if (d.split) {
+    const int seg_pad = d.cin_pad / 3;
+    seg = ci / seg_pad;
+    ci -= seg * seg_pad;
+  }
   float v = 0.0f;
   if (co < d.Cout && ci < d.Cin_store) {
     int src = p.cin_index ? p.cin_index[ci] : ci;
@@ -87,6 +94,7 @@ __global__ void __launch_bounds__(256) prepack_weights_kernel(const PrepackParam
                                ? (((long long)src * d.Cout + co) * d.KH + kh) * d.KW + kw
                                : (((long long)co * d.Cin + src) * d.KH + kh) * d.KW + kw;
       v = __fmul_rn(load_w(p.w, d.w_dtype, wi), bn_scale(p, co));
+      if (seg == 2) v = __fsub_rn(v, __bfloat162float(__float2bfloat16_rn(v)));
     }
   }
   if (d.layout == BRTPE_PACK_KMAJOR_BF16) {
@@ -125,11 +133,14 @@ extern "C" int brtpe_prepack_weights(const brtpe_prepack_desc* d, const void* w,
                   "brtpe_prepack_weights: bias_len %d < Cout %d", bias_len, d->Cout);
   long long total;
   if (d->layout == BRTPE_PACK_KMAJOR_BF16) {
+    BRTPE_CHECK_ARG(!d->split || (d->cin_pad % 3 == 0 && d->cin_pad / 3 >= d->Cin_store),
+                    "brtpe_prepack_weights: split layers need cin_pad = 3 x padded Cin_store");
     BRTPE_CHECK_ARG(d->cin_pad >= d->Cin_store && d->cout_pad >= d->Cout,
                     "brtpe_prepack_weights: padded dims (%d, %d) smaller than (%d, %d)", d->cin_pad,
                     d->cout_pad, d->Cin_store, d->Cout);
     total = (long long)d->ntaps * d->cout_pad * d->cin_pad;
   } else {
+    BRTPE_CHECK_ARG(!d->split, "brtpe_prepack_weights: split needs the K-major bf16 layout");
     BRTPE_CHECK_ARG(d->layout == BRTPE_PACK_CIN_COUT_F32 && d->Cout_pack >= d->Cout,
                     "brtpe_prepack_weights: bad layout %d / Cout_pack %d", d->layout, d->Cout_pack);
     total = (long long)d->ntaps * d->Cin_store * d->Cout_pack;

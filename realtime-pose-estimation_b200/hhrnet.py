@@ -150,10 +150,11 @@ class HighResolutionModule(nn.Module):
 # ---------------------------------------------------------------------------------------
 class _T:
     """virtual NHWC tensor"""
-    __slots__ = ("n", "h", "w", "ld", "first", "last", "buf", "keep", "lane", "touch", "inherit")
+    __slots__ = ("n", "h", "w", "ld", "cl", "first", "last", "buf", "keep", "lane", "touch", "inherit")
 
-    def __init__(self, n, h, w, ld):
-        self.n, self.h, self.w, self.ld = n, h, w, ld
+    def __init__(self, n, h, w, ld, cl=None):
+        self.n, self.h, self.w, self.ld = n, h, w, ld     # ld: pixel stride in stored elements
+        self.cl = ld if cl is None else cl                # logical channels per pixel
         self.first = None
         self.last = None
         self.buf = None
@@ -173,8 +174,14 @@ class _Recorder:
         self.mode = mode                          # "fp32" | "bf16"
         self.engine = engine                      # ENGINE_AUTO | FFMA | UMMA
         self.device = device
-        self.dt = L.DT_F32 if mode == "fp32" else L.DT_BF16
-        self.tdtype = torch.float32 if mode == "fp32" else torch.bfloat16
+        # fp32 mode on the tensor cores ("split"): activations are (hi, lo) bf16 pairs, every
+        # product is three bf16 MMAs (include/brtpe.h BRTPE_DT_BF16X2); models opt in with
+        # ``_split_fp32`` and ENGINE_FFMA keeps the CUDA-core float32 path
+        self.split = bool(mode == "fp32" and engine != L.ENGINE_FFMA and
+                          getattr(model, "_split_fp32", False))
+        self.tc = mode == "bf16" or self.split    # tcgen05 engines
+        self.dt = L.DT_BF16X2 if self.split else (L.DT_F32 if mode == "fp32" else L.DT_BF16)
+        self.tdtype = torch.bfloat16 if self.tc else torch.float32
         self.ops = []
         self.tensors = []
         self.keepalive = []                       # packed weights / biases
@@ -186,7 +193,8 @@ class _Recorder:
 
     # -- tensors
     def new(self, n, h, w, ld):
-        t = _T(n, h, w, ld)
+        """virtual tensor with ``ld`` logical channels per pixel (split mode stores twice as many)"""
+        t = _T(n, h, w, 2 * ld if self.split else ld, ld)
         self.tensors.append(t)
         return t
 
@@ -242,12 +250,17 @@ class _Recorder:
             cin_pad, cout_pad = C.c_int(0), C.c_int(0)
             lib.brtpe_umma_weight_dims(cin_store, d.Cout_store, C.byref(cin_pad), C.byref(cout_pad))
             pd.layout = L.PACK_KMAJOR_BF16
-            pd.cin_pad, pd.cout_pad = cin_pad.value, cout_pad.value
-            packed = torch.empty((pd.ntaps, cout_pad.value, cin_pad.value), dtype=torch.bfloat16,
+            pd.split = int(self.split)                     # K = [w_hi | w_hi | w_lo]
+            pd.cin_pad = cin_pad.value * (3 if self.split else 1)
+            pd.cout_pad = cout_pad.value
+            packed = torch.empty((pd.ntaps, pd.cout_pad, pd.cin_pad), dtype=torch.bfloat16,
                                  device=self.device)
         else:
             pd.layout = L.PACK_CIN_COUT_F32
             pd.Cout_pack = cout
+            if self.split:
+                raise L.BrtpeError("fp32 mode on the tensor cores: layer not supported by a tcgen05 "
+                                   "engine (%s)" % lib.brtpe_last_error().decode("utf-8", "replace"))
             pd.round_bf16 = int(self.mode == "bf16" and d is not None)   # tcgen05's operand rounding
             packed = torch.empty((pd.ntaps, cin_store, cout), dtype=torch.float32,
                                  device=self.device)
@@ -263,6 +276,9 @@ class _Recorder:
         ci = None
         if cin_index is not None:
             ci = torch.as_tensor(list(cin_index), dtype=torch.int32).to(self.device)
+        if torch.device(self.device).type != "cuda":
+            # host-side recording only (tests of the plan structure): nothing can run the plan
+            return packed, bias
         with torch.cuda.device(self.device):
             L.check(lib.brtpe_prepack_weights(
                 C.byref(pd), L.ptr(w), L.ptr(cb), L.ptr(g), L.ptr(beta), L.ptr(mu), L.ptr(var),
@@ -293,7 +309,7 @@ class _Recorder:
         if cin_index is not None:
             cin = cin_store = len(cin_index)
         dcout = cout
-        if pad_cout and cout_store % 16 == 0 and cout < cout_store and self.mode == "bf16":
+        if pad_cout and cout_store % 16 == 0 and cout < cout_store and self.tc:
             # heads with 17 / 34 real channels: zero weights + zero bias for the pad channels, so
             # that the layer is a whole number of 16-channel chunks (vectorised epilogue; the pad
             # channels were written as zeros before, too)
@@ -333,7 +349,7 @@ class _Recorder:
               cout_store, out_coff, residual, relu):
         d = L.ConvDesc()
         d.dtype = self.dt
-        d.engine = self.engine if self.mode == "bf16" else L.ENGINE_FFMA
+        d.engine = self.engine if self.tc else L.ENGINE_FFMA
         d.N, d.Hin, d.Win = x.n, x.h, x.w
         d.Cin, d.in_ld, d.in_coff = cin, x.ld, in_coff
         d.Hm, d.Wm, d.in_stride = hm, wm, stride
@@ -420,7 +436,7 @@ class _Recorder:
     # -- arena + native plan
     def build(self, in_buf):
         lib = L.load(require_cuda=False)
-        esize = 4 if self.mode == "fp32" else 2
+        esize = 2 if self.tc else 4
         # Liveness-packed arena.  Released buffers go back to the pool of the lane that
         # created them and are only re-used by that lane, so arena re-use does not serialise
         # independent lanes; the ops that used the previous tenants are still recorded as
@@ -525,7 +541,8 @@ class _Recorder:
                 elif kind == "im2col":
                     _, cols = op
                     L.check(lib.brtpe_plan_add_stem_im2col(
-                        plan, L.ptr(in_buf), int(self.in_is_half) | int(self.stem_mode), self.n,
+                        plan, L.ptr(in_buf), int(self.in_is_half) | int(self.stem_mode) |
+                        (8 if self.split else 0), self.n,
                         self.h, self.w, L.ptr(cols.buf[1])), "brtpe_plan_add_stem_im2col")
                 k = lib.brtpe_plan_num_ops(plan) - 1
                 deps = self.deps[k]
@@ -809,6 +826,7 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
         self.num_joints = num_joints
 
         self._init_runner()
+        self._split_fp32 = True        # float32 parameters -> split-bf16 tcgen05 path (<= 1e-4)
 
     # ---------------------------------------------------------------- construction helpers
     def _make_layer(self, block, planes, blocks, stride=1):
@@ -869,7 +887,7 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
         R = _Recorder(self, n, h, w, mode, self.conv_engine, device, in_is_half)
         R.stem_mode = stem_mode
         par = self.parallel_branches
-        if mode == "bf16" and self.conv_engine != L.ENGINE_FFMA:
+        if R.tc and self.conv_engine != L.ENGINE_FFMA:
             x = R.stem_tc(self.conv1, self.bn1)
         else:
             x = R.stem(self.conv1, self.bn1)
@@ -964,7 +982,7 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
             R.to_nchw(y, head0.out_channels, 0, y0_out)
         for i in range(self.num_deconvs):
             dl = self.deconv_layers[i]
-            x = R.deconv4x4s2(x, dl[0][0], dl[0][1], x.ld if cat else dl[0][0].in_channels,
+            x = R.deconv4x4s2(x, dl[0][0], dl[0][1], x.cl if cat else dl[0][0].in_channels,
                               lanes=(0, 1, 2, 3) if par else (0,))
             for k in range(1, len(dl)):
                 blk = dl[k][0]
@@ -986,7 +1004,7 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
     def supports_flip_pair(self, x):
         """The fused flip-test batch needs the tensor-core stem (im2col) and N * H / 2 <= 65535 rows
         per plan replay."""
-        return (self._mode() == "bf16" and self.conv_engine != L.ENGINE_FFMA and x.dim() == 4 and
+        return (self.conv_engine != L.ENGINE_FFMA and x.dim() == 4 and
                 min(self.chunk_size, 2 * x.shape[0]) * (x.shape[2] // 2) <= 65535)
 
     def forward_flip_pair(self, x, via_half=False, borrow=False):

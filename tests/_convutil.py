@@ -78,3 +78,57 @@ def run_conv(engine, mode, n, h, w, cin, cout, k, stride, relu, use_res, seed=0,
         ref = F.relu(ref)
     got = out[..., :cout].float().permute(0, 3, 1, 2)
     return got, ref.float(), eng
+
+
+def split_hi_lo(t):
+    """float32 -> (hi, lo) bf16 pair of BRTPE_DT_BF16X2: hi = bf16(v), lo = bf16(v - hi)."""
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def run_conv_split(engine, n, h, w, cin, cout, k, stride, relu, use_res, seed=0, device="cuda"):
+    """fp32 mode of the tcgen05 engines (BRTPE_DT_BF16X2): split activations, weights packed by
+    brtpe_prepack_weights(split=1).  -> (out NCHW f32 = hi + lo, float64 reference, engine)."""
+    lib = L.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn((n, cin, h, w), generator=g).to(device)
+    wgt = (torch.randn((cout, cin, k, k), generator=g) / (cin * k * k) ** 0.5).to(device)
+    bias = torch.randn((cout,), generator=g).to(device) * 0.1
+    ho, wo = h // stride, w // stride
+    res = torch.randn((n, cout, ho, wo), generator=g).to(device) if use_res else None
+    d, taps = make_desc(L.DT_BF16X2, engine, n, h, w, cin, cout, k, stride, relu, in_ld=2 * cin,
+                        out_ld=2 * cout, res_ld=(2 * cout if use_res else 0))
+    eng = lib.brtpe_conv_select_engine(C.byref(d))
+    assert eng in (L.ENGINE_UMMA, L.ENGINE_UMMA_HALO), lib.brtpe_last_error()
+
+    def to_split_nhwc(t):
+        hi, lo = split_hi_lo(t.permute(0, 2, 3, 1).contiguous())
+        return torch.cat((hi, lo), dim=3).contiguous()
+    xin = to_split_nhwc(x)
+    rin = to_split_nhwc(res) if use_res else None
+    cp, op = C.c_int(0), C.c_int(0)
+    lib.brtpe_umma_weight_dims(cin, cout, C.byref(cp), C.byref(op))
+    pd = L.PrepackDesc()
+    pd.w_dtype, pd.transposed = L.WT_F32, 0
+    pd.Cout, pd.Cin, pd.KH, pd.KW = cout, cin, k, k
+    pd.ntaps = len(taps)
+    for i, (dy, dx) in enumerate(taps):
+        pd.tap_kh[i], pd.tap_kw[i] = dy + k // 2, dx + k // 2
+    pd.Cin_store, pd.layout, pd.split = cin, L.PACK_KMAJOR_BF16, 1
+    pd.cin_pad, pd.cout_pad = 3 * cp.value, op.value
+    packed = torch.empty((len(taps), op.value, 3 * cp.value), dtype=torch.bfloat16, device=device)
+    L.check(lib.brtpe_prepack_weights(C.byref(pd), L.ptr(wgt), None, None, None, None, None, None,
+                                      L.ptr(packed), None, 0, L.stream_ptr()), "brtpe_prepack_weights")
+    out = torch.full((n, ho, wo, 2 * cout), float("nan"), dtype=torch.bfloat16, device=device)
+    L.check(lib.brtpe_conv_run(C.byref(d), L.ptr(xin), L.ptr(packed), L.ptr(bias), L.ptr(rin),
+                               L.ptr(out), L.stream_ptr()), "brtpe_conv_run")
+    torch.cuda.synchronize()
+    xr = (xin[..., :cin].double() + xin[..., cin:].double()).permute(0, 3, 1, 2)
+    ref = F.conv2d(xr, wgt.double(), bias.double(), stride=stride, padding=k // 2)
+    if use_res:
+        ref = ref + (rin[..., :cout].double() + rin[..., cout:].double()).permute(0, 3, 1, 2)
+    if relu:
+        ref = F.relu(ref)
+    got = (out[..., :cout].float() + out[..., cout:].float()).permute(0, 3, 1, 2)
+    return got, ref.float(), eng

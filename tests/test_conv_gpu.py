@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from rtpe_b200 import _lib as L
-from _convutil import run_conv
+from _convutil import run_conv, run_conv_split
 
 pytestmark = pytest.mark.gpu
 
@@ -138,3 +138,43 @@ def test_umma_halo_many_items(cuda_device):
         assert eng == L.ENGINE_UMMA_HALO
         assert torch.isfinite(got).all()
         assert _err(got, ref) <= 6e-3
+
+
+# ---- fp32 mode on the tensor cores: split (hi, lo) bf16 activations, three MMAs per product
+SPLIT_SHAPES = [
+    # n, h, w, cin, cout, k, stride, relu, res  (Cout a multiple of 16: the split epilogue's contract)
+    (2, 32, 48, 48, 48, 3, 1, True, True),
+    (1, 40, 40, 96, 96, 3, 1, True, False),
+    (3, 20, 20, 192, 192, 3, 1, False, True),
+    (1, 20, 20, 384, 384, 3, 1, True, True),
+    (1, 16, 16, 256, 48, 3, 1, True, False),
+    (2, 24, 40, 64, 64, 3, 1, True, False),
+    (2, 32, 32, 64, 256, 1, 1, True, True),
+    (1, 32, 32, 256, 64, 1, 1, True, False),
+    (2, 32, 32, 48, 96, 3, 2, True, False),
+    (1, 64, 64, 64, 64, 3, 2, True, False),
+    (2, 32, 32, 192, 384, 3, 2, True, False),
+    (3, 24, 40, 48, 32, 1, 1, False, False),
+    (1, 16, 16, 384, 48, 1, 1, False, False),
+    (2, 32, 32, 32, 64, 1, 1, True, False),
+]
+
+
+@pytest.mark.parametrize("shape", SPLIT_SHAPES)
+def test_split_fp32_on_tcgen05(cuda_device, shape):
+    got, ref, eng = run_conv_split(L.ENGINE_AUTO, *shape)
+    assert eng in (L.ENGINE_UMMA, L.ENGINE_UMMA_HALO)
+    assert torch.isfinite(got).all()
+    # hi*hi + lo*hi + hi*lo drops the lo*lo term (2^-16 relative) and the output is rounded to
+    # 16 significant bits: 3e-5 of the tensor max is the contract the network test builds on
+    assert _err(got, ref) <= 3e-5
+
+
+def test_split_fp32_per_tap_engine_and_many_items(cuda_device):
+    for shape in [(2, 32, 48, 48, 48, 3, 1, True, True), (1, 40, 40, 96, 96, 3, 1, True, True)]:
+        got, ref, eng = run_conv_split(L.ENGINE_UMMA, *shape)
+        assert eng == L.ENGINE_UMMA and _err(got, ref) <= 3e-5
+    for shape in [(7, 80, 72, 48, 48, 3, 1, True, True), (3, 80, 80, 96, 96, 3, 1, True, True),
+                  (9, 40, 40, 192, 192, 3, 1, True, True)]:
+        got, ref, eng = run_conv_split(L.ENGINE_UMMA_HALO, *shape)
+        assert eng == L.ENGINE_UMMA_HALO and _err(got, ref) <= 3e-5

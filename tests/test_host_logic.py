@@ -20,6 +20,7 @@ def test_plan_recording_layer_list_and_flops():
     concat-buffer wiring and the arena without any kernel launch."""
     lib = L.load(require_cuda=False)
     net = rtpe_b200.PoseHigherResolutionNet().eval()
+    net.conv_engine = L.ENGINE_FFMA        # the tcgen05 engines need a CUDA driver (tensor maps)
     dev = torch.device("cpu")
     R, outs = net._record(1, 128, 128, "fp32", dev, False, False)
     in_buf = torch.zeros(1, 3, 128, 128)
