@@ -283,6 +283,84 @@ def workload_config(args):
                   % (args.batch * 3 * args.size * args.size * 4 / 1e6)}
 
 
+def conv_rooflines(net, chunk, size, in_dtype, peaks, mode):
+    """(roofline of conv_halo_kernel, roofline of conv_umma_kernel, per-op ms) of one plan replay:
+    algorithmic FLOP (2 * MAC of the reference layer) / CUDA-event time of the launches."""
+    net.plan_profile(chunk, size, size, in_dtype)
+    ms_ops, kinds, flops = net.plan_profile(chunk, size, size, in_dtype)
+    conv_ms = sum(m for m, k in zip(ms_ops, kinds) if k in (0, 1, 3))
+
+    def one(kset, name):
+        ms = sum(m for m, k in zip(ms_ops, kinds) if k in kset)
+        fl = sum(f for f, k in zip(flops, kinds) if k in kset)
+        nl = sum(1 for k in kinds if k in kset)
+        ach = fl / max(ms, 1e-9) / 1e9
+        return {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peaks["tflops"],
+                "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": None, "launches": nl,
+                "avg_launch_ms": ms / max(nl, 1), "flop_per_launch_avg": fl / max(nl, 1),
+                "share_of_forward": ms / max(sum(ms_ops), 1e-9), "peak_source": peaks["source"],
+                "chunk": chunk}
+
+    # dominant kernel: the 3x3/s1 tcgen05 halo kernel (kind 3); the per-tap tcgen05 kernel (1x1,
+    # stride 2, deconv phases, stem) is reported beside it
+    roofline = one((3,), "conv_halo_kernel (tcgen05 implicit GEMM, 3x3 s1)")
+    other = one((0,), "conv_umma_kernel (tcgen05 implicit GEMM, 1x1 / s2 / deconv / 3x3 384ch on 20x20 maps)")
+    if mode == "fp32":
+        if roofline["launches"] == 0:          # BRTPE engine override: CUDA-core float32 path
+            roofline = one((1,), "conv_ffma_kernel (fp32 FFMA implicit GEMM)")
+            roofline["note"] = "fp32 CUDA-core path; frac is against the bf16 tensor peak"
+        else:
+            note = ("fp32 mode = split (hi, lo) bf16 activations, THREE bf16 tcgen05 MMAs per product "
+                    "(BRTPE_DT_BF16X2); achieved = algorithmic FLOP of the layer / time, so the "
+                    "tensor pipe does 3x this work: frac * 3 is the pipe's share of the bf16 peak")
+            roofline["note"] = note
+            roofline["pipe_frac"] = 3 * roofline["frac"]
+            other["pipe_frac"] = 3 * other["frac"]
+    roofline["conv_share_of_forward"] = conv_ms / max(sum(ms_ops), 1e-9)
+    return roofline, other, ms_ops
+
+
+def fp32_leg(args, dev, x_dev, ref, peaks):
+    """configs[1] names bf16 AND fp32: the same step with float32 parameters (split-bf16 tcgen05
+    path, <= 1e-4), measured next to the bf16 headline and checked against the CPU leg."""
+    import rtpe_b200
+    from rtpe_b200 import inference
+    torch.manual_seed(0)
+    model = rtpe_b200.get_hrnet_w48_teacher(None, half=False).to(dev)
+    model.chunk_size = args.chunk
+    model.freeze()
+    parser = rtpe_b200.HeatmapParser(**PARSER_KW)
+    pipe = inference.TeacherPipeline(model, parser, flip_test=True)
+    for _ in range(2):
+        pipe.run_device(x_dev, True, True)
+    torch.cuda.synchronize()
+    steps = max(2, min(args.steps, 5))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        pipe.run_device(x_dev, True, True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    roofline, other, _ = conv_rooflines(model, min(args.chunk, 2 * args.batch), args.size,
+                                        torch.float32, peaks, "fp32")
+    out = {"value": x_dev.shape[0] / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms, "steps": steps,
+           "dtype": "fp32 (split bf16x2 on tcgen05)", "roofline": roofline,
+           "roofline_other_convs": other, "scope": "device-resident, 1 GPU, same step as `value`"}
+    if ref is not None:
+        n = x_dev.shape[0]
+        with torch.no_grad():
+            y0, y1 = pipe._forward_flip(x_dev)
+            errs = []
+            for got, want in ((y0[0:1], ref["y"][0]), (y1[0:1], ref["y"][1]),
+                              (y0[n:n + 1], ref["yf"][0]), (y1[n:n + 1], ref["yf"][1])):
+                errs.append(float((got.double().cpu() - want.double()).abs().max() /
+                                  want.double().abs().max()))
+        out["max_rel_err_vs_cpu_leg"] = max(errs)
+        out["parity_checked"] = bool(max(errs) <= 1e-4)
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
@@ -392,33 +470,10 @@ def run_ours(args, rank, world, local_rank):
     peaks = load_peaks()
     in_dtype = torch.float16 if args.mode == "bf16" else torch.float32
     chunk = min(args.chunk, 2 * args.batch)
-    net.plan_profile(chunk, args.size, args.size, in_dtype)
-    ms_ops, kinds, flops = net.plan_profile(chunk, args.size, args.size, in_dtype)
-    conv_ms = sum(m for m, k in zip(ms_ops, kinds) if k in (0, 1, 3))
-
-    def conv_roofline(kset, name):
-        ms = sum(m for m, k in zip(ms_ops, kinds) if k in kset)
-        fl = sum(f for f, k in zip(flops, kinds) if k in kset)
-        nl = sum(1 for k in kinds if k in kset)
-        ach = fl / max(ms, 1e-9) / 1e9
-        return {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peaks["tflops"],
-                "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": None, "launches": nl,
-                "avg_launch_ms": ms / max(nl, 1), "flop_per_launch_avg": fl / max(nl, 1),
-                "share_of_forward": ms / max(sum(ms_ops), 1e-9), "peak_source": peaks["source"],
-                "chunk": chunk}
-
-    # dominant kernel: the 3x3/s1 tcgen05 halo kernel (kind 3); the per-tap tcgen05 kernel (1x1,
-    # stride 2, deconv phases, stem) is reported beside it
-    roofline = conv_roofline((3,), "conv_halo_kernel (tcgen05 implicit GEMM, 3x3 s1)")
-    if args.mode == "fp32":
-        # fp32 mode has no tensor-core kernel (<= 1e-4 rules out single-pass TF32/bf16): the
-        # CUDA-core FFMA kernel is the dominant one; the tensor peak is kept as denominator
-        roofline = conv_roofline((1,), "conv_ffma_kernel (fp32 FFMA implicit GEMM)")
-        roofline["note"] = "fp32 CUDA-core path; frac is against the bf16 tensor peak"
-    roofline_other = conv_roofline((0,), "conv_umma_kernel (tcgen05 implicit GEMM, 1x1 / s2 / deconv / 3x3 384ch on 20x20 maps)")
-    roofline["conv_share_of_forward"] = conv_ms / max(sum(ms_ops), 1e-9)
+    roofline, roofline_other, ms_ops = conv_rooflines(net, chunk, args.size, in_dtype, peaks,
+                                                      args.mode)
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.isfile(tpath):
+    if os.path.isfile(tpath) and args.mode == "bf16":
         with open(tpath) as f:
             t = json.load(f)
         roofline["traffic"] = t.get("dram_bytes_per_launch")
@@ -482,7 +537,7 @@ def run_ours(args, rank, world, local_rank):
     n_chunks = -(-2 * args.batch // args.chunk)
     gpu_launches = (n_chunks * plan_ops + 1 + 9) * args.steps
 
-    cpu_baseline, parity = None, None
+    cpu_baseline, parity, ref = None, None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = CpuPath(args.size)
         xs = x_host[:1].clone()                       # image 0 of the timed batch
@@ -505,6 +560,9 @@ def run_ours(args, rank, world, local_rank):
         gpu.update(det=gdet[0:1], tag=gtag[0:1], people=gans[0, :c0].cpu().numpy(),
                    scores=gscores[0, :c0].cpu().numpy())
         parity = parity_check(cpu, ref, gpu, 2e-2 if args.mode == "bf16" else 1e-4)
+    fp32 = None
+    if rank == 0 and world == 1 and args.mode == "bf16" and not args.no_fp32:
+        fp32 = fp32_leg(args, dev, x_dev, ref if parity else None, peaks)
 
     if rank == 0:
         h2d = x_host.numel() * x_host.element_size()
@@ -520,7 +578,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline_other_convs": roofline_other,
             "roofline_decode": roofline_decode, "cpu_baseline": cpu_baseline,
             "parity_checked": bool(parity and parity["float_ok"] and parity["decode_bit_exact"]),
-            "parity": parity,
+            "parity": parity, "fp32": fp32,
             "forward_tflops_effective": 2 * args.batch * world * args.steps *
             FLOP_PER_FORWARD_640 * (args.size / 640.0) ** 2 / (ms_dev * 1e-3) / 1e12,
             "people_per_image": people_mean,
@@ -542,6 +600,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=64,
                     help="forwards per plan replay (64 = the whole flip-test batch in one CUDA graph)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-mode leg of the bf16 line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

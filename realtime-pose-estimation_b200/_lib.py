@@ -12,7 +12,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libbrtpe.so")
+# BRTPE_LIB: another build of the same library (A/B measurements of two builds on one GPU box)
+LIB_PATH = os.environ.get("BRTPE_LIB") or os.path.join(_HERE, "csrc", "libbrtpe.so")
 
 MAX_TAG_DIMS = 4
 MAX_TOPK = 64

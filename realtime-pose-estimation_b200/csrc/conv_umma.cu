@@ -66,6 +66,14 @@ __device__ __forceinline__ uint32_t um_desc_lo(uint32_t smem_addr) {
   return ((smem_addr >> 4) & 0x3fffu) | (1u << 16);
 }
 
+template <int K16>
+__device__ __forceinline__ void um_issue_k(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                           uint32_t idesc, uint32_t first) {
+#pragma unroll
+  for (int k = 0; k < K16; ++k)
+    umma_f16_lohi(d_tmem, a_lo + 2u * k, hi, b_lo + 2u * k, hi, idesc, (first | (uint32_t)k) ? 1u : 0u);
+}
+
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
@@ -176,10 +184,14 @@ conv_umma_kernel(const __grid_constant__ UmmaParams p) {
           const int seg = (kb >= nkb_seg) + (kb >= 2 * nkb_seg);
           const int k16 = (kb - seg * nkb_seg == nkb_seg - 1) ? last_k16 : 4;
           if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < k16)
-                umma_f16_lohi(d_tmem, a_lo + 2u * k, HI, b_lo + 2u * k, HI, idesc, (first | k) ? 1u : 0u);
+            // no run-time branch between the MMAs of a K block (tools/exp_umma_seq.cu: a partial
+            // block issued through `if (k < k16)` costs ~10 cycles per MMA)
+            switch (k16) {
+              case 4: um_issue_k<4>(d_tmem, a_lo, b_lo, HI, idesc, first); break;
+              case 3: um_issue_k<3>(d_tmem, a_lo, b_lo, HI, idesc, first); break;
+              case 2: um_issue_k<2>(d_tmem, a_lo, b_lo, HI, idesc, first); break;
+              default: um_issue_k<1>(d_tmem, a_lo, b_lo, HI, idesc, first); break;
+            }
             umma_commit(smem_u32(&empty_bar[stage]));
           }
           __syncwarp();
