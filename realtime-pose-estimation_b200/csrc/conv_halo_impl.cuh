@@ -390,10 +390,16 @@ __device__ __forceinline__ void halo_epilogue_split(const HaloParams& p, const f
   }
 }
 
-template <bool SPLIT>
+// Instantiations (the kernel is ~8000 instructions with every path in it, and the hot loops are
+// sensitive to code size: an extra, unused epilogue variant cost 5 % on the 48-channel layers,
+// profiles/r02_mma_issue.md): SPLIT = BRTPE_DT_BF16X2 epilogue; PROFT = cycle counters compiled in;
+// EPI = -1: epilogue chosen at run time (general path included; only ONE instantiation may call the
+// non-inlined epi_drain: ptxas 12.9 crashes on two), -2: run-time choice among the fast epilogues,
+// 0..3: fast epilogue with RES = EPI >> 1, RELU = EPI & 1 only.
+template <bool SPLIT, bool PROFT, int EPI>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
-  const bool PROF = p.prof != nullptr;   // debug counters (brtpe_debug_halo_prof), warp-uniform
+  const bool PROF = PROFT && p.prof != nullptr;   // debug counters (brtpe_debug_halo_prof), warp-uniform
   extern __shared__ uint8_t smem_raw[];
   long long pc[HL_PROF_SLOTS];
 #pragma unroll
@@ -727,6 +733,8 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
         if (e.relu) halo_epilogue_split<false, true>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep);
         else halo_epilogue_split<false, false>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep);
       }
+    } else if (EPI >= 0) {
+      halo_epilogue_fast<(EPI >> 1) != 0, (EPI & 1) != 0>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
     } else if (e.fast) {
       if (e.res != nullptr) {
         if (e.relu) halo_epilogue_fast<true, true>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
@@ -735,7 +743,7 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
         if (e.relu) halo_epilogue_fast<false, true>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
         else halo_epilogue_fast<false, false>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
       }
-    } else {
+    } else if (EPI == -1) {
       // general epilogue (ragged channel counts): single-CTA mode only (host guarantees cg == 1)
       const int m = lg * 32 + lane;
       const int nchunks = BN >> 4;
@@ -824,6 +832,20 @@ static void halo_n_tiling(int cout_store, int pairs, int workers, int* n_tiles, 
 }
 
 static bool HL_NAME(g_halo_attr_set) = false;
+
+// kernel instantiations: 0..3 fast epilogue with (RES, RELU) = (v >> 1, v & 1); 4 run-time epilogue
+// choice (general path); 5 split (BRTPE_DT_BF16X2); 6 with the debug cycle counters
+constexpr int HL_NUM_VARIANTS = 7;
+#define HL_FOR_VARIANT(v, CALL)                                                   \
+  switch (v) {                                                                    \
+    case 0: CALL((HL_NAME(conv_halo_kernel)<false, false, 0>)); break;            \
+    case 1: CALL((HL_NAME(conv_halo_kernel)<false, false, 1>)); break;            \
+    case 2: CALL((HL_NAME(conv_halo_kernel)<false, false, 2>)); break;            \
+    case 3: CALL((HL_NAME(conv_halo_kernel)<false, false, 3>)); break;            \
+    case 4: CALL((HL_NAME(conv_halo_kernel)<false, false, -1>)); break;           \
+    case 5: CALL((HL_NAME(conv_halo_kernel)<true, false, -2>)); break;            \
+    default: CALL((HL_NAME(conv_halo_kernel)<false, true, -2>)); break;           \
+  }
 
 // Output tensor map of the epilogue's TMA stores: (C = out_coff + Cout, W, H, N) with the pixel
 // stride of the output buffer; box = 32 channels x 8 px x 4 rows (one epilogue warp's slab),
@@ -1073,13 +1095,16 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
     P->out_encoded = out;
   }
   if (!HL_NAME(g_halo_attr_set)) {
-    if (cudaFuncSetAttribute(HL_NAME(conv_halo_kernel)<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             HL_SMEM_MAX) != cudaSuccess ||
-        cudaFuncSetAttribute(HL_NAME(conv_halo_kernel)<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             HL_SMEM_MAX) != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(HL_NAME(conv_halo_kernel)) failed");
-      delete P;
-      return nullptr;
+    for (int v = 0; v < HL_NUM_VARIANTS; ++v) {
+      cudaError_t ae = cudaSuccess;
+#define HL_SET_ATTR(K) ae = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM_MAX)
+      HL_FOR_VARIANT(v, HL_SET_ATTR)
+#undef HL_SET_ATTR
+      if (ae != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(HL_NAME(conv_halo_kernel)) failed");
+        delete P;
+        return nullptr;
+      }
     }
     HL_NAME(g_halo_attr_set) = true;
   }
@@ -1122,8 +1147,15 @@ int HL_NAME(halo_conv_launch)(const HaloConvPrepared* P, const float* bias, cons
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = p.epi.split ? cudaLaunchKernelEx(&cfg, HL_NAME(conv_halo_kernel)<true>, p)
-                              : cudaLaunchKernelEx(&cfg, HL_NAME(conv_halo_kernel)<false>, p);
+  int variant;
+  if (p.epi.split) variant = 5;
+  else if (p.prof != nullptr && p.epi.fast) variant = 6;
+  else if (p.epi.fast && p.dbg == 0) variant = (p.epi.res != nullptr ? 2 : 0) + (p.epi.relu ? 1 : 0);
+  else variant = 4;
+  cudaError_t e = cudaSuccess;
+#define HL_LAUNCH(K) e = cudaLaunchKernelEx(&cfg, K, p)
+  HL_FOR_VARIANT(variant, HL_LAUNCH)
+#undef HL_LAUNCH
   if (e != cudaSuccess) {
     set_error("HL_NAME(conv_halo_kernel) launch failed: %s", cudaGetErrorString(e));
     return BRTPE_ECUDA;
