@@ -18,13 +18,20 @@ int halo_conv_launch_cg2(const HaloConvPrepared* P, const float* bias, const voi
                          cudaStream_t st);
 
 bool halo_conv_supported(const brtpe_conv_desc* d) {
-  if ((d->dtype != BRTPE_DT_BF16 && d->dtype != BRTPE_DT_BF16X2) || d->ntaps != 9 ||
-      d->in_stride != 1 || d->out_scale != 1)
+  if ((d->dtype != BRTPE_DT_BF16 && d->dtype != BRTPE_DT_BF16X2) || d->ntaps != 9 || d->out_scale != 1)
     return false;
   if (conv_is_split(d) && (!epi_split_ok(d) || d->in_ld / 2 < d->in_coff + d->Cin)) return false;
-  if (d->out_oy || d->out_ox || d->Hm != d->Hin || d->Wm != d->Win || d->Hout != d->Hin ||
-      d->Wout != d->Win)
+  if (d->out_oy || d->out_ox || d->Hout != d->Hm || d->Wout != d->Wm) return false;
+  if (d->in_stride == 1) {
+    if (d->Hm != d->Hin || d->Wm != d->Win) return false;
+  } else if (d->in_stride == 2) {
+    // 3x3 / stride 2 / pad 1 on an even-sized map: four pixel-parity planes per tile; needs the
+    // chunk-aligned fast epilogue (one tile per CTA, shared by the two epilogue groups)
+    if ((d->Hin | d->Win) & 1 || d->Hm * 2 != d->Hin || d->Wm * 2 != d->Win) return false;
+    if (!epi_fast_ok(d) || (d->Cout_store + 15) / 16 * 16 > 256) return false;
+  } else {
     return false;
+  }
   for (int t = 0; t < 9; ++t)
     if (d->tap_dy[t] != t / 3 - 1 || d->tap_dx[t] != t % 3 - 1) return false;
   if (d->Cin % 16 || d->in_ld % 8 || d->in_coff % 8 || d->out_ld % 8 || d->out_coff % 8 ||

@@ -47,7 +47,8 @@ constexpr int HL_STAGE_OUT = 2048;                        // per epilogue warp: 
 constexpr int HL_STAGE_BYTES = 8 * HL_STAGE_OUT;          // x out_slabs (1 or 2 slabs per warp)
 
 struct alignas(64) HaloParams {
-  CUtensorMap tmap_a;
+  CUtensorMap tmap_a;           // stride 1: the halo tile; stride 2: pixel-parity plane (even row, even col)
+  CUtensorMap tmap_a2[3];       // stride 2: planes (even, odd col), (odd row, even), (odd, odd)
   CUtensorMap tmap_b;
   CUtensorMap tmap_o;           // output (C, W, H, N), box 32 ch x 8 px x 4 rows, SWIZZLE_64B
   CUtensorMap tmap_r;           // residual (C, W, H, N), box BN ch x 8 px x 16 rows: L2 prefetch only
@@ -58,6 +59,13 @@ struct alignas(64) HaloParams {
   int nkb_seg, lo_off;          // split (BRTPE_DT_BF16X2): num_kb = 3 segments [hi | lo | hi] of
                                 // nkb_seg 64-channel blocks; the lo half starts lo_off channels in
   int a_stages, b_stages, b_stage_bytes, a_stage_bytes;
+  int s2_ld;                    // stride 2: input pixel stride (the second pixel of a column pair)
+  int s2;                       // 1: 3x3 / stride 2 (four pixel-parity planes per tile instead of one halo tile)
+  int a_tile_bytes;             // shared-memory bytes of one pixel tile's activations (1024-aligned)
+  int a_tx_bytes;               // bytes TMA delivers per pixel tile
+  int sub_off[4];               // stride 2: byte offset of the parity planes inside a tile
+  uint32_t tap_aoff[9];         // per tap: descriptor start offset inside the tile (bytes >> 4) ...
+  uint32_t tap_ahi[9];          // ... and descriptor high word (SBO = rows-of-8 pitch of the plane the tap reads)
   int tps, b_groups;            // taps per weight stage, stages per channel block (tps*b_groups = 9)
   int resident;                 // 1: all weights stay in smem for the whole kernel
   int cg;                       // 1: one CTA per MMA; 2: CTA pair (tcgen05 cta_group::2): M = 256 over
@@ -176,8 +184,11 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const fl
   // channel chunks [cbeg, cend)
   const int tile_sel = (p.tpc == 2) ? group : 0;
   const int allchunks = BN >> 4;
-  const int cbeg = (p.tpc == 2) ? 0 : group * (allchunks >> 1);
-  const int nchunks = (p.tpc == 2) ? allchunks : cbeg + (group == 0 ? (allchunks >> 1) : allchunks - (allchunks >> 1));
+  // one-tile mode: group 0 takes the chunks [0, csplit), group 1 [csplit, allchunks); csplit is even
+  // (chunks are drained in pairs, and a 32-channel TMA store must not straddle the two groups)
+  const int csplit = ((allchunks + 3) >> 2) << 1;
+  const int cbeg = (p.tpc == 2) ? 0 : (group == 0 ? 0 : (csplit < allchunks ? csplit : allchunks));
+  const int nchunks = (p.tpc == 2) ? allchunks : (group == 0 ? (csplit < allchunks ? csplit : allchunks) : allchunks);
   const int acc_stages = p.acc_stages;
   const int acc_cols = p.tpc * BN;
   const uint32_t bias_u32 = smem_u32(bias_s);
@@ -215,6 +226,14 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const fl
     HL_TIMED(10, mbar_wait(smem_u32(&tfull[acc]), accph));
     if (PROF) pc[11] += 1;
     tc_fence_after();
+    if (cbeg >= nchunks) {                             // this group has no chunk of the tile
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (remote) mbar_arrive_cluster(tempty_addr + 8u * acc);
+        else mbar_arrive(tempty_addr + 8u * acc);
+      }
+    }
 #pragma unroll 1
     for (int c0 = cbeg; c0 < nchunks; c0 += 4) {
       Chunk32 cur[4];
@@ -295,14 +314,15 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const fl
 // two pixel tiles: K16 MMAs per tap and tile, no branch between them.  Tap (kh, kw) reads the halo
 // tile through a descriptor advanced by (kh*PITCH + kw) rows of 128 B.
 template <int K16, bool CG2>
-__device__ __forceinline__ void halo_issue_taps(uint32_t d0, uint32_t d1, uint32_t a0, uint32_t a1,
-                                                uint32_t b_lo, uint32_t b_tap_lo, uint32_t a_hi,
-                                                uint32_t b_hi, uint32_t idesc, int tap0, int tps,
-                                                int tpc, uint32_t first_base) {
-  int kh = tap0 / 3, kw = tap0 - kh * 3;
+__device__ __forceinline__ void halo_issue_taps(const HaloParams& p, uint32_t d0, uint32_t d1,
+                                                uint32_t a0, uint32_t a1, uint32_t b_lo,
+                                                uint32_t b_tap_lo, uint32_t b_hi, uint32_t idesc,
+                                                int tap0, int tps, int tpc, uint32_t first_base) {
 #pragma unroll 1
   for (int t = 0; t < tps; ++t) {
-    const uint32_t a_off = (uint32_t)(((kh * HL_PITCH + kw) * 128) >> 4);
+    // stride 1: the tile read at (kh*PITCH + kw) rows of 128 B; stride 2: the tap's parity plane
+    const uint32_t a_off = p.tap_aoff[tap0 + t];
+    const uint32_t a_hi = p.tap_ahi[tap0 + t];
     const uint32_t bt = b_lo + (uint32_t)t * b_tap_lo;
     const uint32_t first = first_base | (uint32_t)t;
 #pragma unroll
@@ -317,7 +337,6 @@ __device__ __forceinline__ void halo_issue_taps(uint32_t d0, uint32_t d1, uint32
         else umma_f16_lohi(d1, a1 + a_off + 2u * k, a_hi, bt + 2u * k, b_hi, idesc, (first | (uint32_t)k) ? 1u : 0u);
       }
     }
-    if (++kw == 3) { kw = 0; ++kh; }
   }
 }
 
@@ -334,8 +353,11 @@ __device__ __forceinline__ void halo_epilogue_split(const HaloParams& p, const f
   const int BN = p.BN, n_tiles = p.n_tiles, num_items = p.num_items;
   const int tile_sel = (p.tpc == 2) ? group : 0;
   const int allchunks = BN >> 4;
-  const int cbeg = (p.tpc == 2) ? 0 : group * (allchunks >> 1);
-  const int nchunks = (p.tpc == 2) ? allchunks : cbeg + (group == 0 ? (allchunks >> 1) : allchunks - (allchunks >> 1));
+  // one-tile mode: group 0 takes the chunks [0, csplit), group 1 [csplit, allchunks); csplit is even
+  // (chunks are drained in pairs, and a 32-channel TMA store must not straddle the two groups)
+  const int csplit = ((allchunks + 3) >> 2) << 1;
+  const int cbeg = (p.tpc == 2) ? 0 : (group == 0 ? 0 : (csplit < allchunks ? csplit : allchunks));
+  const int nchunks = (p.tpc == 2) ? allchunks : (group == 0 ? (csplit < allchunks ? csplit : allchunks) : allchunks);
   const int acc_stages = p.acc_stages;
   const int acc_cols = p.tpc * BN;
   const uint32_t bias_u32 = smem_u32(bias_s);
@@ -353,6 +375,14 @@ __device__ __forceinline__ void halo_epilogue_split(const HaloParams& p, const f
                             (uint32_t)(acc * acc_cols + tile_sel * BN);
     mbar_wait(smem_u32(&tfull[acc]), accph);
     tc_fence_after();
+    if (cbeg >= nchunks) {                             // this group has no chunk of the tile
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (remote) mbar_arrive_cluster(tempty_addr + 8u * acc);
+        else mbar_arrive(tempty_addr + 8u * acc);
+      }
+    }
 #pragma unroll 1
     for (int c = cbeg; c < nchunks; c += 2) {
       const bool two = c + 1 < nchunks;
@@ -535,16 +565,28 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
           if (leader) mbar_arrive(fa);
         } else {
           const uint32_t dst = smem_u32(a_ring + (size_t)as_ * a_stage_bytes);
-          if (leader) mbar_expect_tx(fa, (uint32_t)(tpi * HL_A_BYTES));
-          if (cg2) {
-            const uint32_t fas = sig(&full_a[as_]);
+          if (leader) mbar_expect_tx(fa, (uint32_t)(tpi * p.a_tx_bytes));
+          const uint32_t fas = cg2 ? sig(&full_a[as_]) : fa;
+          if (p.s2) {
+            // the four pixel-parity planes of the (2*16+1) x (2*8+1) input window (tpc == 1): plane
+            // (rp, cp) holds input rows 2*j + rp, columns 2*i + cp; the odd planes start one
+            // element earlier (input row / column -1 = padding, zero-filled by TMA)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int rp = q >> 1, cp = q & 1;
+              const CUtensorMap* m = q == 0 ? &p.tmap_a : &p.tmap_a2[q - 1];
+              const int c0 = cp * p.s2_ld + ch0;
+              if (cg2) tma_load_5d_cg2(dst + (uint32_t)p.sub_off[q], m, fas, c0, o0.x0 - cp, rp, o0.y0 - rp, o0.n);
+              else tma_load_5d(dst + (uint32_t)p.sub_off[q], m, fas, c0, o0.x0 - cp, rp, o0.y0 - rp, o0.n);
+            }
+          } else if (cg2) {
             tma_load_5d_cg2(dst, &p.tmap_a, fas, ch0, o0.x0 - 1, 0, o0.y0 - 1, o0.n);
             if (tpc == 2)
-              tma_load_5d_cg2(dst + HL_A_TILE, &p.tmap_a, fas, ch0, o1.x0 - 1, 0, o1.y0 - 1, o1.n);
+              tma_load_5d_cg2(dst + (uint32_t)p.a_tile_bytes, &p.tmap_a, fas, ch0, o1.x0 - 1, 0, o1.y0 - 1, o1.n);
           } else {
             tma_load_5d(dst, &p.tmap_a, fa, ch0, o0.x0 - 1, 0, o0.y0 - 1, o0.n);
             if (tpc == 2)
-              tma_load_5d(dst + HL_A_TILE, &p.tmap_a, fa, ch0, o1.x0 - 1, 0, o1.y0 - 1, o1.n);
+              tma_load_5d(dst + (uint32_t)p.a_tile_bytes, &p.tmap_a, fa, ch0, o1.x0 - 1, 0, o1.y0 - 1, o1.n);
           }
         }
       }
@@ -622,12 +664,11 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
         it = 1;
         if (item0 + istep < num_items) skip_item();    // item 0 is the other warp's
       }
-      constexpr uint32_t A_HI = desc_hi(HL_PITCH * 128);
       constexpr uint32_t B_HI = desc_hi(1024);
       const uint32_t a_ring_lo = desc_lo(smem_u32(a_ring));
       const uint32_t b_ring_lo = desc_lo(smem_u32(b_ring));
       const uint32_t a_stage_lo = (uint32_t)(a_stage_bytes >> 4);
-      const uint32_t a_tile_lo = (uint32_t)(HL_A_TILE >> 4);
+      const uint32_t a_tile_lo = (uint32_t)(p.a_tile_bytes >> 4);
       const uint32_t b_stage_lo = (uint32_t)(b_stage_bytes >> 4);
       const uint32_t b_tap_lo = (uint32_t)((BNh * 128) >> 4);
       const bool no_mma = (dbg & 1) != 0;
@@ -668,10 +709,10 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
                 // at N = 48, 73.1 instead of 59.8 at N = 96; tools/exp_umma_seq.cu, profiles/r02_mma_issue.md)
                 const uint32_t first = (uint32_t)(kb | g);
                 switch (k16) {
-                  case 4: halo_issue_taps<4, cg2>(d0, d1, a0, a1, b_lo, b_tap_lo, A_HI, B_HI, idesc, g * tps, tps, tpc, first); break;
-                  case 3: halo_issue_taps<3, cg2>(d0, d1, a0, a1, b_lo, b_tap_lo, A_HI, B_HI, idesc, g * tps, tps, tpc, first); break;
-                  case 2: halo_issue_taps<2, cg2>(d0, d1, a0, a1, b_lo, b_tap_lo, A_HI, B_HI, idesc, g * tps, tps, tpc, first); break;
-                  default: halo_issue_taps<1, cg2>(d0, d1, a0, a1, b_lo, b_tap_lo, A_HI, B_HI, idesc, g * tps, tps, tpc, first); break;
+                  case 4: halo_issue_taps<4, cg2>(p, d0, d1, a0, a1, b_lo, b_tap_lo, B_HI, idesc, g * tps, tps, tpc, first); break;
+                  case 3: halo_issue_taps<3, cg2>(p, d0, d1, a0, a1, b_lo, b_tap_lo, B_HI, idesc, g * tps, tps, tpc, first); break;
+                  case 2: halo_issue_taps<2, cg2>(p, d0, d1, a0, a1, b_lo, b_tap_lo, B_HI, idesc, g * tps, tps, tpc, first); break;
+                  default: halo_issue_taps<1, cg2>(p, d0, d1, a0, a1, b_lo, b_tap_lo, B_HI, idesc, g * tps, tps, tpc, first); break;
                 }
               }
               if (!resident) {
@@ -897,7 +938,9 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
   P->res_encoded = nullptr;
   HaloParams& p = P->p;
   memset(&p, 0, sizeof(p));
-  p.N = d->N; p.H = d->Hin; p.W = d->Win;
+  p.s2 = d->in_stride == 2 ? 1 : 0;
+  p.s2_ld = d->in_ld;
+  p.N = d->N; p.H = d->Hm; p.W = d->Wm;             // tiles walk the OUTPUT pixels (== input for stride 1)
   p.tiles_x = ceil_div(p.W, HL_TW);
   p.tiles_y = ceil_div(p.H, HL_TH);
   p.m_tiles = p.tiles_x * p.tiles_y * p.N;
@@ -919,6 +962,16 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
     const int v = atoi(getenv("BRTPE_HALO_TPC"));
     if (v == 2 || (v == 1 && epi_fast_ok(d) && (cp0 / 16) % 2 == 0)) p.tpc = v;
   }
+  if (p.s2) {
+    // the input window of a stride-2 tile is 33 x 17 pixels (72 KB per 64-channel block): one tile
+    // per CTA and item; needs the fast epilogue (the two epilogue groups share the one tile)
+    if (!epi_fast_ok(d) || cp0 > HL_MAX_BN) {
+      delete P;
+      set_error("halo conv (stride 2): needs Cout == Cout_store <= %d, a multiple of 16", HL_MAX_BN);
+      return nullptr;
+    }
+    p.tpc = 1;
+  }
   const int tpi = p.tpc * p.cg;
   const int workers = num_sms() / p.cg;               // CTAs (cg 1) or CTA pairs (cg 2)
   const int pairs = ceil_div(p.m_tiles, tpi);         // work units of 2*cg pixel tiles
@@ -939,11 +992,6 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
   p.lo_off = d->in_ld / 2;
   p.in_coff = d->in_coff;
   p.dbg = getenv("BRTPE_HALO_DBG") ? atoi(getenv("BRTPE_HALO_DBG")) : 0;
-  if (p.tpc == 1 && (p.BN / 16) % 2 != 0) {        // the two epilogue groups split the chunks evenly
-    delete P;
-    set_error("halo conv: one-tile mode needs an even number of 16-channel chunks (BN %d)", p.BN);
-    return nullptr;
-  }
   p.acc_stages = (2 * p.tpc * p.BN <= 512) ? 2 : 1;
   int cols = 32;
   while (cols < p.acc_stages * p.tpc * p.BN) cols *= 2;
@@ -962,7 +1010,35 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
   if (split) p.tma_out = 0;                         // the split epilogue stores directly
   // two output slabs per epilogue warp unless that would push resident weights out / leave the
   // weight ring with fewer than two stages
-  p.a_stage_bytes = p.tpc * HL_A_TILE;
+  // activation tile in shared memory: stride 1 = the 18 x 10 halo tile; stride 2 = four parity planes
+  // (even/odd rows x even/odd columns) of 16|17 rows x 8|9 pixels, each 1024-aligned
+  if (p.s2) {
+    const int rows[2] = {HL_TH, HL_TH + 1}, cols[2] = {HL_TW, HL_TW + 1};
+    int off = 0;
+    p.a_tx_bytes = 0;
+    for (int q = 0; q < 4; ++q) {
+      p.sub_off[q] = off;
+      const int bytes = rows[q >> 1] * cols[q & 1] * 128;
+      p.a_tx_bytes += bytes;
+      off += (int)align_up((size_t)bytes, 1024);
+    }
+    p.a_tile_bytes = off;
+    for (int t = 0; t < 9; ++t) {
+      const int kh = t / 3, kw = t % 3;
+      const int q = ((kh != 1) ? 2 : 0) + ((kw != 1) ? 1 : 0);
+      const int pitch = cols[q & 1];
+      p.tap_aoff[t] = (uint32_t)((p.sub_off[q] + (((kh == 2) ? pitch : 0) + ((kw == 2) ? 1 : 0)) * 128) >> 4);
+      p.tap_ahi[t] = desc_hi((uint32_t)(pitch * 128));
+    }
+  } else {
+    p.a_tile_bytes = HL_A_TILE;
+    p.a_tx_bytes = HL_A_BYTES;
+    for (int t = 0; t < 9; ++t) {
+      p.tap_aoff[t] = (uint32_t)((((t / 3) * HL_PITCH + t % 3) * 128) >> 4);
+      p.tap_ahi[t] = desc_hi(HL_PITCH * 128);
+    }
+  }
+  p.a_stage_bytes = p.tpc * p.a_tile_bytes;
   const int A2 = 2 * p.a_stage_bytes;                 // the minimum: two activation stages
   p.out_slabs = 2;
   {
@@ -1057,14 +1133,30 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
 
   auto encode = halo_encode_fn();
   const cuuint64_t ld_b = (cuuint64_t)d->in_ld * 2;
-  cuuint64_t gdim[5] = {(cuuint64_t)(split ? d->in_ld : d->in_coff + d->Cin), (cuuint64_t)d->Win, 1,
-                        (cuuint64_t)d->Hin, (cuuint64_t)d->N};
-  cuuint64_t gstr[4] = {ld_b, ld_b * d->Win, ld_b * d->Win, ld_b * d->Win * d->Hin};
-  cuuint32_t box[5] = {64, (cuuint32_t)HL_PITCH, 1, (cuuint32_t)(HL_TH + 2), 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = encode(&p.tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), gdim,
-                      gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = CUDA_SUCCESS;
+  if (!p.s2) {
+    cuuint64_t gdim[5] = {(cuuint64_t)(split ? d->in_ld : d->in_coff + d->Cin), (cuuint64_t)d->Win, 1,
+                          (cuuint64_t)d->Hin, (cuuint64_t)d->N};
+    cuuint64_t gstr[4] = {ld_b, ld_b * d->Win, ld_b * d->Win, ld_b * d->Win * d->Hin};
+    cuuint32_t box[5] = {64, (cuuint32_t)HL_PITCH, 1, (cuuint32_t)(HL_TH + 2), 1};
+    r = encode(&p.tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), gdim, gstr, box,
+               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    // (channel of a column PAIR, W/2, row parity, H/2, N) view: coordinate (c + cp*ld, j, rp, i, n) is
+    // input pixel (row 2i + rp, column 2j + cp); one map per parity plane (the box sizes differ)
+    cuuint64_t gdim[5] = {(cuuint64_t)(split ? 2 * d->in_ld : d->in_ld + d->in_coff + d->Cin),
+                          (cuuint64_t)(d->Win / 2), 2, (cuuint64_t)(d->Hin / 2), (cuuint64_t)d->N};
+    cuuint64_t gstr[4] = {2 * ld_b, ld_b * d->Win, 2 * ld_b * d->Win, ld_b * d->Win * d->Hin};
+    for (int q = 0; q < 4 && r == CUDA_SUCCESS; ++q) {
+      cuuint32_t box[5] = {64, (cuuint32_t)(HL_TW + (q & 1)), 1, (cuuint32_t)(HL_TH + (q >> 1)), 1};
+      r = encode(q == 0 ? &p.tmap_a : &p.tmap_a2[q - 1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                 const_cast<void*>(in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+  }
   if (r != CUDA_SUCCESS) {
     set_error("halo conv: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
     delete P;

@@ -56,9 +56,25 @@ static int choose_engine(const brtpe_conv_desc* d) {
       const char* e = getenv("BRTPE_HALO_MIN_UTIL");
       min_util = e ? atoi(e) : 60;
     }
-    const long covered = (long)((d->Hm + 7) / 8 * 8) * ((d->Wm + 15) / 16 * 16);
+    const long covered = (long)((d->Hm + 15) / 16 * 16) * ((d->Wm + 7) / 8 * 8);
     const bool wasteful = 100L * d->Hm * d->Wm < (long)min_util * covered;
-    if (!(wasteful && ok && d->Cin >= 256 && d->Cout_store >= 256)) return BRTPE_ENGINE_UMMA_HALO;
+    if (d->in_stride == 2) {
+      // stride 2 (profiles/r02_halo_s2.md): the per-tap engine loads every input pixel 2.25 times; the
+      // parity-plane halo tile loads it once.  Measured at 64 images: 48 -> 96 @80x80 0.064 -> 0.049 ms,
+      // 48 -> 48 @80x80 0.052 -> 0.044 (both then at 70-75 % of the HBM roofline: the input is a
+      // 160 x 160 map), 64 -> 64 @160x160 +7 %, 256 -> 96 +2 %; wide layers on small maps lose
+      // (96 -> 192 @40x40 0.047 -> 0.065 ms: 72 KB activation stages leave two weight stages).
+      // BRTPE_HALO_S2: 0 = never, 1 = by this rule (default), 2 = whenever the layer is supported.
+      static int s2 = -1;
+      if (s2 < 0) {
+        const char* e = getenv("BRTPE_HALO_S2");
+        s2 = e ? atoi(e) : 1;
+      }
+      const bool wins = d->Cout_store <= 96 && (d->Cout_store <= 64 || d->Hm >= 64);
+      if (s2 == 2 || (s2 == 1 && wins && !(wasteful && ok))) return BRTPE_ENGINE_UMMA_HALO;
+    } else if (!(wasteful && ok && d->Cin >= 256 && d->Cout_store >= 256)) {
+      return BRTPE_ENGINE_UMMA_HALO;
+    }
   }
   if (d->engine == BRTPE_ENGINE_UMMA) {
     if (!ok) {

@@ -178,3 +178,33 @@ def test_split_fp32_per_tap_engine_and_many_items(cuda_device):
                   (9, 40, 40, 192, 192, 3, 1, True, True)]:
         got, ref, eng = run_conv_split(L.ENGINE_UMMA_HALO, *shape)
         assert eng == L.ENGINE_UMMA_HALO and _err(got, ref) <= 3e-5
+
+
+# ---- 3x3 / stride 2 on the halo engine: four pixel-parity planes per tile (one input load per pixel)
+HALO_S2_SHAPES = [
+    # n, h, w, cin, cout, k, stride, relu, res   (h, w = INPUT size)
+    (2, 64, 64, 48, 96, 3, 2, True, False),
+    (2, 64, 96, 48, 48, 3, 2, False, False),
+    (3, 80, 80, 96, 192, 3, 2, True, False),
+    (1, 160, 160, 64, 64, 3, 2, True, False),
+    (2, 64, 64, 256, 96, 3, 2, True, False),
+    (2, 80, 80, 48, 192, 3, 2, False, True),
+    (5, 32, 48, 192, 256, 3, 2, True, False),
+    (1, 34 * 2, 22 * 2, 48, 48, 3, 2, True, True),      # ragged tiles: 34 x 22 output pixels
+    (7, 160, 144, 48, 96, 3, 2, True, False),           # more work items than SMs
+]
+
+
+@pytest.mark.parametrize("shape", HALO_S2_SHAPES)
+def test_umma_halo_stride2_bf16(cuda_device, shape):
+    got, ref, eng = run_conv(L.ENGINE_UMMA_HALO, "bf16", *shape)
+    assert eng == L.ENGINE_UMMA_HALO
+    assert torch.isfinite(got).all()
+    assert _err(got, ref) <= 6e-3
+
+
+@pytest.mark.parametrize("shape", HALO_S2_SHAPES[:6])
+def test_umma_halo_stride2_split_fp32(cuda_device, shape):
+    got, ref, eng = run_conv_split(L.ENGINE_UMMA_HALO, *shape)
+    assert eng == L.ENGINE_UMMA_HALO
+    assert _err(got, ref) <= 3e-5
