@@ -320,6 +320,57 @@ def conv_rooflines(net, chunk, size, in_dtype, peaks, mode):
     return roofline, other, ms_ops
 
 
+def config3_leg(args, rank, world, dev, pipe, net, parser):
+    """BASELINE.json configs[2] (legacy/valid_ae_avg.py:159-205): synthetic batch 256 sharded over
+    the ranks (inference.shard_range), scales 2.0 / 1.0 / 0.5 (inputs 1280^2 / 640^2 / 320^2,
+    transforms.py:155-176 with min_scale 0.5), flip test, projection to 640 x 640, T = 2, AE grouping.
+    STRONG scaling: the job is the same 256 images whatever N.  Device-resident, timed with CUDA
+    events, max over ranks; the per-rank results are all-gathered once per batch."""
+    import torch.distributed as dist
+    from rtpe_b200 import inference
+    total, sub, size = 256, 32, args.size
+    lo, hi = inference.shard_range(total, rank, world)
+    shard = hi - lo
+    g = torch.Generator().manual_seed(100 + rank)
+    xs = [(sc, torch.randn(sub, 3, int(size * sc), int(size * sc), generator=g).to(dev))
+          for sc in (2.0, 1.0, 0.5)]
+    gatherer = inference.ResultGatherer()
+    pcap = parser.person_capacity
+
+    def one_batch():
+        outs = []
+        for s0 in range(0, shard, sub):                 # the shard in passes of `sub` images
+            det, tag = pipe.forward_aggregate_multiscale(xs, (size, size))
+            ans, count, scores = parser.decode_device(det, tag, True, True, full_capacity=True)
+            outs.append(inference.pack_results(*inference.pad_results(ans, count, scores, pcap)))
+        payload = torch.cat(outs, 0) if len(outs) > 1 else outs[0]
+        out, ev = gatherer.gather(payload)
+        torch.cuda.current_stream(dev).wait_event(ev)
+        return out
+
+    one_batch()
+    dist.barrier()
+    torch.cuda.synchronize()
+    reps = 2
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = one_batch()
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    people = float(out[:, 0].contiguous().view(torch.int32).float().mean().item())
+    return {"workload": "configs[2]: batch 256 synthetic 640x640 sharded %d per GPU, scales 2.0/1.0/0.5 "
+                        "+ flip test, projected to 640x640 (T=2), decode; %d images per pass" % (shard, sub),
+            "scaling": "strong", "n_gpus": world, "images": total, "ms_per_batch": ms,
+            "value": total / (ms * 1e-3), "unit": "images/s", "per_gpu": total / (ms * 1e-3) / world,
+            "forward_tflops_effective": 2 * (4 + 1 + 0.25) * FLOP_PER_FORWARD_640 * total / (ms * 1e-3) / 1e12,
+            "people_per_image": people, "gathered_rows": int(out.shape[0])}
+
+
 def fp32_leg(args, dev, x_dev, ref, peaks):
     """configs[1] names bf16 AND fp32: the same step with float32 parameters (split-bf16 tcgen05
     path, <= 1e-4), measured next to the bf16 headline and checked against the CPU leg."""
@@ -371,6 +422,7 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cores = inference.pin_to_gpu_numa(local_rank)   # host threads next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -391,19 +443,36 @@ def run_ours(args, rank, world, local_rank):
     x_dev = x_host.to(dev)
     pcap = parser.person_capacity
 
+    # The only collective: ONE packed all-gather of the padded per-image results per step, on a side
+    # stream, so that it overlaps the next step's network; the gathered tensor stays on the device,
+    # every rank copies only its own shard to the host (d2h bytes per rank do not grow with N).
+    gatherer = inference.ResultGatherer() if world > 1 else None
+    pending = {"ev": None, "slot": 0}
+
+    def gather_async(ans, count, scores):
+        if gatherer is None:
+            return
+        if pending["ev"] is not None:          # the previous step's gather (other slot) must be done
+            torch.cuda.current_stream(dev).wait_event(pending["ev"])
+        _, pending["ev"] = gatherer.gather(inference.pack_results(ans, count, scores), pending["slot"])
+        pending["slot"] ^= 1
+
+    def gather_drain():
+        if pending["ev"] is not None:
+            torch.cuda.current_stream(dev).wait_event(pending["ev"])
+            pending["ev"] = None
+
     def step_device():
         ans, count, scores = pipe.run_device(x_dev, True, True)
         ans, count, scores = inference.pad_results(ans, count, scores, pcap)
-        if world > 1:
-            ans, count, scores = inference.gather_results(ans, count, scores)
+        gather_async(ans, count, scores)
         return ans, count, scores
 
     host_out = {}
 
     def finish_e2e(ans, count, scores):
         ans, count, scores = inference.pad_results(ans, count, scores, pcap)
-        if world > 1:
-            ans, count, scores = inference.gather_results(ans, count, scores)
+        gather_async(ans, count, scores)
         for k, t in (("ans", ans), ("count", count), ("scores", scores)):
             if k not in host_out:
                 host_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
@@ -415,6 +484,7 @@ def run_ours(args, rank, world, local_rank):
         results back to pinned host memory."""
         for ans, count, scores in pipe.run_stream((x_host for _ in range(nsteps)), True, True):
             finish_e2e(ans, count, scores)
+        gather_drain()
 
     def timed(fn, steps, warmup, sample_clocks):
         sampler = ClockSampler(local_rank) if sample_clocks else None
@@ -430,6 +500,7 @@ def run_ours(args, rank, world, local_rank):
         e0.record()
         for _ in range(steps):
             fn()
+        gather_drain()                     # the last step's gather belongs to the timed region
         e1.record()
         torch.cuda.synchronize()
         t_wall1 = time.time()
@@ -458,6 +529,7 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms_e2e = float(ms_t.item())
     ans, count, scores = step_device()
+    gather_drain()
     torch.cuda.synchronize()
     people_mean = float(count.float().mean().item())
 
@@ -564,6 +636,10 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and args.mode == "bf16" and not args.no_fp32:
         fp32 = fp32_leg(args, dev, x_dev, ref if parity else None, peaks)
 
+    config3 = None
+    if world > 1 and args.mode == "bf16" and not args.no_config3:
+        config3 = config3_leg(args, rank, world, dev, pipe, net, parser)
+
     if rank == 0:
         h2d = x_host.numel() * x_host.element_size()
         d2h = sum(v.numel() * v.element_size() for v in host_out.values())
@@ -578,7 +654,8 @@ def run_ours(args, rank, world, local_rank):
             "roofline_other_convs": roofline_other,
             "roofline_decode": roofline_decode, "cpu_baseline": cpu_baseline,
             "parity_checked": bool(parity and parity["float_ok"] and parity["decode_bit_exact"]),
-            "parity": parity, "fp32": fp32,
+            "parity": parity, "fp32": fp32, "config3": config3,
+            "host": {"numa_cores_bound": numa_cores, "cpu_count": os.cpu_count()},
             "forward_tflops_effective": 2 * args.batch * world * args.steps *
             FLOP_PER_FORWARD_640 * (args.size / 640.0) ** 2 / (ms_dev * 1e-3) / 1e12,
             "people_per_image": people_mean,
@@ -601,6 +678,8 @@ def main():
                     help="forwards per plan replay (64 = the whole flip-test batch in one CUDA graph)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-mode leg of the bf16 line")
+    ap.add_argument("--no-config3", action="store_true",
+                    help="skip the multi-scale batch-256 leg (BASELINE configs[2]) of multi-GPU runs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -274,17 +274,26 @@ class HeatmapParser(object):
         return keypoints
 
     # ------------------------------------------------------------------ parse
-    def decode_device(self, det, tag, adjust=True, refine=True):
-        """Whole decode on the device, no host sync except a possible capacity retry.
-        -> ans (N,Pmax,J,3+T) f32, count (N) i32, scores (N,Pmax) f32 (all CUDA)."""
+    def decode_device(self, det, tag, adjust=True, refine=True, full_capacity=False):
+        """Whole decode on the device.
+        -> ans (N,Pmax,J,3+T) f32, count (N) i32, scores (N,Pmax) f32 (all CUDA).
+        ``full_capacity=False``: the person lists are sized ``person_capacity`` and the capacity
+        flag is read once at the end (ONE host sync per decode; an overflow re-runs with J*K).
+        ``full_capacity=True``: the lists are sized J*K = the reference's own bound (173 KB per image
+        at T = 2), nothing can overflow and the call never synchronises with the host -- what the
+        device-resident pipeline uses, so that decode(i) can be enqueued behind forward(i+1)."""
         lib = L.load()
         dev = det.device
         n, j, h, w = det.shape
         val_k, ind_k, _, tag_k = self.top_k_device(det, tag)
-        # optimistic: everything is enqueued for the default person capacity and the capacity
-        # flag is read once at the end (one host sync per decode, after the last launch, instead
-        # of one in the middle that left the GPU waiting for the remaining launches)
-        ans, count, pmax, flag = self.match_device(val_k, ind_k, tag_k, w, defer_overflow=True)
+        if full_capacity:
+            ans, count, pmax = self.match_device(val_k, ind_k, tag_k, w, pmax=self._pmax_full())
+            flag = None
+        else:
+            # optimistic: everything is enqueued for the default person capacity and the capacity
+            # flag is read once at the end (after the last launch, instead of a sync in the middle
+            # that left the GPU waiting for the remaining launches)
+            ans, count, pmax, flag = self.match_device(val_k, ind_k, tag_k, w, defer_overflow=True)
         while True:
             if adjust:
                 self.adjust_device(ans, count, det)

@@ -186,10 +186,10 @@ class TeacherPipeline:
 
     @torch.no_grad()
     def run_device(self, x, adjust=True, refine=True):
-        """-> ans (N,Pmax,J,3+T), count (N), scores (N,Pmax): CUDA tensors, no host sync
-        besides the parser's capacity check."""
+        """-> ans (N,Pmax,J,3+T), count (N), scores (N,Pmax): CUDA tensors, Pmax = J*K (the
+        reference's bound), NO host synchronisation."""
         det, tag = self.forward_aggregate(x)
-        return self.parser.decode_device(det, tag, adjust, refine)
+        return self.parser.decode_device(det, tag, adjust, refine, full_capacity=True)
 
     @torch.no_grad()
     def run_stream(self, host_batches, adjust=True, refine=True, early_images=None):
@@ -209,9 +209,18 @@ class TeacherPipeline:
         if early_images is None and "BRTPE_EARLY_IMAGES" in os.environ:
             early_images = int(os.environ["BRTPE_EARLY_IMAGES"])
         dev = torch.device("cuda", torch.cuda.current_device())
-        copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
-        bufs = [None, None]                    # device input buffers (allocated on first use)
+        # the copy stream and the two device input buffers belong to the pipeline, not to one call
+        # of this generator: a buffer handed back to the caching allocator could be given to other
+        # main-stream work that is still pending when the next call's first side-stream copy lands
+        if getattr(self, "_copy_stream", None) is None or self._copy_stream.device != dev:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._in_bufs = [None, None]
+        copy_stream = self._copy_stream
+        bufs = self._in_bufs
+        # the first copy has no event to wait for: order the whole copy stream after everything
+        # already enqueued on the main stream (the last readers of the buffers included)
+        copy_stream.wait_stream(main)
         state = {"k": 0}
 
         def stage_part(k, xh, lo, hi, after):
@@ -268,7 +277,7 @@ class TeacherPipeline:
                 nxt[0] = (pending["k"], pending["evs"])
 
             det, tag = self.forward_aggregate(bufs[k], after_forward=stage_next)
-            yield self.parser.decode_device(det, tag, adjust, refine)
+            yield self.parser.decode_device(det, tag, adjust, refine, full_capacity=True)
 
     @torch.no_grad()
     def run(self, x, adjust=True, refine=True):
@@ -315,14 +324,98 @@ def pad_results(ans, count, scores, pcap):
     return a.contiguous(), count.contiguous(), s.contiguous()
 
 
+def pack_results(ans, count, scores):
+    """(ans (N,P,J,3+T) f32, count (N) i32, scores (N,P) f32) -> ONE float32 payload (N, 1 + P +
+    P*J*(3+T)) per image: [count (the int32 bit pattern) | scores | people], so that the final
+    gather is a single collective."""
+    n = ans.shape[0]
+    return torch.cat((count.contiguous().view(torch.float32).view(n, 1), scores.reshape(n, -1),
+                      ans.reshape(n, -1)), dim=1).contiguous()
+
+
+def unpack_payload(payload, pcap, num_joints, width):
+    """inverse of ``pack_results`` -> (ans, count, scores) views of the payload."""
+    n = payload.shape[0]
+    count = payload[:, 0].contiguous().view(torch.int32)
+    scores = payload[:, 1:1 + pcap]
+    ans = payload[:, 1 + pcap:].view(n, pcap, num_joints, width)
+    return ans, count, scores
+
+
+class ResultGatherer:
+    """The only collective of the data-parallel path: ONE all-gather of the packed
+    per-image results per batch, issued on a side stream so that it overlaps the next batch's
+    network (NCCL on GPUs; gloo in the CPU tests, where streams do not exist).  The gathered tensor
+    stays where it is -- nobody copies it to the host implicitly; every rank keeps (and may copy
+    out) its own shard."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.stream = None
+        self._out = {}
+
+    def _buffer(self, payload, slot):
+        key = (slot, tuple(payload.shape), payload.dtype, payload.device)
+        buf = self._out.get(key)
+        if buf is None:
+            buf = torch.empty((self.world * payload.shape[0],) + tuple(payload.shape[1:]),
+                              dtype=payload.dtype, device=payload.device)
+            self._out[key] = buf
+        return buf
+
+    def gather(self, payload, slot=0):
+        """-> (gathered (world*N, ...) in rank order, event or None).  On CUDA the collective runs
+        on the gatherer's side stream after everything enqueued on the current stream so far; the
+        caller waits for the returned event (``torch.cuda.current_stream().wait_event``) before it
+        reads ``gathered`` or re-uses ``payload`` / the same ``slot``."""
+        out = self._buffer(payload, slot)
+        if not payload.is_cuda:
+            self.dist.all_gather_into_tensor(out, payload.contiguous(), group=self.group)
+            return out, None
+        dev = payload.device
+        if self.stream is None:
+            self.stream = torch.cuda.Stream(device=dev)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        payload.record_stream(self.stream)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            self.dist.all_gather_into_tensor(out, payload, group=self.group)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        return out, done
+
+
 def gather_results(ans, count, scores, group=None):
-    """all_gather of equally shaped per-rank results (NCCL on GPUs, gloo in the CPU tests).
+    """Blocking form: one packed all-gather of equally shaped per-rank results.
     -> concatenated (ans, count, scores) in rank order on every rank."""
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    outs = []
-    for t in (ans, count, scores):
-        bufs = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(bufs, t.contiguous(), group=group)
-        outs.append(torch.cat(bufs, 0))
-    return tuple(outs)
+    g = ResultGatherer(group)
+    payload = pack_results(ans, count, scores)
+    out, done = g.gather(payload)
+    if done is not None:
+        torch.cuda.current_stream(payload.device).wait_event(done)
+    return unpack_payload(out, ans.shape[1], ans.shape[2], ans.shape[3])
+
+
+def pin_to_gpu_numa(device_index):
+    """Bind this process to the CPU cores next to its GPU (NVML's ideal CPU affinity = the GPU's
+    NUMA node): eight ranks that each stream 157 MB per step from pinned host memory should not
+    cross the socket interconnect.  Best effort: returns the number of cores bound, or 0."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cores = [c for c in cores if c in allowed]
+        if cores:
+            os.sched_setaffinity(0, cores)
+            return len(cores)
+    except Exception:
+        pass
+    return 0

@@ -78,3 +78,19 @@ def test_gather_world2_gloo(tmp_path):
     res = inference.unpack_results(torch.from_numpy(z["a"]), torch.from_numpy(z["c"]),
                                    torch.from_numpy(z["s"]))
     assert [r[0].shape[0] if r[0].size else 0 for r in res] == [g % 4 for g in range(total)]
+
+
+def test_pack_results_round_trip():
+    ans = torch.randn(3, 5, 17, 5)
+    count = torch.tensor([5, 0, 2], dtype=torch.int32)
+    scores = torch.rand(3, 5)
+    payload = inference.pack_results(ans, count, scores)
+    assert payload.shape == (3, 1 + 5 + 5 * 17 * 5) and payload.dtype == torch.float32
+    a, c, s = inference.unpack_payload(payload, 5, 17, 5)
+    assert torch.equal(a, ans) and torch.equal(c, count) and torch.equal(s, scores)
+
+
+def test_pin_to_gpu_numa_is_best_effort():
+    before = os.sched_getaffinity(0)
+    n = inference.pin_to_gpu_numa(0)            # no GPU here: must not raise, must not change anything
+    assert n == 0 and os.sched_getaffinity(0) == before
