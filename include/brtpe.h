@@ -191,6 +191,17 @@ typedef struct brtpe_conv_desc {
   int32_t res_ld, res_coff;   /* residual tensor has the output's (N,Hout,Wout) geometry */
   int32_t relu;
   int32_t Cout_store;     /* channels written per pixel (>= Cout; extra ones get 0)     */
+  /* HRNet cross-resolution fuse-add in the epilogue (HighResolutionModule.forward,
+   * pose_higher_hrnet.py:245-254: y_i = relu(sum_j f_ij(x_j))): up to three extra addends, term k a
+   * (N, Hout >> add_shift[k], Wout >> add_shift[k], add_ld[k]) tensor of Cout channels read with
+   * nearest-neighbour upsampling (nn.Upsample(scale_factor=2^shift), :202-209).
+   *   out2_ld == 0:  out  = act(conv + bias + residual + sum_k up(add_k))
+   *   out2_ld  > 0:  out  = act(conv + bias + residual)            (the branch output x_i)
+   *                  out2 = relu(out + sum_k up(add_k))             (the fused output y_i)
+   * tcgen05 engines only, whole 16-channel chunks (Cout == Cout_store, a multiple of 16). */
+  int32_t n_add;
+  int32_t add_ld[3], add_shift[3];
+  int32_t out2_ld;
 } brtpe_conv_desc;
 
 /* FFMA path weights: float32 [ntaps][Cin][Cout].  UMMA path weights: bf16
@@ -198,6 +209,12 @@ typedef struct brtpe_conv_desc {
  * bias: float32 [Cout] (may be NULL).  residual may be NULL. */
 int brtpe_conv_run(const brtpe_conv_desc* d, const void* in, const void* weights,
                    const float* bias, const void* residual, void* out, void* stream);
+
+/* brtpe_conv_run for a descriptor with fuse addends: add_ptrs[n_add] device tensors, out2 the second
+ * output (NULL unless out2_ld > 0). */
+int brtpe_conv_run_fused(const brtpe_conv_desc* d, const void* in, const void* weights,
+                         const float* bias, const void* residual, void* out,
+                         const void* const* add_ptrs, void* out2, void* stream);
 
 /* Engine brtpe_conv_run / brtpe_plan_add_conv will use for this descriptor
  * (BRTPE_ENGINE_FFMA, BRTPE_ENGINE_UMMA or BRTPE_ENGINE_UMMA_HALO), or a negative error code. */
@@ -277,6 +294,8 @@ void brtpe_plan_destroy(brtpe_plan*);
 int brtpe_plan_add_conv(brtpe_plan*, const brtpe_conv_desc* d, const void* in,
                         const void* weights, const float* bias, const void* residual,
                         void* out);
+/* addend tensors / second output of the conv op added last (descriptor with n_add > 0) */
+int brtpe_plan_set_conv_fuse(brtpe_plan*, const void* const* add_ptrs, void* out2);
 int brtpe_plan_add_stem(brtpe_plan*, const void* img, int img_is_half, int N, int H, int W,
                         const float* w, const float* bias, int Cout, void* out, int out_dtype);
 int brtpe_plan_add_fuse(brtpe_plan*, int dtype, int nterms, const void* const* terms,

@@ -48,7 +48,9 @@ class ConvDesc(C.Structure):
                 ("out_oy", C.c_int32), ("out_ox", C.c_int32), ("Cout", C.c_int32),
                 ("out_ld", C.c_int32), ("out_coff", C.c_int32),
                 ("res_ld", C.c_int32), ("res_coff", C.c_int32),
-                ("relu", C.c_int32), ("Cout_store", C.c_int32)]
+                ("relu", C.c_int32), ("Cout_store", C.c_int32),
+                ("n_add", C.c_int32), ("add_ld", C.c_int32 * 3), ("add_shift", C.c_int32 * 3),
+                ("out2_ld", C.c_int32)]
 
 
 class PrepackDesc(C.Structure):
@@ -89,6 +91,8 @@ _SIGS = {
     "brtpe_aggregate_scale": (_I, [_P, _P, _P, _P] + [_I] * 9 + [C.POINTER(C.c_int32), _I,
                                                                  C.c_float, _P, _P, _P]),
     "brtpe_conv_run": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
+    "brtpe_conv_run_fused": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, C.POINTER(_P), _P, _P]),
+    "brtpe_plan_set_conv_fuse": (_I, [_P, C.POINTER(_P), _P]),
     "brtpe_conv_select_engine": (_I, [C.POINTER(ConvDesc)]),
     "brtpe_umma_weight_dims": (_I, [_I, _I, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "brtpe_prepack_weights": (_I, [C.POINTER(PrepackDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),

@@ -15,7 +15,7 @@ bool umma_conv_supported(const brtpe_conv_desc* d, const char** why);
 UmmaConvPrepared* umma_conv_prepare(const brtpe_conv_desc* d, const void* in, const void* weights);
 void umma_conv_release(UmmaConvPrepared*);
 int umma_conv_launch(const UmmaConvPrepared* p, const float* bias, const void* residual, void* out,
-                     cudaStream_t st);
+                     cudaStream_t st, const void* const* add_ptrs = nullptr, void* out2 = nullptr);
 
 // ---- tcgen05 halo-tile back end for 3x3 stride-1 convs (conv_halo.cu)
 struct HaloConvPrepared;
@@ -24,7 +24,7 @@ HaloConvPrepared* halo_conv_prepare(const brtpe_conv_desc* d, const void* in, co
                                     void* out);
 void halo_conv_release(HaloConvPrepared*);
 int halo_conv_launch(const HaloConvPrepared* p, const float* bias, const void* residual, void* out,
-                     cudaStream_t st);
+                     cudaStream_t st, const void* const* add_ptrs = nullptr, void* out2 = nullptr);
 
 int stem_conv1_launch(const void* img, int img_is_half, int N, int H, int W, const float* w,
                       const float* bias, int Cout, void* out, int out_dtype, cudaStream_t st);

@@ -28,6 +28,12 @@ struct EpiParams {
   int fast;                       // 1: vec32 and Cout == Cout_store is a multiple of 16
   int split;                      // 1: BRTPE_DT_BF16X2 activations (hi / lo bf16 pairs)
   int out_lo, res_lo;             // split: element offset of the lo half inside a pixel (ld / 2)
+  // HRNet fuse addends (brtpe_conv_desc.n_add): term k read at (y >> shift, x >> shift)
+  const __nv_bfloat16* add[3];
+  int add_ld[3], add_shift[3], n_add;
+  int Hout, Wout;                 // output tensor geometry (addend indexing)
+  __nv_bfloat16* out2;            // second output (fused y_i) or nullptr
+  int out2_ld;
 };
 
 // q = x / d for 0 <= x < 2^32 / d  (mul = floor(2^32 / d) + 1; mul == 0 selects plain division)
@@ -123,6 +129,80 @@ __device__ __forceinline__ void tmem_ld16_lo(uint32_t taddr, uint32_t (&r)[32]) 
       : "memory");
 }
 
+// sum of the fuse addends of one 16-channel chunk at output pixel (n, y, x), channel co
+template <int K0 = 0>
+__device__ __forceinline__ void epi_terms16(const EpiParams& e, int n, int y, int x, int co,
+                                            float (&s)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s[i] = 0.0f;
+#pragma unroll
+  for (int k = K0; k < 3; ++k) {
+    if (k < e.n_add) {
+      const int sh = e.add_shift[k];
+      const size_t pix = ((size_t)n * (e.Hout >> sh) + (size_t)(y >> sh)) * (size_t)(e.Wout >> sh) +
+                         (size_t)(x >> sh);
+      const Chunk32 c = ld_chunk32(e.add[k] + pix * e.add_ld[k] + co, true);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[2 * i] += bf16lo(c.w[i]);
+        s[2 * i + 1] += bf16hi(c.w[i]);
+      }
+    }
+  }
+}
+// address of addend k's chunk for output pixel (n, y, x)
+__device__ __forceinline__ const __nv_bfloat16* epi_term_ptr(const EpiParams& e, int k, int n, int y,
+                                                             int x, int co) {
+  const int sh = e.add_shift[k];
+  const size_t pix = ((size_t)n * (e.Hout >> sh) + (size_t)(y >> sh)) * (size_t)(e.Wout >> sh) +
+                     (size_t)(x >> sh);
+  return e.add[k] + pix * e.add_ld[k] + co;
+}
+// s += the 16 bf16 values of a prefetched addend chunk
+__device__ __forceinline__ void epi_acc_chunk(float (&s)[16], const Chunk32& c) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s[2 * i] += bf16lo(c.w[i]);
+    s[2 * i + 1] += bf16hi(c.w[i]);
+  }
+}
+// single-output form: the addends join the accumulator (out = act(acc + sum + bias + res))
+template <int OFF>
+__device__ __forceinline__ void epi_add_terms(uint32_t (&a)[32], const float (&s)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[OFF + i] = __float_as_uint(__uint_as_float(a[OFF + i]) + s[i]);
+}
+// two-output form: op gets x = act(acc + bias + res) (the branch output), op2 gets relu(x + sum)
+template <bool RES, bool RELU, int OFF>
+__device__ __forceinline__ void epi_dual_chunk(const uint32_t (&a)[32], uint32_t bias16_smem,
+                                               const Chunk32& rc, const float (&s)[16],
+                                               __nv_bfloat16* op, __nv_bfloat16* op2) {
+  Chunk32 oc, oc2;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float4 b;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+        : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "r"(bias16_smem + 16u * q));
+    float v[4] = {__uint_as_float(a[OFF + 4 * q]) + b.x, __uint_as_float(a[OFF + 4 * q + 1]) + b.y,
+                  __uint_as_float(a[OFF + 4 * q + 2]) + b.z, __uint_as_float(a[OFF + 4 * q + 3]) + b.w};
+    if (RES) {
+      v[0] += bf16lo(rc.w[2 * q]); v[1] += bf16hi(rc.w[2 * q]);
+      v[2] += bf16lo(rc.w[2 * q + 1]); v[3] += bf16hi(rc.w[2 * q + 1]);
+    }
+    if (RELU) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.0f);
+    }
+    oc.w[2 * q] = pack_bf16x2(v[0], v[1]);
+    oc.w[2 * q + 1] = pack_bf16x2(v[2], v[3]);
+    oc2.w[2 * q] = pack_bf16x2_act<true>(v[0] + s[4 * q], v[1] + s[4 * q + 1]);
+    oc2.w[2 * q + 1] = pack_bf16x2_act<true>(v[2] + s[4 * q + 2], v[3] + s[4 * q + 3]);
+  }
+  st_chunk32(op, oc, true);
+  st_chunk32(op2, oc2, true);
+}
+
 // one 16-channel chunk: acc (16 raw fp32 words at a[OFF..OFF+15]) + bias + residual -> out
 template <bool RES, bool RELU, int OFF>
 __device__ __forceinline__ void epi_fast_chunk(const uint32_t (&a)[32], uint32_t bias16_smem,
@@ -173,11 +253,12 @@ __device__ __forceinline__ void epi_pack_chunk(const uint32_t (&a)[32], uint32_t
 
 // Waits for the accumulator (tfull_bar / parity), drains it and arrives on `arrive_bar`
 // (tmem_empty, one lane per warp) as soon as the last TMEM read of the tile has completed.
-template <bool RES, bool RELU>
+template <bool RES, bool RELU, bool ADD = false>
 __device__ __forceinline__ void epi_fast(const EpiParams& e, const float* __restrict__ bias_s,
                                          uint32_t t_addr, int nchunks, int co0, bool valid,
                                          size_t opix, uint32_t tfull_bar, uint32_t tfull_parity,
-                                         uint32_t arrive_bar, int lane) {
+                                         uint32_t arrive_bar, int lane, int pn = 0, int py = 0,
+                                         int px = 0) {
   const __nv_bfloat16* rp = RES ? e.res + opix * e.res_ld + e.res_coff + co0 : nullptr;
   __nv_bfloat16* op = e.out + opix * e.out_ld + e.out_coff + co0;
   const uint32_t bias_u32 = smem_u32(bias_s);
@@ -209,6 +290,15 @@ __device__ __forceinline__ void epi_fast(const EpiParams& e, const float* __rest
     }
     if (valid) {
       const uint32_t bs = bias_u32 + (uint32_t)((co0 + c * 16) * 4);
+      if (ADD) {                                   // HRNet fuse addends (nearest-upsampled terms)
+        float s[16];
+        epi_terms16(e, pn, py, px, co0 + c * 16, s);
+        epi_add_terms<0>(a, s);
+        if (two) {
+          epi_terms16(e, pn, py, px, co0 + c * 16 + 16, s);
+          epi_add_terms<16>(a, s);
+        }
+      }
       epi_fast_chunk<RES, RELU, 0>(a, bs, r0, op + c * 16);
       if (two) epi_fast_chunk<RES, RELU, 16>(a, bs + 64u, r1, op + c * 16 + 16);
     }
@@ -398,6 +488,20 @@ __device__ __forceinline__ void epi_tile(const EpiParams& e, const float* __rest
   }
 }
 
+// Dispatch of the kernels with HRNet fuse addends (fast-path layers only, checked at prepare)
+__device__ __forceinline__ void epi_tile_add(const EpiParams& e, const float* __restrict__ bias_s,
+                                             uint32_t t_addr, int nchunks, int co0, bool valid,
+                                             size_t opix, uint32_t tfull_bar, uint32_t tfull_parity,
+                                             uint32_t arrive_bar, int lane, int pn, int py, int px) {
+  if (e.res != nullptr) {
+    if (e.relu) epi_fast<true, true, true>(e, bias_s, t_addr, nchunks, co0, valid, opix, tfull_bar, tfull_parity, arrive_bar, lane, pn, py, px);
+    else epi_fast<true, false, true>(e, bias_s, t_addr, nchunks, co0, valid, opix, tfull_bar, tfull_parity, arrive_bar, lane, pn, py, px);
+  } else {
+    if (e.relu) epi_fast<false, true, true>(e, bias_s, t_addr, nchunks, co0, valid, opix, tfull_bar, tfull_parity, arrive_bar, lane, pn, py, px);
+    else epi_fast<false, false, true>(e, bias_s, t_addr, nchunks, co0, valid, opix, tfull_bar, tfull_parity, arrive_bar, lane, pn, py, px);
+  }
+}
+
 // Dispatch of the split (BRTPE_DT_BF16X2) kernels: split layers always satisfy the fast-path
 // conditions (checked at prepare).
 __device__ __forceinline__ void epi_tile_split(const EpiParams& e, const float* __restrict__ bias_s,
@@ -426,6 +530,28 @@ static inline bool conv_is_split(const brtpe_conv_desc* d) { return d->dtype == 
 static inline int epi_split_ok(const brtpe_conv_desc* d) {
   return (epi_fast_ok(d) && d->out_ld % 32 == 0 && d->res_ld % 32 == 0 && d->in_ld % 32 == 0 &&
           d->in_coff % 8 == 0) ? 1 : 0;
+}
+// fuse addends need the fast epilogue, 32-byte aligned chunks in every addend and shifts that
+// divide the output size
+static inline bool epi_add_ok(const brtpe_conv_desc* d) {
+  if (d->n_add == 0 && d->out2_ld == 0) return true;
+  if (d->n_add < 0 || d->n_add > 3 || !epi_fast_ok(d) || d->dtype != BRTPE_DT_BF16) return false;
+  if (d->out2_ld && (d->out2_ld % 16 || d->out2_ld < d->Cout)) return false;
+  for (int k = 0; k < d->n_add; ++k) {
+    if (d->add_ld[k] % 16 || d->add_ld[k] < d->Cout || d->add_shift[k] < 0 || d->add_shift[k] > 4) return false;
+    if ((d->Hout % (1 << d->add_shift[k])) || (d->Wout % (1 << d->add_shift[k]))) return false;
+  }
+  return true;
+}
+static inline void epi_set_add(EpiParams* e, const brtpe_conv_desc* d) {
+  e->n_add = d->n_add;
+  for (int k = 0; k < 3; ++k) {
+    e->add[k] = nullptr;
+    e->add_ld[k] = k < d->n_add ? d->add_ld[k] : 0;
+    e->add_shift[k] = k < d->n_add ? d->add_shift[k] : 0;
+  }
+  e->Hout = d->Hout; e->Wout = d->Wout;
+  e->out2 = nullptr; e->out2_ld = d->out2_ld;
 }
 static inline void epi_set_split(EpiParams* e, const brtpe_conv_desc* d) {
   e->split = conv_is_split(d) ? 1 : 0;

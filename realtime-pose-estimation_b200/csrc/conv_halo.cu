@@ -15,7 +15,7 @@ int g_halo_prof_ctas = 0;
 HaloConvPrepared* halo_conv_prepare_cg2(const brtpe_conv_desc* d, const void* in, const void* weights,
                                         void* out);
 int halo_conv_launch_cg2(const HaloConvPrepared* P, const float* bias, const void* residual, void* out,
-                         cudaStream_t st);
+                         cudaStream_t st, const void* const* add_ptrs, void* out2);
 
 bool halo_conv_supported(const brtpe_conv_desc* d) {
   if ((d->dtype != BRTPE_DT_BF16 && d->dtype != BRTPE_DT_BF16X2) || d->ntaps != 9 || d->out_scale != 1)
@@ -66,9 +66,9 @@ HaloConvPrepared* halo_conv_prepare(const brtpe_conv_desc* d, const void* in, co
 void halo_conv_release(HaloConvPrepared* p) { delete p; }
 
 int halo_conv_launch(const HaloConvPrepared* P, const float* bias, const void* residual, void* out,
-                     cudaStream_t st) {
-  return P->p.cg == 2 ? halo_conv_launch_cg2(P, bias, residual, out, st)
-                      : halo_conv_launch_cg1(P, bias, residual, out, st);
+                     cudaStream_t st, const void* const* add_ptrs, void* out2) {
+  return P->p.cg == 2 ? halo_conv_launch_cg2(P, bias, residual, out, st, add_ptrs, out2)
+                      : halo_conv_launch_cg1(P, bias, residual, out, st, add_ptrs, out2);
 }
 
 void halo_set_prof(long long* buf, int max_ctas) {

@@ -146,12 +146,14 @@ __device__ __forceinline__ TileOrg tile_origin(const HaloParams& p, int mt) {
 struct EpiPix {
   bool valid;
   size_t opix;
+  int n, y, x;                   // output pixel (fuse addends are indexed at (y >> s, x >> s))
 };
 __device__ __forceinline__ EpiPix epi_pixel(const HaloParams& p, int item, int tile, int m,
                                             int rank) {
   EpiPix e;
   e.valid = false;
   e.opix = 0;
+  e.n = e.y = e.x = 0;
   if (item >= p.num_items) return e;
   const int unit = (int)fdiv((uint32_t)item, p.fd_nt);
   const int mt = unit * (p.tpc * p.cg) + rank * p.tpc + tile;
@@ -159,6 +161,7 @@ __device__ __forceinline__ EpiPix epi_pixel(const HaloParams& p, int item, int t
   const int y = o.y0 + (m >> 3), x = o.x0 + (m & 7);
   e.valid = mt < p.m_tiles && y < p.H && x < p.W;
   e.opix = e.valid ? ((size_t)o.n * p.H + y) * p.W + x : 0;
+  e.n = o.n; e.y = y; e.x = x;
   return e;
 }
 
@@ -171,7 +174,7 @@ __device__ __forceinline__ void epi_fetch_round(Chunk32 (&r)[4], const __nv_bflo
   }
 }
 
-template <bool RES, bool RELU>
+template <bool RES, bool RELU, bool ADD>
 __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const float* bias_s,
                                                    uint32_t tmem_base, uint64_t* tfull,
                                                    uint32_t tempty_addr, int group, int lg,
@@ -258,14 +261,47 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const fl
               else mbar_arrive(tempty_addr + 8u * acc);
             }
           }
+          const Chunk32& r0 = cur[2 * h];
+          const Chunk32& r1 = cur[2 * h + 1];
+          // HRNet fuse addends (loaded here, not prefetched: a register-prefetched variant with in-place
+          // refill spilled and was 4 % slower on the whole forward, profiles/r02_fuse_epilogue.md):
+          // single output -> they join the accumulator; two outputs (direct stores only) ->
+          // x = act(acc + bias + res) goes to out, relu(x + sum) to out2
+          const bool dual = ADD && e.out2 != nullptr;
+          // sum of the addends of chunk c + k (k = 0, 1), loaded at their point of use (register
+          // prefetch variants -- in-place refill a round ahead, early loads before the accumulator wait
+          // -- spilled / indexed local memory and were 3-4 % slower: profiles/r02_fuse_epilogue.md)
+          auto terms = [&](int k, float (&s)[16]) {
+            epi_terms16(e, px.n, px.y, px.x, co0 + (c + k) * 16, s);
+          };
+          if (ADD && !dual && px.valid) {
+            float s[16];
+            terms(0, s);
+            epi_add_terms<0>(a, s);
+            if (two) {
+              terms(1, s);
+              epi_add_terms<16>(a, s);
+            }
+          }
           if (!tma_out || (!two && n_tiles > 1)) {
             // 16-channel tail of a Cout tile that has a neighbour: the 32-channel store box
             // would spill into the neighbour's channels, so this chunk is stored directly
             if (px.valid) {
               const uint32_t bs = bias_u32 + (uint32_t)((co0 + c * 16) * 4);
               __nv_bfloat16* op = e.out + px.opix * e.out_ld + e.out_coff + co0 + c * 16;
-              epi_fast_chunk<RES, RELU, 0>(a, bs, cur[2 * h], op);
-              if (two) epi_fast_chunk<RES, RELU, 16>(a, bs + 64u, cur[2 * h + 1], op + 16);
+              if (dual) {
+                __nv_bfloat16* op2 = e.out2 + px.opix * e.out2_ld + co0 + c * 16;
+                float s[16];
+                terms(0, s);
+                epi_dual_chunk<RES, RELU, 0>(a, bs, r0, s, op, op2);
+                if (two) {
+                  terms(1, s);
+                  epi_dual_chunk<RES, RELU, 16>(a, bs + 64u, r1, s, op + 16, op2 + 16);
+                }
+              } else {
+                epi_fast_chunk<RES, RELU, 0>(a, bs, r0, op);
+                if (two) epi_fast_chunk<RES, RELU, 16>(a, bs + 64u, r1, op + 16);
+              }
             }
           } else {
             // 32 (or 16) channels of 32 pixels -> bf16 in registers -> this warp's staging
@@ -274,8 +310,8 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const fl
             // 32-byte global stores (profiles/r01e_halo_pair.md).
             const uint32_t bs = bias_u32 + (uint32_t)((co0 + c * 16) * 4);
             Chunk32 o0, o1;
-            epi_pack_chunk<RES, RELU, 0>(a, bs, cur[2 * h], o0);
-            if (two) epi_pack_chunk<RES, RELU, 16>(a, bs + 64u, cur[2 * h + 1], o1);
+            epi_pack_chunk<RES, RELU, 0>(a, bs, r0, o0);
+            if (two) epi_pack_chunk<RES, RELU, 16>(a, bs + 64u, r1, o1);
             // slab (re-)use: with two slabs per warp only the store before the previous one
             // must have finished reading
             if (lane == 0) {
@@ -775,14 +811,14 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
         else halo_epilogue_split<false, false>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep);
       }
     } else if (EPI >= 0) {
-      halo_epilogue_fast<(EPI >> 1) != 0, (EPI & 1) != 0>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
+      halo_epilogue_fast<((EPI >> 1) & 1) != 0, (EPI & 1) != 0, (EPI >= 4)>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
     } else if (e.fast) {
       if (e.res != nullptr) {
-        if (e.relu) halo_epilogue_fast<true, true>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
-        else halo_epilogue_fast<true, false>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
+        if (e.relu) halo_epilogue_fast<true, true, false>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
+        else halo_epilogue_fast<true, false, false>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
       } else {
-        if (e.relu) halo_epilogue_fast<false, true>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
-        else halo_epilogue_fast<false, false>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
+        if (e.relu) halo_epilogue_fast<false, true, false>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
+        else halo_epilogue_fast<false, false, false>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
       }
     } else if (EPI == -1) {
       // general epilogue (ragged channel counts): single-CTA mode only (host guarantees cg == 1)
@@ -875,8 +911,9 @@ static void halo_n_tiling(int cout_store, int pairs, int workers, int* n_tiles, 
 static bool HL_NAME(g_halo_attr_set) = false;
 
 // kernel instantiations: 0..3 fast epilogue with (RES, RELU) = (v >> 1, v & 1); 4 run-time epilogue
-// choice (general path); 5 split (BRTPE_DT_BF16X2); 6 with the debug cycle counters
-constexpr int HL_NUM_VARIANTS = 7;
+// choice (general path); 5 split (BRTPE_DT_BF16X2); 6 with the debug cycle counters; 7..10 = 0..3 with
+// the HRNet fuse addends
+constexpr int HL_NUM_VARIANTS = 11;
 #define HL_FOR_VARIANT(v, CALL)                                                   \
   switch (v) {                                                                    \
     case 0: CALL((HL_NAME(conv_halo_kernel)<false, false, 0>)); break;            \
@@ -885,6 +922,10 @@ constexpr int HL_NUM_VARIANTS = 7;
     case 3: CALL((HL_NAME(conv_halo_kernel)<false, false, 3>)); break;            \
     case 4: CALL((HL_NAME(conv_halo_kernel)<false, false, -1>)); break;           \
     case 5: CALL((HL_NAME(conv_halo_kernel)<true, false, -2>)); break;            \
+    case 7: CALL((HL_NAME(conv_halo_kernel)<false, false, 4>)); break;            \
+    case 8: CALL((HL_NAME(conv_halo_kernel)<false, false, 5>)); break;            \
+    case 9: CALL((HL_NAME(conv_halo_kernel)<false, false, 6>)); break;            \
+    case 10: CALL((HL_NAME(conv_halo_kernel)<false, false, 7>)); break;           \
     default: CALL((HL_NAME(conv_halo_kernel)<false, true, -2>)); break;           \
   }
 
@@ -1112,6 +1153,15 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
   // the fast epilogue walks whole 16-channel chunks of real channels
   p.epi.fast = (epi_fast_ok(d) && p.n_tiles * p.BN == d->Cout) ? 1 : 0;
   epi_set_split(&p.epi, d);
+  epi_set_add(&p.epi, d);
+  if (d->n_add > 0 || d->out2_ld > 0) {
+    // two outputs go through the direct-store epilogue (Cout tiles <= 64 channels)
+    if (!epi_add_ok(d) || !p.epi.fast || split || d->n_add == 0 || (d->out2_ld > 0 && p.tma_out)) {
+      set_error("halo conv: fuse addends need the fast bf16 epilogue (two outputs: Cout tile <= 64)");
+      delete P;
+      return nullptr;
+    }
+  }
   if (split && !p.epi.fast) {
     set_error("halo conv: split layers need Cout = n_tiles * BN (Cout %d, %d x %d)", d->Cout, p.n_tiles, p.BN);
     delete P;
@@ -1204,18 +1254,41 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
 }
 
 int HL_NAME(halo_conv_launch)(const HaloConvPrepared* P, const float* bias, const void* residual, void* out,
-                     cudaStream_t st) {
+                     cudaStream_t st, const void* const* add_ptrs, void* out2) {
   HaloParams p = P->p;
   p.bias = bias;
   p.epi.res = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.epi.out = reinterpret_cast<__nv_bfloat16*>(out);
+  for (int k = 0; k < p.epi.n_add; ++k) {
+    if (!add_ptrs || !add_ptrs[k]) {
+      set_error("halo conv: fuse addend %d is null", k);
+      return BRTPE_EINVAL;
+    }
+    p.epi.add[k] = reinterpret_cast<const __nv_bfloat16*>(add_ptrs[k]);
+  }
+  if (p.epi.out2_ld > 0) {
+    if (!out2) {
+      set_error("halo conv: second output is null");
+      return BRTPE_EINVAL;
+    }
+    p.epi.out2 = reinterpret_cast<__nv_bfloat16*>(out2);
+  }
   if (p.epi.fast && out != P->out_encoded) {       // output buffer changed since prepare
     if (!halo_encode_out(&P->d, out, &p.tmap_o)) return BRTPE_ECUDA;
   }
   p.res_prefetch = 0;
-  // Opt-in (BRTPE_HALO_RES_PREFETCH=1): measured neutral for 48 channels and 9 % slower for 96
-  // (the epilogue gets its data sooner, but the extra TMA traffic delays the operand loads).
-  if (residual != nullptr && p.epi.fast && getenv("BRTPE_HALO_RES_PREFETCH")) {
+  // L2 prefetch of the residual tiles by the TMA producer.  With two MMA-issuing warps the narrow
+  // layers wait for their epilogue, which waits for the residual (HBM latency, one tile of loads in
+  // flight per warp): 48 channels 0.0970 -> 0.0933 ms with the prefetch, but 96 channels 0.0629 ->
+  // 0.0675 (the extra TMA traffic delays the operand loads): on for Cout tiles <= 64 channels.
+  // BRTPE_HALO_RES_PREFETCH=0 / 1 forces it off / on.
+  static int res_pf = -1;
+  if (res_pf < 0) {
+    const char* e = getenv("BRTPE_HALO_RES_PREFETCH");
+    res_pf = e ? (atoi(e) ? 1 : 0) : 2;
+  }
+  if (residual != nullptr && p.epi.fast && !p.epi.split && !p.s2 &&
+      (res_pf == 1 || (res_pf == 2 && p.BN <= 64))) {
     HaloConvPrepared* PM = const_cast<HaloConvPrepared*>(P);     // cache of the encoded map
     if (residual != PM->res_encoded) {
       if (!halo_encode_res(&P->d, residual, p.BN, &PM->tmap_r_cache)) return BRTPE_ECUDA;
@@ -1242,6 +1315,7 @@ int HL_NAME(halo_conv_launch)(const HaloConvPrepared* P, const float* bias, cons
   int variant;
   if (p.epi.split) variant = 5;
   else if (p.prof != nullptr && p.epi.fast) variant = 6;
+  else if (p.epi.n_add > 0) variant = 7 + (p.epi.res != nullptr ? 2 : 0) + (p.epi.relu ? 1 : 0);
   else if (p.epi.fast && p.dbg == 0) variant = (p.epi.res != nullptr ? 2 : 0) + (p.epi.relu ? 1 : 0);
   else variant = 4;
   cudaError_t e = cudaSuccess;

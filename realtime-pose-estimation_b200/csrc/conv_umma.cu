@@ -77,7 +77,7 @@ __device__ __forceinline__ void um_issue_k(uint32_t d_tmem, uint32_t a_lo, uint3
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
-template <bool SPLIT>
+template <bool SPLIT, bool ADD>
 __global__ void __launch_bounds__(UM_THREADS)
 conv_umma_kernel(const __grid_constant__ UmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -215,6 +215,7 @@ conv_umma_kernel(const __grid_constant__ UmmaParams p) {
     const int out_scale = p.out_scale, out_oy = p.out_oy, out_ox = p.out_ox, acc_cols = p.acc_cols;
     int it = 0;
     // output pixel / channel offset of this thread in a tile (valid = inside the tensor)
+    int pn = 0, py = 0, px = 0;                    // output pixel of this thread (fuse addends)
     auto locate = [&](int tile, size_t& opix, int& co0) -> bool {
       const int mt = (int)fdiv((uint32_t)tile, p.fd_nt);
       const int nt = tile - mt * n_tiles;
@@ -229,13 +230,13 @@ conv_umma_kernel(const __grid_constant__ UmmaParams p) {
                          (size_t)(xm * out_scale + out_ox)
                    : 0;
       co0 = nt * BN;
+      pn = n; py = ym * out_scale + out_oy; px = xm * out_scale + out_ox;
       return valid;
     };
     const bool res_pf = p.res_l2_prefetch != 0 && e.res != nullptr;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       size_t opix;
       int co0;
-      const bool valid = locate(tile, opix, co0);
       if (res_pf && tile + (int)gridDim.x < total_tiles) {
         // the residual row of this thread's pixel in the NEXT tile -> L2 (no registers held): the
         // HBM-bound 1x1 layers wait on exactly these loads (ncu: 70 % long-scoreboard)
@@ -247,12 +248,16 @@ conv_umma_kernel(const __grid_constant__ UmmaParams p) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + b));
         }
       }
+      const bool valid = locate(tile, opix, co0);    // (after the prefetch: it leaves pn / py / px)
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * acc_cols);
       if (SPLIT)
         epi_tile_split(e, bias_s, t_addr, nchunks, co0, valid, opix, smem_u32(&tfull_bar[as]), aphase,
                        smem_u32(&tempty_bar[as]), lane);
+      else if (ADD)
+        epi_tile_add(e, bias_s, t_addr, nchunks, co0, valid, opix, smem_u32(&tfull_bar[as]), aphase,
+                     smem_u32(&tempty_bar[as]), lane, pn, py, px);
       else
         epi_tile(e, bias_s, t_addr, nchunks, co0, valid, opix, smem_u32(&tfull_bar[as]), aphase,
                  smem_u32(&tempty_bar[as]), lane);
@@ -440,6 +445,13 @@ UmmaConvPrepared* umma_conv_prepare(const brtpe_conv_desc* d, const void* in, co
   // for tilings that cover the channels exactly (176 = 2 x 96 would write 16 channels too many)
   p.epi.fast = (epi_fast_ok(d) && p.n_tiles * p.BN == d->Cout) ? 1 : 0;
   epi_set_split(&p.epi, d);
+  epi_set_add(&p.epi, d);
+  if ((d->n_add > 0 || d->out2_ld > 0) && (!epi_add_ok(d) || !p.epi.fast || d->out2_ld > 0)) {
+    set_error("tcgen05 conv (per-tap engine): fuse addends need the fast epilogue, aligned addends and "
+              "no second output");
+    delete P;
+    return nullptr;
+  }
   if (split && !p.epi.fast) {
     set_error("tcgen05 conv: split layers need a Cout tiling that covers the channels exactly "
               "(Cout %d, %d x %d)", d->Cout, p.n_tiles, p.BN);
@@ -496,9 +508,11 @@ UmmaConvPrepared* umma_conv_prepare(const brtpe_conv_desc* d, const void* in, co
     return nullptr;
   }
   if (!g_attr_set) {
-    if (cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(conv_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(conv_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              227 * 1024) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(conv_umma_kernel) failed: %s",
                 cudaGetErrorString(cudaGetLastError()));
@@ -513,13 +527,22 @@ UmmaConvPrepared* umma_conv_prepare(const brtpe_conv_desc* d, const void* in, co
 void umma_conv_release(UmmaConvPrepared* p) { delete p; }
 
 int umma_conv_launch(const UmmaConvPrepared* P, const float* bias, const void* residual, void* out,
-                     cudaStream_t st) {
+                     cudaStream_t st, const void* const* add_ptrs, void* out2) {
   UmmaParams p = P->p;
   p.bias = bias;
   p.epi.res = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.epi.out = reinterpret_cast<__nv_bfloat16*>(out);
-  if (p.epi.split) conv_umma_kernel<true><<<P->grid, UM_THREADS, P->smem, st>>>(p);
-  else conv_umma_kernel<false><<<P->grid, UM_THREADS, P->smem, st>>>(p);
+  for (int k = 0; k < p.epi.n_add; ++k) {
+    if (!add_ptrs || !add_ptrs[k]) {
+      set_error("tcgen05 conv: fuse addend %d is null", k);
+      return BRTPE_EINVAL;
+    }
+    p.epi.add[k] = reinterpret_cast<const __nv_bfloat16*>(add_ptrs[k]);
+  }
+  (void)out2;
+  if (p.epi.split) conv_umma_kernel<true, false><<<P->grid, UM_THREADS, P->smem, st>>>(p);
+  else if (p.epi.n_add > 0) conv_umma_kernel<false, true><<<P->grid, UM_THREADS, P->smem, st>>>(p);
+  else conv_umma_kernel<false, false><<<P->grid, UM_THREADS, P->smem, st>>>(p);
   BRTPE_LAUNCH_CHECK();
   return BRTPE_OK;
 }

@@ -24,6 +24,8 @@ struct Op {
   void* out;
   UmmaConvPrepared* umma;  // non-null: tcgen05 per-tap path
   HaloConvPrepared* halo;  // non-null: tcgen05 halo-tile path
+  const void* add_ptrs[3]; // HRNet fuse addends of the epilogue (d.n_add of them)
+  void* out2;              // second output (d.out2_ld > 0)
   // stem / tonchw / fuse
   int i[16];
   const void* terms[4];
@@ -89,8 +91,12 @@ static int choose_engine(const brtpe_conv_desc* d) {
 static int run_op(const Op& op, cudaStream_t st) {
   switch (op.kind) {
     case OP_CONV:
-      if (op.halo) return halo_conv_launch(op.halo, op.bias, op.res, op.out, st);
-      if (op.umma) return umma_conv_launch(op.umma, op.bias, op.res, op.out, st);
+      if (op.halo) return halo_conv_launch(op.halo, op.bias, op.res, op.out, st, op.add_ptrs, op.out2);
+      if (op.umma) return umma_conv_launch(op.umma, op.bias, op.res, op.out, st, op.add_ptrs, op.out2);
+      if (op.d.n_add > 0 || op.d.out2_ld > 0) {
+        set_error("conv: fuse addends need a tcgen05 engine");
+        return BRTPE_EINVAL;
+      }
       return conv_ffma_launch(&op.d, op.in, op.w, op.bias, op.res, op.out, st);
     case OP_STEM:
       return stem_conv1_launch(op.in, op.i[0], op.i[1], op.i[2], op.i[3], op.stem_w, op.bias,
@@ -152,6 +158,49 @@ extern "C" int brtpe_conv_run(const brtpe_conv_desc* d, const void* in, const vo
     return rc;
   }
   return conv_ffma_launch(d, in, weights, bias, residual, out, (cudaStream_t)stream);
+}
+
+extern "C" int brtpe_conv_run_fused(const brtpe_conv_desc* d, const void* in, const void* weights,
+                                    const float* bias, const void* residual, void* out,
+                                    const void* const* add_ptrs, void* out2, void* stream) {
+  int rc = conv_validate(d);
+  if (rc) return rc;
+  BRTPE_CHECK_ARG(in && weights && out, "brtpe_conv_run_fused: null tensor");
+  BRTPE_CHECK_ARG(d->n_add >= 0 && d->n_add <= 3 && (d->n_add == 0 || add_ptrs),
+                  "brtpe_conv_run_fused: bad addends");
+  const int eng = choose_engine(d);
+  if (eng < 0) return BRTPE_EINVAL;
+  if (eng == BRTPE_ENGINE_UMMA_HALO) {
+    HaloConvPrepared* p = halo_conv_prepare(d, in, weights, out);
+    if (!p) return BRTPE_ECUDA;
+    rc = halo_conv_launch(p, bias, residual, out, (cudaStream_t)stream, add_ptrs, out2);
+    halo_conv_release(p);
+    return rc;
+  }
+  if (eng == BRTPE_ENGINE_UMMA) {
+    UmmaConvPrepared* p = umma_conv_prepare(d, in, weights);
+    if (!p) return BRTPE_ECUDA;
+    rc = umma_conv_launch(p, bias, residual, out, (cudaStream_t)stream, add_ptrs, out2);
+    umma_conv_release(p);
+    return rc;
+  }
+  set_error("brtpe_conv_run_fused: fuse addends need a tcgen05 engine");
+  return BRTPE_EINVAL;
+}
+
+extern "C" int brtpe_plan_set_conv_fuse(brtpe_plan* pl, const void* const* add_ptrs, void* out2) {
+  BRTPE_CHECK_ARG(pl && !pl->ops.empty() && pl->ops.back().kind == OP_CONV,
+                  "brtpe_plan_set_conv_fuse: the last op is not a conv");
+  Op& op = pl->ops.back();
+  BRTPE_CHECK_ARG(op.d.n_add == 0 || add_ptrs, "brtpe_plan_set_conv_fuse: null addends");
+  for (int k = 0; k < op.d.n_add; ++k) {
+    BRTPE_CHECK_ARG(add_ptrs[k], "brtpe_plan_set_conv_fuse: addend %d is null", k);
+    op.add_ptrs[k] = add_ptrs[k];
+  }
+  BRTPE_CHECK_ARG((op.d.out2_ld > 0) == (out2 != nullptr),
+                  "brtpe_plan_set_conv_fuse: out2 must be given exactly when out2_ld > 0");
+  op.out2 = out2;
+  return BRTPE_OK;
 }
 
 extern "C" int brtpe_conv_select_engine(const brtpe_conv_desc* d) {

@@ -290,10 +290,14 @@ class _Recorder:
 
     # -- ops
     def conv(self, x, conv, bn, relu, residual=None, out=None, out_coff=0, in_coff=0,
-             cin_store=None, cout_store=None, pad_cout=False, cin_index=None):
+             cin_store=None, cout_store=None, pad_cout=False, cin_index=None, addends=None,
+             out2=None):
         """conv (+BN) (+residual) (+ReLU) over virtual tensor x -> virtual tensor.
         ``cin_index``: for every stored input channel the module's input channel it carries, or -1
-        for a pad channel (zero weights) -- inputs whose real channels sit in padded slots."""
+        for a pad channel (zero weights) -- inputs whose real channels sit in padded slots.
+        ``addends``: [(tensor, shift), ...] HRNet fuse terms added in the epilogue, term k read with
+        nearest-neighbour upsampling by 2^shift; ``out2``: second output -- then ``out`` receives
+        act(conv + residual) and ``out2`` relu(out + sum of the addends) (brtpe_conv_desc.n_add)."""
         k = conv.kernel_size[0]
         s = conv.stride[0]
         dil = conv.dilation[0]                       # dilated 3x3 = the same taps, spread out
@@ -316,9 +320,14 @@ class _Recorder:
             dcout = cout_store
         d = self._desc(x, in_coff, cin_store, taps, s, ho, wo, out, 1, 0, 0, dcout, cout_store,
                        out_coff, residual, relu)
+        addends = list(addends or [])
+        d.n_add = len(addends)
+        for k, (t, sh) in enumerate(addends):
+            d.add_ld[k], d.add_shift[k] = t.ld, sh
+        d.out2_ld = out2.ld if out2 is not None else 0
         packed, b = self._prepack(d, conv.weight, False, bn, conv.bias, khkw, cin_store, cout,
                                   cin_index=cin_index)
-        self._emit_conv(d, x, packed, b, residual, out)
+        self._emit_conv(d, x, packed, b, residual, out, addends=addends, out2=out2)
         return out
 
     def deconv4x4s2(self, x, deconv, bn, cin_store, lanes=(0, 1, 2, 3)):
@@ -365,15 +374,15 @@ class _Recorder:
         d.Cout_store = cout_store
         return d
 
-    def _emit_conv(self, d, x, packed, bias, residual, out, group=None):
+    def _emit_conv(self, d, x, packed, bias, residual, out, group=None, addends=(), out2=None):
         self.keepalive += [packed, bias]
         idx = len(self.ops)
-        self.ops.append(("conv", d, x, packed, bias, residual, out))
-        self._sched([x, residual], [out], group)
-        self._touch(x, idx)
-        if residual is not None:
-            self._touch(residual, idx)
-        self._touch(out, idx)
+        adds = [t for t, _ in addends]
+        self.ops.append(("conv", d, x, packed, bias, residual, out, adds, out2))
+        self._sched([x, residual] + adds, [out] + ([out2] if out2 is not None else []), group)
+        for t in [x, residual, out, out2] + adds:
+            if t is not None:
+                self._touch(t, idx)
 
     def stem(self, conv, bn):
         cout = conv.out_channels                                           # (64,3,3,3)
@@ -502,11 +511,16 @@ class _Recorder:
             for op in self.ops:
                 kind = op[0]
                 if kind == "conv":
-                    _, d, x, packed, bias, residual, out = op
+                    _, d, x, packed, bias, residual, out, adds, out2 = op
                     L.check(lib.brtpe_plan_add_conv(
                         plan, C.byref(d), L.ptr(x.buf[1]), L.ptr(packed), L.ptr(bias),
                         L.ptr(residual.buf[1]) if residual is not None else None,
                         L.ptr(out.buf[1])), "brtpe_plan_add_conv")
+                    if adds or out2 is not None:
+                        ap = (C.c_void_p * max(len(adds), 1))(*[t.buf[1].data_ptr() for t in adds])
+                        L.check(lib.brtpe_plan_set_conv_fuse(
+                            plan, ap, L.ptr(out2.buf[1]) if out2 is not None else None),
+                            "brtpe_plan_set_conv_fuse")
                 elif kind == "stem":
                     _, wp, b, out = op
                     L.check(lib.brtpe_plan_add_stem(
@@ -623,7 +637,7 @@ class _PlanRunner:
 
     def _get_plan(self, n, h, w, mode, device, in_dtype, stem_mode=0):
         key = (n, h, w, mode, str(device), in_dtype, self.conv_engine, self.parallel_branches,
-               stem_mode, self._plan_extra_key())
+               stem_mode, self._plan_extra_key(), getattr(self, "fuse_in_epilogue", False))
         plan = self._plans.get(key)
         if plan is None:
             in_is_half = in_dtype == torch.float16
@@ -827,6 +841,13 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
 
         self._init_runner()
         self._split_fp32 = True        # float32 parameters -> split-bf16 tcgen05 path (<= 1e-4)
+        # HRNet fuse sums folded into conv epilogues (bf16 tcgen05 path): parity-green and the
+        # fuse_sum launches disappear, but measured 1.3 % SLOWER than the stand-alone fuse_sum kernel
+        # (26.63 vs 26.98 ms per 64 forwards, same box, profiles/r02_fuse_epilogue.md: the epilogue of
+        # the 48-channel layers is the critical stage and the addend loads lengthen it), hence opt-in:
+        # ``net.fuse_in_epilogue = True`` (+ ``invalidate_plans()``) or BRTPE_FUSE_EPILOGUE=1
+        import os
+        self.fuse_in_epilogue = os.environ.get("BRTPE_FUSE_EPILOGUE", "0") == "1"
 
     # ---------------------------------------------------------------- construction helpers
     def _make_layer(self, block, planes, blocks, stride=1):
@@ -902,6 +923,10 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
 
         ys = [x]
         nj = self.num_joints
+        # HRNet cross-resolution fuse-add in the conv epilogues (tcgen05 bf16 path); the stand-alone
+        # fuse_sum kernel stays for the fp32 modes and as the A/B reference (fuse_in_epilogue = False)
+        fuse_epi = bool(self.fuse_in_epilogue and R.tc and not R.split and
+                        self.conv_engine != L.ENGINE_FFMA)
         head0 = self.final_layers[0]
         cat = self.deconv_cat[0] if self.num_deconvs else False
         cat_ld = None
@@ -921,6 +946,16 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
                         t = R.conv(t, sub[0], sub[1], True)
                     xs.append(t)
             for mi, mod in enumerate(stage):
+                final_module = si == 3 and mi == len(stage) - 1
+                dst0 = None
+                if final_module and cat:
+                    # stage-4 output lands in channels [0, c) of the concat buffer
+                    c = mod.num_inchannels[0]
+                    cat_ld = (c + head0.out_channels + 15) // 16 * 16
+                    dst0 = R.new(n, xs[0].h, xs[0].w, cat_ld)
+                if fuse_epi and mod.fuse_layers is not None:
+                    xs = self._record_module_fused(R, mod, xs, par, dst0)
+                    continue
                 # interleave the branches block by block: the recording order is also the
                 # issue order of the capture, so independent launches sit next to each other
                 nblk = max(len(b) for b in mod.branches)
@@ -933,7 +968,6 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
                         t = R.conv(xs[i], blk.conv1, blk.bn1, True)
                         xs[i] = R.conv(t, blk.conv2, blk.bn2, True, residual=xs[i])
                 outs = []
-                final_module = si == 3 and mi == len(stage) - 1
                 nout = len(mod.fuse_layers)
                 terms_of = [[None] * mod.num_branches for _ in range(nout)]
                 shifts_of = [[0] * mod.num_branches for _ in range(nout)]
@@ -954,12 +988,8 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
                 for i in range(nout):
                     R.lane = i if par else 0
                     c = mod.num_inchannels[i]
-                    dst = None
-                    if final_module and i == 0 and cat:
-                        # stage-4 output lands in channels [0, c) of the concat buffer
-                        cat_ld = (c + head0.out_channels + 15) // 16 * 16
-                        dst = R.new(n, xs[0].h, xs[0].w, cat_ld)
-                    outs.append(R.fuse(terms_of[i], shifts_of[i], c, True, out=dst))
+                    outs.append(R.fuse(terms_of[i], shifts_of[i], c, True,
+                                       out=dst0 if i == 0 else None))
                 xs = outs
             ys = xs
         R.lane = 0
@@ -995,6 +1025,84 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
             R.to_nchw(y, head.out_channels, 0, yo)
             outs.append(yo)
         return R, outs
+
+    def _record_module_fused(self, R, mod, xs, par, dst0):
+        """One HighResolutionModule with the fuse sums (pose_higher_hrnet.py:245-254) folded into
+        conv epilogues.  Every conv takes at most ONE same-resolution addend (its residual) and
+        ONE nearest-upsampled addend (shift 1), so the sums are built as chains:
+          * upsampled terms of output i (branches j > i): W_{B-1} = c_{i,B-1}(x_{B-1}) and
+            W_j = c_ij(x_j) + up2(W_{j+1}) in the epilogue of the 1x1 conv c_ij -- nearest
+            upsampling composes exactly (up4 = up2 o up2), the partial sums live at low resolution;
+          * stride-2 chains of output i >= 1 (branches j < i): the last conv of the chain from
+            branch j takes the running sum S (starting with x_i) as residual; the chain from
+            branch 0 comes last, adds up2(W_{i+1}) and applies the ReLU;
+          * output 0: y_0 = relu(x_0 + up2(W_1)) leaves the epilogue of branch 0's LAST conv2, which
+            writes x_0 (the stride-2 chains read it) and y_0.
+        Recording order = dependency order: the other branches finish first, then their fuse
+        convs, then branch 0's last conv2, then the chains that start from x_0."""
+        nb = mod.num_branches
+        nout = len(mod.fuse_layers)
+        xs = list(xs)
+        nblk = max(len(b) for b in mod.branches)
+        last0 = None
+        for bi in range(nblk):
+            for i in range(nb):
+                if bi >= len(mod.branches[i]):
+                    continue
+                R.lane = i if par else 0
+                blk = mod.branches[i][bi]
+                t = R.conv(xs[i], blk.conv1, blk.bn1, True)
+                if i == 0 and bi == len(mod.branches[0]) - 1:
+                    last0 = (t, blk, xs[0])              # conv2 of branch 0's last block comes later
+                else:
+                    xs[i] = R.conv(t, blk.conv2, blk.bn2, True, residual=xs[i])
+        # upsampled terms: W[i] = sum_{j > i} up_{2^(j-i-1)}(c_ij(x_j)) at the resolution of branch i+1
+        W = {}
+        for i in range(min(nout, nb - 1)):
+            w = None
+            for j in range(nb - 1, i, -1):
+                R.lane = j if par else 0
+                f = mod.fuse_layers[i][j]
+                w = R.conv(xs[j], f[0], f[1], False, addends=[(w, 1)] if w is not None else None)
+            W[i] = w
+        # stride-2 chains that do not start from branch 0: running sums S[i] = x_i + chains
+        S = {i: xs[i] for i in range(1, nout)}
+        for j in range(1, nb):
+            R.lane = j if par else 0
+            for i in range(j + 1, nout):
+                t = xs[j]
+                f = mod.fuse_layers[i][j]
+                for k, sub in enumerate(f):
+                    last = k == len(f) - 1
+                    t = R.conv(t, sub[0], sub[1], not last, residual=S[i] if last else None)
+                S[i] = t
+        # branch 0: last conv2 -> x_0 and y_0
+        R.lane = 0
+        t, blk, res0 = last0
+        c0 = mod.num_inchannels[0]
+        y0 = dst0 if dst0 is not None else R.new(res0.n, res0.h, res0.w, c0)
+        adds0 = [(W[0], 1)]
+        if nout > 1:
+            x0 = R.conv(t, blk.conv2, blk.bn2, True, residual=res0, addends=adds0, out2=y0)
+        else:
+            # nobody reads x_0 after the last module: both stores go to the same pixels, the
+            # second one (y_0) stays
+            x0 = R.conv(t, blk.conv2, blk.bn2, True, residual=res0, out=y0, addends=adds0, out2=y0)
+        outs = [y0]
+        # chains from x_0; their last conv adds the running sum and the upsampled terms, then ReLU
+        for i in range(1, nout):
+            f = mod.fuse_layers[i][0]
+            t = x0
+            for k, sub in enumerate(f):
+                if k < len(f) - 1:
+                    R.lane = 0
+                    t = R.conv(t, sub[0], sub[1], True)
+                else:
+                    R.lane = i if par else 0
+                    t = R.conv(t, sub[0], sub[1], True, residual=S[i],
+                               addends=[(W[i], 1)] if i in W else None)
+            outs.append(t)
+        return outs
 
     # ---------------------------------------------------------------- forward
     def forward(self, x):

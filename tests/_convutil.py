@@ -132,3 +132,53 @@ def run_conv_split(engine, n, h, w, cin, cout, k, stride, relu, use_res, seed=0,
         ref = F.relu(ref)
     got = (out[..., :cout].float() + out[..., cout:].float()).permute(0, 3, 1, 2)
     return got, ref.float(), eng
+
+
+def run_conv_fused(engine, n, h, w, cin, cout, k, stride, relu, use_res, shifts, dual, seed=0,
+                   device="cuda"):
+    """HRNet fuse-add in the epilogue (brtpe_conv_run_fused): addends at resolution >> shift, read
+    with nearest-neighbour upsampling.  -> (out, out2 or None, ref_out, ref_out2 or None, engine)."""
+    lib = L.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn((n, cin, h, w), generator=g).to(device)
+    wgt = (torch.randn((cout, cin, k, k), generator=g) / (cin * k * k) ** 0.5).to(device)
+    bias = torch.randn((cout,), generator=g).to(device) * 0.1
+    ho, wo = h // stride, w // stride
+    res = torch.randn((n, cout, ho, wo), generator=g).to(device) if use_res else None
+    adds = [torch.randn((n, cout, ho >> s, wo >> s), generator=g).to(device) for s in shifts]
+    d, taps = make_desc(L.DT_BF16, engine, n, h, w, cin, cout, k, stride, relu,
+                        res_ld=(cout if use_res else 0))
+    d.n_add = len(shifts)
+    for i, s in enumerate(shifts):
+        d.add_ld[i], d.add_shift[i] = cout, s
+    d.out2_ld = cout if dual else 0
+    eng = lib.brtpe_conv_select_engine(C.byref(d))
+    assert eng in (L.ENGINE_UMMA, L.ENGINE_UMMA_HALO), lib.brtpe_last_error()
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    xin, rin = nhwc(x), (nhwc(res) if use_res else None)
+    ain = [nhwc(a) for a in adds]
+    packed = pack_weights(lib, wgt, taps, k, d, eng, True)
+    out = torch.full((n, ho, wo, d.out_ld), float("nan"), dtype=torch.bfloat16, device=device)
+    out2 = torch.full((n, ho, wo, cout), float("nan"), dtype=torch.bfloat16, device=device) if dual else None
+    ap = (C.c_void_p * max(len(ain), 1))(*[a.data_ptr() for a in ain])
+    L.check(lib.brtpe_conv_run_fused(C.byref(d), L.ptr(xin), L.ptr(packed), L.ptr(bias), L.ptr(rin),
+                                     L.ptr(out), ap, L.ptr(out2), L.stream_ptr()), "brtpe_conv_run_fused")
+    torch.cuda.synchronize()
+    ref = F.conv2d(xin.double().permute(0, 3, 1, 2), wgt.to(torch.bfloat16).double(), bias.double(),
+                   stride=stride, padding=k // 2)
+    if use_res:
+        ref = ref + rin.double().permute(0, 3, 1, 2)
+    tot = 0
+    for a, s in zip(ain, shifts):
+        up = a.double().permute(0, 3, 1, 2)
+        if s:
+            up = F.interpolate(up, scale_factor=2 ** s, mode="nearest")
+        tot = tot + up
+    got = out[..., :cout].float().permute(0, 3, 1, 2)
+    if dual:
+        r1 = F.relu(ref) if relu else ref
+        r2 = F.relu(r1 + tot)
+        return got, out2.float().permute(0, 3, 1, 2), r1.float(), r2.float(), eng
+    r1 = ref + tot
+    r1 = F.relu(r1) if relu else r1
+    return got, None, r1.float(), None, eng

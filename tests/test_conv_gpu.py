@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from rtpe_b200 import _lib as L
-from _convutil import run_conv, run_conv_split
+from _convutil import run_conv, run_conv_fused, run_conv_split
 
 pytestmark = pytest.mark.gpu
 
@@ -208,3 +208,30 @@ def test_umma_halo_stride2_split_fp32(cuda_device, shape):
     got, ref, eng = run_conv_split(L.ENGINE_UMMA_HALO, *shape)
     assert eng == L.ENGINE_UMMA_HALO
     assert _err(got, ref) <= 3e-5
+
+
+# ---- HRNet cross-resolution fuse-add in the conv epilogue (pose_higher_hrnet.py:245-254)
+FUSED_CASES = [
+    # engine, n, h, w, cin, cout, k, stride, relu, res, addend shifts, two outputs
+    (L.ENGINE_UMMA_HALO, 2, 64, 64, 48, 48, 3, 1, True, True, (1, 2, 3), True),     # y_0 of a 4-branch module
+    (L.ENGINE_UMMA_HALO, 3, 32, 48, 48, 48, 3, 1, True, True, (1,), True),          # stage 2
+    (L.ENGINE_UMMA_HALO, 7, 80, 72, 48, 48, 3, 1, True, True, (1, 2), True),        # many items
+    (L.ENGINE_UMMA_HALO, 2, 64, 64, 48, 96, 3, 2, True, True, (1, 2), False),       # y_1: stride-2 halo, TMA stores
+    (L.ENGINE_UMMA_HALO, 2, 64, 96, 48, 96, 3, 2, True, True, (), False),
+    (L.ENGINE_UMMA, 2, 64, 64, 48, 192, 3, 2, True, True, (0, 1), False),           # y_2: per-tap engine
+    (L.ENGINE_UMMA, 2, 32, 32, 48, 384, 3, 2, True, True, (0, 0), False),           # y_3
+    (L.ENGINE_UMMA, 3, 40, 40, 96, 192, 3, 2, True, True, (1,), False),
+    (L.ENGINE_UMMA, 2, 32, 32, 96, 48, 1, 1, False, False, (0, 2), False),
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES)
+def test_fuse_addends_in_epilogue(cuda_device, case):
+    eng_req, rest = case[0], case[1:]
+    got, got2, ref, ref2, eng = run_conv_fused(eng_req, *rest)
+    assert eng == eng_req
+    assert torch.isfinite(got).all()
+    assert _err(got, ref) <= 6e-3
+    if ref2 is not None:
+        assert torch.isfinite(got2).all()
+        assert _err(got2, ref2) <= 6e-3

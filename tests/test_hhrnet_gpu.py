@@ -111,3 +111,23 @@ def test_forward_flip_pair_equals_materialised_batch(cuda_device, chunk):
         for c, d in zip(yc, yd):
             assert c.shape == d.shape
             assert (c - d.float()).abs().max().item() <= 1e-3 * c.abs().max().item()
+
+
+def test_fuse_in_epilogue_matches_fuse_kernel(cuda_device, model_and_ref):
+    """HRNet cross-resolution fuse-add folded into the conv epilogues (opt-in) against the stand-alone
+    fuse_sum path and the oracle: same network, sums taken in a different order / with bf16 partial
+    sums at low resolution, so equal within the bf16 budget, and the plan has no fuse op left."""
+    net, x, ref = model_and_ref
+    import copy
+    half = rtpe_b200.network_to_half(copy.deepcopy(net).float()).cuda().eval()
+    with torch.no_grad():
+        half[1].fuse_in_epilogue = False
+        a = [o.clone() for o in half(x.cuda())]
+        half[1].fuse_in_epilogue = True
+        b = [o.clone() for o in half(x.cuda())]
+    plans = [p for k, p in half[1]._plans.items() if k[-1] is True]
+    assert plans and all(op[0] != "fuse" for op in plans[0].recorder.ops)
+    assert any(op[0] == "conv" and op[1].n_add > 0 for op in plans[0].recorder.ops)
+    for u, v, r in zip(a, b, ref):
+        assert _rel(v, r) <= TOL_BF16
+        assert _rel(u, v.cpu()) <= TOL_BF16
