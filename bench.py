@@ -283,6 +283,76 @@ def workload_config(args):
                   % (args.batch * 3 * args.size * args.size * 4 / 1e6)}
 
 
+def conv_bound_split(net, chunk, size, in_dtype, peaks, ms_ops, kinds, flops):
+    """Every conv launch against ITS roofline: algorithmic bytes = input + output (+ residual) of the
+    layer once (activations are larger than the L2 at the bench's chunk), arithmetic intensity below
+    the ridge (tensor peak / HBM peak) = HBM-bound.  -> summary of both groups."""
+    plan = net._get_plan(chunk, size, size, net._mode(), net._ref_param().device, in_dtype)
+    esz = 2
+    ridge = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    grp = {"tensor": [0.0, 0.0, 0.0, 0], "hbm": [0.0, 0.0, 0.0, 0]}     # ms, flop, bytes, launches
+    for i, op in enumerate(plan.recorder.ops):
+        if op[0] != "conv" or kinds[i] not in (0, 3):
+            continue
+        d = op[1]
+        split = 2 if d.dtype == 2 else 1
+        b = d.N * d.Hin * d.Win * d.Cin * esz * split + d.N * d.Hm * d.Wm * d.Cout * esz * split
+        if op[5] is not None:
+            b += d.N * d.Hm * d.Wm * d.Cout * esz * split
+        b += sum(d.N * (d.Hout >> d.add_shift[k]) * (d.Wout >> d.add_shift[k]) * d.Cout * esz
+                 for k in range(d.n_add))
+        if d.out2_ld:
+            b += d.N * d.Hm * d.Wm * d.Cout * esz
+        g = grp["hbm" if flops[i] / b < ridge else "tensor"]
+        g[0] += ms_ops[i]; g[1] += flops[i]; g[2] += b; g[3] += 1
+    out = {"ridge_flop_per_byte": ridge,
+           "note": "per launch: algorithmic bytes = layer input + output (+ residual) once"}
+    for name, (ms, fl, by, nl) in grp.items():
+        out[name + "_bound"] = {
+            "launches": nl, "ms": ms, "tflops": fl / max(ms, 1e-9) / 1e9,
+            "tensor_frac": fl / max(ms, 1e-9) / 1e9 / peaks["tflops"],
+            "gbs": by / max(ms, 1e-9) / 1e6, "hbm_frac": by / max(ms, 1e-9) / 1e6 / peaks["hbm_gbs"]}
+    return out
+
+
+def config5_leg(peaks):
+    """BASELINE.json configs[4]: decode-only stress, batch 1024, 17 x 320 x 320, T = 1, K = 30
+    (SURVEY.md 8d generator); device time per stage, algorithmic bytes against the HBM peak."""
+    import rtpe_b200
+    n, sz = 1024, 320
+    parts = [rtpe_b200.synth_decode_batch(128, height=sz, width=sz, tag_dims=1, max_people=30,
+                                          seed=1234, device="cuda", first_index=i)
+             for i in range(0, n, 128)]
+    det = torch.cat([q[0] for q in parts])
+    tag = torch.cat([q[1] for q in parts])
+    del parts
+    parser = rtpe_b200.HeatmapParser(**PARSER_KW)
+    for _ in range(2):
+        parser.decode_device(det, tag, full_capacity=True)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    torch.cuda._sleep(8_000_000)
+    ev[0].record()
+    val_k, ind_k, _, tag_k = parser.top_k_device(det, tag)
+    ev[1].record()
+    ans, count, pmax = parser.match_device(val_k, ind_k, tag_k, sz, pmax=parser._pmax_full())
+    ev[2].record()
+    parser.adjust_device(ans, count, det)
+    ev[3].record()
+    parser.refine_device(det, tag, ans, count)
+    ev[4].record()
+    torch.cuda.synchronize()
+    t = [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+    b_topk, b_ref = det.numel() * 4, (det.numel() + tag.numel()) * 4
+    total = sum(t)
+    pk = peaks["hbm_gbs"]
+    return {"workload": "configs[4]: decode-only stress, batch %d, 17 x %d x %d, T=1, K=30" % (n, sz, sz),
+            "value": n / total * 1e3, "unit": "images/s", "people_per_image": float(count.float().mean()),
+            "ms": {"top_k": t[0], "match": t[1], "adjust": t[2], "refine": t[3], "parse_total": total},
+            "top_k_frac": b_topk / t[0] / 1e6 / pk, "refine_frac": b_ref / t[3] / 1e6 / pk,
+            "parse_frac": (b_topk + b_ref) / total / 1e6 / pk, "hbm_peak_gbs": pk}
+
+
 def conv_rooflines(net, chunk, size, in_dtype, peaks, mode):
     """(roofline of conv_halo_kernel, roofline of conv_umma_kernel, per-op ms) of one plan replay:
     algorithmic FLOP (2 * MAC of the reference layer) / CUDA-event time of the launches."""
@@ -317,6 +387,10 @@ def conv_rooflines(net, chunk, size, in_dtype, peaks, mode):
             roofline["pipe_frac"] = 3 * roofline["frac"]
             other["pipe_frac"] = 3 * other["frac"]
     roofline["conv_share_of_forward"] = conv_ms / max(sum(ms_ops), 1e-9)
+    try:
+        roofline["by_bound"] = conv_bound_split(net, chunk, size, in_dtype, peaks, ms_ops, kinds, flops)
+    except Exception as exc:                     # reporting only: never fail the bench on it
+        roofline["by_bound"] = {"error": repr(exc)}
     return roofline, other, ms_ops
 
 
@@ -636,6 +710,9 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and args.mode == "bf16" and not args.no_fp32:
         fp32 = fp32_leg(args, dev, x_dev, ref if parity else None, peaks)
 
+    config5 = None
+    if rank == 0 and world == 1 and not args.no_config5:
+        config5 = config5_leg(peaks)
     config3 = None
     if world > 1 and args.mode == "bf16" and not args.no_config3:
         config3 = config3_leg(args, rank, world, dev, pipe, net, parser)
@@ -654,7 +731,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline_other_convs": roofline_other,
             "roofline_decode": roofline_decode, "cpu_baseline": cpu_baseline,
             "parity_checked": bool(parity and parity["float_ok"] and parity["decode_bit_exact"]),
-            "parity": parity, "fp32": fp32, "config3": config3,
+            "parity": parity, "fp32": fp32, "config3": config3, "config5_decode": config5,
             "host": {"numa_cores_bound": numa_cores, "cpu_count": os.cpu_count()},
             "forward_tflops_effective": 2 * args.batch * world * args.steps *
             FLOP_PER_FORWARD_640 * (args.size / 640.0) ** 2 / (ms_dev * 1e-3) / 1e12,
@@ -678,6 +755,8 @@ def main():
                     help="forwards per plan replay (64 = the whole flip-test batch in one CUDA graph)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-mode leg of the bf16 line")
+    ap.add_argument("--no-config5", action="store_true",
+                    help="skip the decode-only stress leg (BASELINE configs[4]) of the 1-GPU line")
     ap.add_argument("--no-config3", action="store_true",
                     help="skip the multi-scale batch-256 leg (BASELINE configs[2]) of multi-GPU runs")
     args = ap.parse_args()
