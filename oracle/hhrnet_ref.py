@@ -45,7 +45,15 @@ class _SD:
 def _basic_block(s: _SD, x, pfx):
     out = F.relu(s.bn(s.conv(x, pfx + ".conv1", 1, 1), pfx + ".bn1"))
     out = s.bn(s.conv(out, pfx + ".conv2", 1, 1), pfx + ".bn2")
-    return F.relu(out + x)
+    res = x
+    if s.has(pfx + ".downsample.0.weight"):          # :64-65 (branches whose width changes)
+        res = s.bn(s.conv(x, pfx + ".downsample.0"), pfx + ".downsample.1")
+    return F.relu(out + res)
+
+
+def _block(s: _SD, x, pfx):
+    """BasicBlock (:46-75) or Bottleneck (:78-116), told apart by the third conv."""
+    return _bottleneck(s, x, pfx) if s.has(pfx + ".conv3.weight") else _basic_block(s, x, pfx)
 
 
 def _bottleneck(s: _SD, x, pfx):
@@ -70,7 +78,7 @@ def _hr_module(s: _SD, xs, pfx):
     for i in range(nb):
         nblk = _count(s, re.escape(pfx) + r"\.branches\.%d\.(\d+)\.conv1\.weight" % i)
         for b in range(nblk):
-            xs[i] = _basic_block(s, xs[i], "%s.branches.%d.%d" % (pfx, i, b))
+            xs[i] = _block(s, xs[i], "%s.branches.%d.%d" % (pfx, i, b))
     nout = _count(s, re.escape(pfx) + r"\.fuse_layers\.(\d+)\.")
     outs = []
     for i in range(nout):
@@ -148,10 +156,11 @@ def hhrnet_forward_ref(state_dict, x: torch.Tensor, dtype=torch.float32):
     ndeconv = _count(s, r"deconv_layers\.(\d+)\.0\.0\.weight")
     for i in range(ndeconv):
         w = s.sd["deconv_layers.%d.0.0.weight" % i]
-        assert w.shape[-1] == 4, "only the 4x4/s2/p1 deconv of the W48 config is restated"
+        k = w.shape[-1]                              # _get_deconv_cfg (:535-546)
+        pad, opad = {4: (1, 0), 3: (1, 1), 2: (0, 0)}[k]
         if w.shape[0] != x.shape[1]:                 # deconv_cat
             x = torch.cat((x, y), 1)
-        x = F.conv_transpose2d(x, w, None, stride=2, padding=1, output_padding=0)
+        x = F.conv_transpose2d(x, w, None, stride=2, padding=pad, output_padding=opad)
         x = F.relu(s.bn(x, "deconv_layers.%d.0.1" % i))
         k = 1
         while s.has("deconv_layers.%d.%d.0.conv1.weight" % (i, k)):

@@ -84,7 +84,7 @@ class Bottleneck(nn.Module):
 
 
 class HighResolutionModule(nn.Module):
-    """Parameter container of pose_higher_hrnet.py:119-256 (BASIC blocks)."""
+    """Parameter container of pose_higher_hrnet.py:119-256 (BASIC or BOTTLENECK blocks)."""
 
     def __init__(self, num_branches, blocks, num_blocks, num_inchannels, num_channels,
                  fuse_method, multi_scale_output=True):
@@ -330,18 +330,24 @@ class _Recorder:
         self._emit_conv(d, x, packed, b, residual, out, addends=addends, out2=out2)
         return out
 
-    def deconv4x4s2(self, x, deconv, bn, cin_store, lanes=(0, 1, 2, 3)):
-        """ConvTranspose2d(k4,s2,p1)+BN+ReLU as four output-parity 2x2 convs (independent:
-        they write disjoint pixels of the output, one lane each)."""
+    # output-parity phases of ConvTranspose2d(stride 2): output row 2*y + a takes the kernel rows kh from
+    # input rows y + dy, as (dy, kh) lists per kernel size (padding / output_padding of
+    # pose_higher_hrnet.py:535-546: k4 p1, k3 p1 op1, k2 p0); columns alike
+    _DECONV_SEL = {4: ([(0, 1), (-1, 3)], [(1, 0), (0, 2)]),
+                   3: ([(0, 1)], [(1, 0), (0, 2)]),
+                   2: ([(0, 0)], [(0, 1)])}
+
+    def deconv_s2(self, x, deconv, bn, cin_store, lanes=(0, 1, 2, 3)):
+        """ConvTranspose2d(k, stride 2)+BN+ReLU as four output-parity convs of up to 2x2 taps
+        (independent: they write disjoint pixels of the output, one lane each)."""
         cout = deconv.out_channels
         out = self.new(x.n, 2 * x.h, 2 * x.w, cout)
+        sel = self._DECONV_SEL[deconv.kernel_size[0]]
         for a in (0, 1):
-            ysel = [(0, 1), (-1, 3)] if a == 0 else [(1, 0), (0, 2)]       # (dy, kh)
             for bb in (0, 1):
-                xsel = [(0, 1), (-1, 3)] if bb == 0 else [(1, 0), (0, 2)]
                 taps, khkw = [], []
-                for dy, kh in ysel:
-                    for dx, kw in xsel:
+                for dy, kh in sel[a]:
+                    for dx, kw in sel[bb]:
                         taps.append((dy, dx))
                         khkw.append((kh, kw))
                 d = self._desc(x, 0, cin_store, taps, 1, x.h, x.w, out, 2, a, bb, cout, cout, 0,
@@ -353,6 +359,8 @@ class _Recorder:
                 self._emit_conv(d, x, packed, b, None, out, group=("deconv", id(out)))
                 self.lane = keep
         return out
+
+    deconv4x4s2 = deconv_s2
 
     def _desc(self, x, in_coff, cin, taps, stride, hm, wm, out, out_scale, oy, ox, cout,
               cout_store, out_coff, residual, relu):
@@ -383,6 +391,19 @@ class _Recorder:
         for t in [x, residual, out, out2] + adds:
             if t is not None:
                 self._touch(t, idx)
+
+    def block(self, x, blk, out=None):
+        """One residual block (BasicBlock :46-75 or Bottleneck :78-116) -> output tensor; ``out``:
+        the virtual tensor the block's last conv writes (a concat buffer)."""
+        res = x
+        if blk.downsample is not None:
+            res = self.conv(x, blk.downsample[0], blk.downsample[1], False)
+        if isinstance(blk, Bottleneck):
+            t = self.conv(x, blk.conv1, blk.bn1, True)
+            t = self.conv(t, blk.conv2, blk.bn2, True)
+            return self.conv(t, blk.conv3, blk.bn3, True, residual=res, out=out)
+        t = self.conv(x, blk.conv1, blk.bn1, True)
+        return self.conv(t, blk.conv2, blk.bn2, True, residual=res, out=out)
 
     def stem(self, conv, bn):
         cout = conv.out_channels                                           # (64,3,3,3)
@@ -765,23 +786,22 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
                  deconv_cat=[True], with_ae_loss=(True, False)):
         super().__init__()
         for bt in (s2_block_type, s3_block_type, s4_block_type):
-            if bt != "BASIC":
-                raise NotImplementedError("stage block type %r: only BASIC stages (the W32/W48 "
-                                          "configurations) are implemented" % bt)
-        if final_conv_ksize != 1:
-            raise NotImplementedError("final_conv_ksize=%r: only the 1x1 heads of the W48 "
-                                      "configuration are implemented" % final_conv_ksize)
-        if deconvs > 1 or any(k != 4 for k in deconv_ksize[:deconvs]):
-            raise NotImplementedError("only one 4x4/stride-2 deconv stage is implemented")
+            if bt not in self.BLOCK_TYPES:
+                raise KeyError(bt)                      # like the reference's BLOCK_TYPES lookup
+        if final_conv_ksize not in (1, 3):
+            raise ValueError("final_conv_ksize must be 1 or 3 (pose_higher_hrnet.py:460-482)")
+        if any(k not in (2, 3, 4) for k in deconv_ksize[:deconvs]):
+            raise ValueError("deconv kernel sizes must be 2, 3 or 4 (pose_higher_hrnet.py:535-546)")
         self.inplanes = inplanes
         self.cfg = {"NUM_JOINTS": num_joints, "TAG_PER_JOINT": tag_per_joint,
                     "FINAL_CONV_KSIZE": final_conv_ksize, "PRETRAINED_LAYERS": pretrained_layers}
-        stages = [("STAGE2", s2_modules, s2_branches, s2_blocks, s2_chans, s2_fuse_method),
-                  ("STAGE3", s3_modules, s3_branches, s3_blocks, s3_chans, s3_fuse_method),
-                  ("STAGE4", s4_modules, s4_branches, s4_blocks, s4_chans, s4_fuse_method)]
-        for name, nm, nb, blocks, chans, fm in stages:
-            self.cfg[name] = {"num_modules": nm, "num_branches": nb, "block_cls": BasicBlock,
-                              "num_blocks": blocks, "num_channels": chans, "fuse_method": fm}
+        stages = [("STAGE2", s2_modules, s2_branches, s2_blocks, s2_chans, s2_fuse_method, s2_block_type),
+                  ("STAGE3", s3_modules, s3_branches, s3_blocks, s3_chans, s3_fuse_method, s3_block_type),
+                  ("STAGE4", s4_modules, s4_branches, s4_blocks, s4_chans, s4_fuse_method, s4_block_type)]
+        for name, nm, nb, blocks, chans, fm, bt in stages:
+            self.cfg[name] = {"num_modules": nm, "num_branches": nb,
+                              "block_cls": self.BLOCK_TYPES[bt], "num_blocks": blocks,
+                              "num_channels": chans, "fuse_method": fm}
         self.cfg["DECONV"] = {"num_deconvs": deconvs, "num_channels": deconv_chans,
                               "kernel_size": deconv_ksize, "num_basic_blocks": deconv_num_blocks,
                               "cat_output": deconv_cat}
@@ -795,15 +815,16 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
         self.layer1 = self._make_layer(Bottleneck, 64, 4)
 
         pre = [256]
-        for si, (name, nm, nb, blocks, chans, fm) in enumerate(stages):
-            cur = [c * BasicBlock.expansion for c in chans]
+        for si, (name, nm, nb, blocks, chans, fm, bt) in enumerate(stages):
+            block_cls = self.BLOCK_TYPES[bt]
+            cur = [c * block_cls.expansion for c in chans]
             setattr(self, "transition%d" % (si + 1), self._make_transition_layer(pre, cur))
             last_stage = si == len(stages) - 1
             mods = []
             inch = cur
             for m in range(nm):
                 multi = not (last_stage and m == nm - 1)
-                mods.append(HighResolutionModule(nb, BasicBlock, blocks, inch, chans, fm, multi))
+                mods.append(HighResolutionModule(nb, block_cls, blocks, inch, chans, fm, multi))
                 inch = mods[-1].get_num_inchannels()
             setattr(self, "stage%d" % (si + 2), nn.Sequential(*mods))
             pre = inch
@@ -825,9 +846,10 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
             if deconv_cat[i]:
                 cin += num_joints + (ae_dims if with_ae_loss[i] else 0)
             cout = deconv_chans[i]
+            dk = deconv_ksize[i]                        # _get_deconv_cfg (:535-546)
             layers = [nn.Sequential(
-                nn.ConvTranspose2d(cin, cout, kernel_size=4, stride=2, padding=1,
-                                   output_padding=0, bias=False),
+                nn.ConvTranspose2d(cin, cout, kernel_size=dk, stride=2, padding=0 if dk == 2 else 1,
+                                   output_padding=1 if dk == 3 else 0, bias=False),
                 nn.BatchNorm2d(cout, momentum=BN_MOMENTUM), nn.ReLU(inplace=True))]
             layers += [nn.Sequential(BasicBlock(cout, cout)) for _ in range(deconv_num_blocks)]
             dls.append(nn.Sequential(*layers))
@@ -926,7 +948,8 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
         # HRNet cross-resolution fuse-add in the conv epilogues (tcgen05 bf16 path); the stand-alone
         # fuse_sum kernel stays for the fp32 modes and as the A/B reference (fuse_in_epilogue = False)
         fuse_epi = bool(self.fuse_in_epilogue and R.tc and not R.split and
-                        self.conv_engine != L.ENGINE_FFMA)
+                        self.conv_engine != L.ENGINE_FFMA and
+                        all(self.cfg[k]["block_cls"] is BasicBlock for k in ("STAGE2", "STAGE3", "STAGE4")))
         head0 = self.final_layers[0]
         cat = self.deconv_cat[0] if self.num_deconvs else False
         cat_ld = None
@@ -964,9 +987,7 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
                         if bi >= len(mod.branches[i]):
                             continue
                         R.lane = i if par else 0
-                        blk = mod.branches[i][bi]
-                        t = R.conv(xs[i], blk.conv1, blk.bn1, True)
-                        xs[i] = R.conv(t, blk.conv2, blk.bn2, True, residual=xs[i])
+                        xs[i] = R.block(xs[i], mod.branches[i][bi])
                 outs = []
                 nout = len(mod.fuse_layers)
                 terms_of = [[None] * mod.num_branches for _ in range(nout)]
@@ -995,35 +1016,43 @@ class PoseHigherResolutionNet(_PlanRunner, nn.Module):
         R.lane = 0
 
         x = ys[0]
-        c0 = head0.in_channels
         odt = torch.float16 if out_half else torch.float32
-        y0_out = torch.empty((n, head0.out_channels, x.h, x.w), dtype=odt, device=device)
-        outs = [y0_out]
-        if cat:
-            pad_store = cat_ld - c0
-            R.conv(x, head0, None, False, out=x, out_coff=c0, in_coff=0, cin_store=c0,
-                   cout_store=pad_store, pad_cout=True)
-            R.lane = 1 if par else 0
-            R.to_nchw(x, head0.out_channels, c0, y0_out)
-            R.lane = 0
-        else:
-            y = R.conv(x, head0, None, False, cout_store=(head0.out_channels + 15) // 16 * 16,
-                       pad_cout=True)
-            R.to_nchw(y, head0.out_channels, 0, y0_out)
-        for i in range(self.num_deconvs):
-            dl = self.deconv_layers[i]
-            x = R.deconv4x4s2(x, dl[0][0], dl[0][1], x.cl if cat else dl[0][0].in_channels,
-                              lanes=(0, 1, 2, 3) if par else (0,))
-            for k in range(1, len(dl)):
-                blk = dl[k][0]
-                t = R.conv(x, blk.conv1, blk.bn1, True)
-                x = R.conv(t, blk.conv2, blk.bn2, True, residual=x)
-            head = self.final_layers[i + 1]
-            y = R.conv(x, head, None, False, cout_store=(head.out_channels + 15) // 16 * 16,
-                       pad_cout=True)
+        outs = []
+        nd = self.num_deconvs
+        for i in range(nd + 1):
+            head = self.final_layers[i]
+            c0 = head.in_channels
             yo = torch.empty((n, head.out_channels, x.h, x.w), dtype=odt, device=device)
-            R.to_nchw(y, head.out_channels, 0, yo)
             outs.append(yo)
+            if i < nd and self.deconv_cat[i]:
+                # torch.cat((x, y), 1) is never built: x already lives in channels [0, c0) of a buffer
+                # that is wide enough for the head's channels, which the head writes behind it
+                assert x.cl >= c0 + head.out_channels, "concat buffer was not reserved"
+                R.lane = 0
+                R.conv(x, head, None, False, out=x, out_coff=c0, in_coff=0, cin_store=c0,
+                       cout_store=x.cl - c0, pad_cout=True)
+                R.lane = 1 if par else 0
+                R.to_nchw(x, head.out_channels, c0, yo)
+                R.lane = 0
+                dc_cin = x.cl
+            else:
+                y = R.conv(x, head, None, False, cin_store=c0,
+                           cout_store=(head.out_channels + 15) // 16 * 16, pad_cout=True)
+                R.to_nchw(y, head.out_channels, 0, yo)
+                dc_cin = c0
+            if i == nd:
+                break
+            dl = self.deconv_layers[i]
+            x = R.deconv_s2(x, dl[0][0], dl[0][1], dc_cin, lanes=(0, 1, 2, 3) if par else (0,))
+            nblocks = len(dl) - 1
+            for k in range(1, len(dl)):
+                dst = None
+                if k == nblocks and i + 1 < nd and self.deconv_cat[i + 1]:
+                    nxt_head = self.final_layers[i + 1]
+                    dst = R.new(n, x.h, x.w, (x.cl + nxt_head.out_channels + 15) // 16 * 16)
+                x = R.block(x, dl[k][0], out=dst)
+            if nblocks == 0 and i + 1 < nd and self.deconv_cat[i + 1]:
+                raise NotImplementedError("deconv_cat after a deconv stage without blocks")
         return R, outs
 
     def _record_module_fused(self, R, mod, xs, par, dst0):

@@ -50,8 +50,10 @@ def test_invalid_configurations_raise():
     import pytest
     with pytest.raises(ValueError):
         rtpe_b200.HighResolutionModule(2, rtpe_b200.BasicBlock, [4], [48, 96], [48, 96], "SUM")
-    with pytest.raises(NotImplementedError):
-        rtpe_b200.PoseHigherResolutionNet(s2_block_type="BOTTLENECK")
+    with pytest.raises(KeyError):
+        rtpe_b200.PoseHigherResolutionNet(s2_block_type="NOPE")
+    with pytest.raises(ValueError):
+        rtpe_b200.PoseHigherResolutionNet(final_conv_ksize=5)
     with pytest.raises(ValueError):
         rtpe_b200.HeatmapParser(17, 30, 0.1, 1.0, True, False, munkres_start_rule="nope")
 

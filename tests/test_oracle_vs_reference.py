@@ -56,6 +56,33 @@ def test_model_oracle_vs_reference(ref):
         assert ((a - b).abs().max() / b.abs().max()).item() <= 1e-5
 
 
+@pytest.mark.parametrize("name", ["two_deconvs_k3_heads", "bottleneck_stages_k3_k2_deconvs",
+                                  "no_deconv_shared_tag"])
+def test_model_variants_oracle_and_dropin_vs_reference(ref, name):
+    """constructor options the W48 teacher does not use (BOTTLENECK stages, 3x3 heads, several deconv
+    stages with kernel sizes 4 / 3 / 2): the drop-in has the reference's state-dict layout and the
+    oracle reproduces the reference's outputs."""
+    from oracle.hhrnet_ref import hhrnet_forward_ref
+    from oracle.variants import variant_kwargs
+    from oracle.weights import fill_params_deterministic
+    _, ref_model = ref
+    net = ref_model.PoseHigherResolutionNet(**variant_kwargs(name)).eval()
+    fill_params_deterministic(net, 31)
+    mine = rtpe_b200.PoseHigherResolutionNet(**variant_kwargs(name))
+    a, b = net.state_dict(), mine.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+    mine.load_state_dict(a, strict=True)
+    x = torch.randn(1, 3, 64, 96, generator=torch.Generator().manual_seed(32))
+    with torch.no_grad():
+        want = net(x)
+        got = hhrnet_forward_ref(net.state_dict(), x)
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape
+        assert ((g - w).abs().max() / w.abs().max()).item() <= 1e-5
+
+
 def test_dropin_state_dict_matches_reference(ref):
     _, ref_model = ref
     a = ref_model.PoseHigherResolutionNet().state_dict()
