@@ -636,9 +636,26 @@ class _PlanRunner:
         self._plans = {}
         self._sig = None
 
+    def load_state_dict(self, *args, **kwargs):
+        """nn.Module.load_state_dict + the compiled plans (BN-folded, packed weights) are dropped."""
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_plans()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        """.to() / .cuda() / .half() / .float(): the packed weights follow the parameters."""
+        out = super()._apply(fn, *args, **kwargs)
+        if hasattr(self, "_plans"):
+            self.invalidate_plans()
+        return out
+
     def _signature(self):
         """Cheap fingerprint of every parameter / buffer (storage address + in-place version
-        counter): load_state_dict, .half(), .to() and optimizer steps all change it."""
+        counter): load_state_dict, .half(), .to() and optimizer steps all change it.  Writes
+        through ``.data`` (``p.data.copy_()``, the reference's fp16_utils
+        ``master_params_to_model_params``) do NOT bump the version counter: call
+        ``invalidate_plans()`` after such an update, the cached plans keep the old folded weights
+        otherwise (a content checksum would cost a device read + host sync per forward)."""
         acc = 0
         for t in list(self.parameters()) + list(self.buffers()):
             acc = (acc * 1000003 + t.data_ptr() * 31 + t._version) & 0xFFFFFFFFFFFFFFFF

@@ -37,27 +37,52 @@ def get_multi_scale_size(image_hw, input_size, current_scale, min_scale):
     return (w_resized, h_resized), center, np.array([scale_w, scale_h])
 
 
-def get_affine_transform(center, scale, output_size):
-    """transforms.py:59-93 for rot = 0, shift = 0, inv = 0.  The reference solves
-    ``cv2.getAffineTransform`` for three float32 point pairs that describe an isotropic scale
-    s = dst_w / (200 * scale[0]) about ``center``; this is that solution in closed form."""
-    src_w = np.float32(scale[0] * 200.0)
+def _affine_points(center, scale, output_size):
+    """The three float32 point pairs of transforms.py:59-90 (rot = 0, shift = 0): the centre, the point
+    half a source width above it and their perpendicular third point (``get_3rd_point``)."""
+    src_w = np.asarray(scale, np.float64)[0] * 200.0
     dst_w, dst_h = output_size[0], output_size[1]
-    cx, cy = np.float32(center[0]), np.float32(center[1])
-    sy1 = np.float32(cy + np.float32(src_w * np.float32(-0.5)))
-    dcx, dcy = np.float32(dst_w * 0.5), np.float32(dst_h * 0.5)
-    dy1 = np.float32(dcy + np.float32(np.float32(dst_w) * np.float32(-0.5)))
-    s = (float(dy1) - float(dcy)) / (float(sy1) - float(cy))
-    return np.array([[s, 0.0, float(dcx) - s * float(cx)],
-                     [0.0, s, float(dcy) - s * float(cy)]], dtype=np.float64)
+    src = np.zeros((3, 2), dtype=np.float32)
+    dst = np.zeros((3, 2), dtype=np.float32)
+    src[0, :] = np.asarray(center)
+    src[1, :] = np.asarray(center) + np.array([0.0, src_w * -0.5])
+    dst[0, :] = [dst_w * 0.5, dst_h * 0.5]
+    dst[1, :] = np.array([dst_w * 0.5, dst_h * 0.5]) + np.array([0, dst_w * -0.5], np.float32)
+    for p in (src, dst):
+        d = p[0, :] - p[1, :]
+        p[2, :] = p[1, :] + np.array([-d[1], d[0]], dtype=np.float32)
+    return src, dst
+
+
+def _solve_affine(src, dst):
+    """``cv2.getAffineTransform(src, dst)``: the 2x3 matrix through three point pairs.  With OpenCV
+    present (it is wherever the reference runs) its own solver is called, so the matrix is the
+    reference's bit for bit -- float32 points make it slightly anisotropic, which a closed-form
+    isotropic scale does not reproduce; without it the same 6x6 system is solved in float64."""
+    try:
+        import cv2
+        return cv2.getAffineTransform(np.float32(src), np.float32(dst))
+    except ImportError:
+        a = np.zeros((6, 6))
+        b = np.zeros(6)
+        for i in range(3):
+            a[2 * i, 0:2], a[2 * i, 2] = src[i], 1.0
+            a[2 * i + 1, 3:5], a[2 * i + 1, 5] = src[i], 1.0
+            b[2 * i], b[2 * i + 1] = dst[i]
+        return np.linalg.solve(a, b).reshape(2, 3)
+
+
+def get_affine_transform(center, scale, output_size):
+    """transforms.py:59-93 for rot = 0, shift = 0, inv = 0."""
+    src, dst = _affine_points(center, scale, output_size)
+    return np.asarray(_solve_affine(src, dst), np.float64)
 
 
 def get_inverse_affine_transform(center, scale, output_size):
     """transforms.py:59-93 with inv = 1 (``cv2.getAffineTransform(dst, src)``): maps heat-map /
     network-input coordinates back to the original image."""
-    m = get_affine_transform(center, scale, output_size)
-    s = m[0, 0]
-    return np.array([[1.0 / s, 0.0, -m[0, 2] / s], [0.0, 1.0 / s, -m[1, 2] / s]], dtype=np.float64)
+    src, dst = _affine_points(center, scale, output_size)
+    return np.asarray(_solve_affine(dst, src), np.float64)
 
 
 def transform_preds(coords, center, scale, output_size):

@@ -174,8 +174,21 @@ class TeacherDumper:
         self._inflight = None
         slot.event.synchronize()                   # the copy has landed in the pinned buffers
         p0, p1 = slot.y0.numpy(), slot.y1.numpy()
-        for i, path in enumerate(paths):
-            self.writer.submit(path, p0[i], p1[i], on_done=slot.release_one)
+        submitted = 0
+        try:
+            for i, path in enumerate(paths):
+                self.writer.submit(path, p0[i], p1[i], on_done=slot.release_one)
+                submitted += 1
+        except BaseException:
+            # submit() re-raises worker errors (disk full, ...): the files that were never handed over
+            # will not call release_one, so take them off the slot's count -- otherwise the next
+            # dump_batch / close that re-uses the slot waits for ever instead of seeing the exception
+            with slot.cv:
+                slot.pending -= len(paths) - submitted
+                if slot.pending <= 0:
+                    slot.pending = 0
+                    slot.cv.notify_all()
+            raise
 
     @torch.no_grad()
     def dump_batch(self, x, img_paths):
