@@ -202,6 +202,10 @@ typedef struct brtpe_conv_desc {
   int32_t n_add;
   int32_t add_ld[3], add_shift[3];
   int32_t out2_ld;
+  /* 1: walk the output tiles from the last image to the first (halo engine).  Activations at the
+   * bench's chunk are larger than the 126 MB L2: a layer that starts where its producer ended finds the
+   * most recently written / read part of its input and residual still in the L2. */
+  int32_t reverse_order;
 } brtpe_conv_desc;
 
 /* FFMA path weights: float32 [ntaps][Cin][Cout].  UMMA path weights: bf16

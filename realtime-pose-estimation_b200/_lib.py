@@ -50,7 +50,7 @@ class ConvDesc(C.Structure):
                 ("res_ld", C.c_int32), ("res_coff", C.c_int32),
                 ("relu", C.c_int32), ("Cout_store", C.c_int32),
                 ("n_add", C.c_int32), ("add_ld", C.c_int32 * 3), ("add_shift", C.c_int32 * 3),
-                ("out2_ld", C.c_int32)]
+                ("out2_ld", C.c_int32), ("reverse_order", C.c_int32)]
 
 
 class PrepackDesc(C.Structure):

@@ -59,6 +59,8 @@ struct alignas(64) HaloParams {
   int nkb_seg, lo_off;          // split (BRTPE_DT_BF16X2): num_kb = 3 segments [hi | lo | hi] of
                                 // nkb_seg 64-channel blocks; the lo half starts lo_off channels in
   int a_stages, b_stages, b_stage_bytes, a_stage_bytes;
+  int reverse;                  // 1: tiles are walked from the last image to the first (L2 reuse between
+                                // consecutive layers, brtpe_conv_desc.reverse_order)
   int s2_ld;                    // stride 2: input pixel stride (the second pixel of a column pair)
   int s2;                       // 1: 3x3 / stride 2 (four pixel-parity planes per tile instead of one halo tile)
   int a_tile_bytes;             // shared-memory bytes of one pixel tile's activations (1024-aligned)
@@ -133,12 +135,14 @@ struct TileOrg {
 __device__ __forceinline__ TileOrg tile_origin(const HaloParams& p, int mt) {
   TileOrg o;
   const int tiles_xy = p.tiles_x * p.tiles_y;
+  const bool past_end = mt >= p.m_tiles;
+  if (p.reverse && !past_end) mt = p.m_tiles - 1 - mt;
   o.n = (int)fdiv((uint32_t)mt, p.fd_xy);
   const int rem = mt - o.n * tiles_xy;
   const int ty = (int)fdiv((uint32_t)rem, p.fd_x);
   o.y0 = ty * HL_TH;
   o.x0 = (rem - ty * p.tiles_x) * HL_TW;
-  if (mt >= p.m_tiles) o.n = p.N;
+  if (past_end) o.n = p.N;
   return o;
 }
 
@@ -979,6 +983,11 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
   P->res_encoded = nullptr;
   HaloParams& p = P->p;
   memset(&p, 0, sizeof(p));
+  {
+    static int rev = -1;                     // BRTPE_HALO_REVERSE=0 ignores reverse_order (A/B switch)
+    if (rev < 0) rev = getenv("BRTPE_HALO_REVERSE") ? atoi(getenv("BRTPE_HALO_REVERSE")) : 1;
+    p.reverse = (rev && d->reverse_order) ? 1 : 0;
+  }
   p.s2 = d->in_stride == 2 ? 1 : 0;
   p.s2_ld = d->in_ld;
   p.N = d->N; p.H = d->Hm; p.W = d->Wm;             // tiles walk the OUTPUT pixels (== input for stride 1)
