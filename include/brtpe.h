@@ -220,6 +220,18 @@ int brtpe_conv_run_fused(const brtpe_conv_desc* d, const void* in, const void* w
                          const float* bias, const void* residual, void* out,
                          const void* const* add_ptrs, void* out2, void* stream);
 
+/* BasicBlock body in ONE launch (rtpe/third_party/pose_higher_hrnet.py:46-75: conv1 + bn1 + relu ->
+ * conv2 + bn2, += residual, relu): d0 / d1 describe two 3x3 stride-1 bf16 layers of equal geometry and
+ * width (<= 64 channels, both with ReLU), `mid` receives conv1's output (written in full, as by two
+ * brtpe_conv_run calls), `residual` is added by conv2.  The launch walks the batch in sub-batches with
+ * conv2 one phase behind conv1, so that a sub-batch's input, intermediate and output are still in the
+ * L2 when conv2 reads them (three tensor passes through HBM instead of five at batch sizes whose
+ * tensors exceed the L2).  Results are bit-identical to two brtpe_conv_run calls.  Plans use it on
+ * their own (BRTPE_CHAIN=0 switches it off); BRTPE_EINVAL when the pair is not chainable. */
+int brtpe_conv_chain_run(const brtpe_conv_desc* d0, const void* in, const void* w0,
+                         const float* bias0, void* mid, const brtpe_conv_desc* d1, const void* w1,
+                         const float* bias1, const void* residual, void* out, void* stream);
+
 /* Engine brtpe_conv_run / brtpe_plan_add_conv will use for this descriptor
  * (BRTPE_ENGINE_FFMA, BRTPE_ENGINE_UMMA or BRTPE_ENGINE_UMMA_HALO), or a negative error code. */
 int brtpe_conv_select_engine(const brtpe_conv_desc* d);

@@ -92,6 +92,7 @@ _SIGS = {
                                                                  C.c_float, _P, _P, _P]),
     "brtpe_conv_run": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
     "brtpe_conv_run_fused": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, C.POINTER(_P), _P, _P]),
+    "brtpe_conv_chain_run": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, C.POINTER(ConvDesc), _P, _P, _P, _P, _P]),
     "brtpe_plan_set_conv_fuse": (_I, [_P, C.POINTER(_P), _P]),
     "brtpe_conv_select_engine": (_I, [C.POINTER(ConvDesc)]),
     "brtpe_umma_weight_dims": (_I, [_I, _I, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

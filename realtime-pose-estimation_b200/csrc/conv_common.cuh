@@ -26,6 +26,13 @@ void halo_conv_release(HaloConvPrepared*);
 int halo_conv_launch(const HaloConvPrepared* p, const float* bias, const void* residual, void* out,
                      cudaStream_t st, const void* const* add_ptrs = nullptr, void* out2 = nullptr);
 
+// chain mode of the halo engine: conv1 -> conv2 (+ residual) of a BasicBlock in one launch whose work
+// list keeps a sub-batch's tensors in L2 (conv_halo_impl.cuh); nullptr when the pair is not chainable
+HaloConvPrepared* halo_chain_prepare(const brtpe_conv_desc* d0, const void* in, const void* w0, void* mid,
+                                     const brtpe_conv_desc* d1, const void* w1, void* out);
+int halo_chain_launch(const HaloConvPrepared* p, const float* bias0, const float* bias1,
+                      const void* residual, void* out, cudaStream_t st);
+
 int stem_conv1_launch(const void* img, int img_is_half, int N, int H, int W, const float* w,
                       const float* bias, int Cout, void* out, int out_dtype, cudaStream_t st);
 int stem_im2col_launch(const void* img, int img_is_half, int N, int H, int W, void* out,

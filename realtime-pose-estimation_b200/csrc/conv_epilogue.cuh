@@ -57,13 +57,15 @@ struct Chunk32 {
 __device__ __forceinline__ Chunk32 ld_chunk32(const __nv_bfloat16* p, bool vec32) {
   Chunk32 c;
   if (vec32) {
-    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    // (not .nc: under programmatic dependent launch the predecessor may still be writing other
+    // buffers while this kernel is resident -- .nc promises read-only data for the kernel's lifetime)
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(c.w[0]), "=r"(c.w[1]), "=r"(c.w[2]), "=r"(c.w[3]), "=r"(c.w[4]),
                    "=r"(c.w[5]), "=r"(c.w[6]), "=r"(c.w[7])
                  : "l"(p));
   } else {
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
-    const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    const uint4 a = *reinterpret_cast<const uint4*>(p);
+    const uint4 b = *(reinterpret_cast<const uint4*>(p) + 1);
     c.w[0] = a.x; c.w[1] = a.y; c.w[2] = a.z; c.w[3] = a.w;
     c.w[4] = b.x; c.w[5] = b.y; c.w[6] = b.z; c.w[7] = b.w;
   }

@@ -700,6 +700,7 @@ __global__ void __launch_bounds__(256) fuse_sum_split_kernel(FuseArgs a) {
 // Same left-to-right fp32 summation order as the generic kernel.
 template <int U, int NT>
 __global__ void __launch_bounds__(256) fuse_sum_bf16x8_rows_kernel(FuseArgs a) {
+  pdl_wait();                                  // PDL (common.cuh): the terms are the predecessors' outputs
   const int px = blockDim.y;
   const int c = threadIdx.x << 3;
   const int y = blockIdx.y, n = blockIdx.z;
@@ -725,10 +726,11 @@ __global__ void __launch_bounds__(256) fuse_sum_bf16x8_rows_kernel(FuseArgs a) {
 #pragma unroll
       for (int j = 0; j < U; ++j) {
         const int x = x0 + j * px;
-        if (x < a.W) v[k][j] = __ldg(reinterpret_cast<const uint4*>(rowp[k] + (x >> sh) * ld));
+        if (x < a.W) v[k][j] = *reinterpret_cast<const uint4*>(rowp[k] + (x >> sh) * ld);
       }
     }
   }
+  pdl_trigger();
 #pragma unroll
   for (int j = 0; j < U; ++j) {
     const int x = x0 + j * px;
@@ -1019,10 +1021,10 @@ int fuse_sum_launch(int dtype, int nterms, const void* const* terms, const int32
     dim3 grid(ceil_div(W, U * px), H, N);
 #define BRTPE_FUSE(UU)                                                                         \
   switch (nterms) {                                                                            \
-    case 1: fuse_sum_bf16x8_rows_kernel<UU, 1><<<grid, block, 0, st>>>(a); break;              \
-    case 2: fuse_sum_bf16x8_rows_kernel<UU, 2><<<grid, block, 0, st>>>(a); break;              \
-    case 3: fuse_sum_bf16x8_rows_kernel<UU, 3><<<grid, block, 0, st>>>(a); break;              \
-    default: fuse_sum_bf16x8_rows_kernel<UU, 4><<<grid, block, 0, st>>>(a); break;             \
+    case 1: launch_ex(fuse_sum_bf16x8_rows_kernel<UU, 1>, grid, block, 0, st, 0, true, a); break;              \
+    case 2: launch_ex(fuse_sum_bf16x8_rows_kernel<UU, 2>, grid, block, 0, st, 0, true, a); break;              \
+    case 3: launch_ex(fuse_sum_bf16x8_rows_kernel<UU, 3>, grid, block, 0, st, 0, true, a); break;              \
+    default: launch_ex(fuse_sum_bf16x8_rows_kernel<UU, 4>, grid, block, 0, st, 0, true, a); break;             \
   }
     if (U == 1) { BRTPE_FUSE(1) }
     else if (U == 4) { BRTPE_FUSE(4) }

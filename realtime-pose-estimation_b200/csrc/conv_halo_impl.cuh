@@ -83,6 +83,27 @@ struct alignas(64) HaloParams {
   FastDiv fd_xy, fd_x, fd_nt;
   const float* bias;
   EpiParams epi;
+  // Chain mode (conv1 -> conv2 of a BasicBlock in ONE launch, halo_chain_prepare): the work list
+  // interleaves sub-batches of the two layers -- [L0 s0][L0 s1][L1 s0][L0 s2][L1 s1] ... -- so that a
+  // sub-batch's block input, intermediate and output (3 x ch_ip*2 tiles) are still in L2 when
+  // layer 1 reads them; a layer-1 tile waits for the layer-0 tiles of ITS image (ch_count).
+  int chain;                    // 1: chain mode
+  int ch_ip, ch_S;              // work items per phase (= one sub-batch of one layer), sub-batches
+  FastDiv fd_ip;
+  CUtensorMap tmap_a1;          // layer 1 reads the intermediate tensor
+  CUtensorMap tmap_b1;          // layer-1 weights (resident next to layer 0's)
+  int in_coff1;
+  const float* bias1;
+  __nv_bfloat16* out1;          // layer-1 output / residual (p.epi describes layer 0)
+  const __nv_bfloat16* res1;
+  int out1_ld, out1_coff, res1_ld, res1_coff;
+  int* ch_count;                // [N] epilogue-warp completions of layer 0 per image, [N] = CTAs done
+  int ch_need;                  // completions that make an image ready: tiles per image x 4 warps
+  int ch_defer;                 // 1: an epilogue warp counts item i when it starts item i+1 (its stores have
+                                // landed by then, the fence costs nothing); needs phases of >= 2 grid rounds
+  int ch_pf;                    // layer-0 activation tiles are prefetched into L2 this many items ahead
+  int ch_dbg;                   // debug (BRTPE_CHAIN_DBG, timing only, results may be wrong): 1 no
+                                // completion signal / fence, 2 no dependency wait
   long long* prof;              // debug: per-CTA role/wait cycle counters
   int dbg;                      // debug (BRTPE_HALO_DBG): 1 no MMA issue, 2 no epilogue work,
                                 // 4 no weight loads, 8 no activation loads (results are garbage)
@@ -116,6 +137,13 @@ struct HaloConvPrepared {
   const void* out_encoded;      // output pointer tmap_o was encoded for
   const void* res_encoded;      // residual pointer tmap_r was encoded for (mutable cache)
   CUtensorMap tmap_r_cache;
+  // chain mode (halo_chain_prepare): second layer + the intermediate tensor + the image counters
+  brtpe_conv_desc d1;
+  void* mid = nullptr;
+  int* counters = nullptr;
+  ~HaloConvPrepared() {
+    if (counters) cudaFree(counters);
+  }
 };
 
 // descriptor halves (see make_kmajor_sw128_desc): lo = start>>4 | LBO(1)<<16, hi = SBO>>4 |
@@ -146,20 +174,54 @@ __device__ __forceinline__ TileOrg tile_origin(const HaloParams& p, int mt) {
   return o;
 }
 
+// work item -> (layer, unit of tpc*cg pixel tiles).  Plain kernels: unit = item / n_tiles.  Chain
+// mode (n_tiles == 1): phase ph = item / ch_ip of the interleaved list (see HaloParams).
+template <bool CHAIN>
+__device__ __forceinline__ int item_unit(const HaloParams& p, int item, int& layer) {
+  if constexpr (CHAIN) {
+    const int ph = (int)fdiv((uint32_t)item, p.fd_ip);
+    const int r = item - ph * p.ch_ip;
+    int s;
+    if (ph == 0) { layer = 0; s = 0; }
+    else if (ph == 2 * p.ch_S - 1) { layer = 1; s = p.ch_S - 1; }
+    else if (ph & 1) { layer = 0; s = (ph + 1) >> 1; }
+    else { layer = 1; s = (ph >> 1) - 1; }
+    return s * p.ch_ip + r;
+  } else {
+    layer = 0;
+    return (int)fdiv((uint32_t)item, p.fd_nt);
+  }
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() {
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
 // ---- epilogue, fast path: one 64-channel round of residual in flight ahead of the math
 struct EpiPix {
   bool valid;
   size_t opix;
   int n, y, x;                   // output pixel (fuse addends are indexed at (y >> s, x >> s))
 };
+template <bool CHAIN = false>
 __device__ __forceinline__ EpiPix epi_pixel(const HaloParams& p, int item, int tile, int m,
-                                            int rank) {
+                                            int rank, int* layer_out = nullptr) {
   EpiPix e;
   e.valid = false;
   e.opix = 0;
   e.n = e.y = e.x = 0;
+  if (layer_out) *layer_out = 0;
   if (item >= p.num_items) return e;
-  const int unit = (int)fdiv((uint32_t)item, p.fd_nt);
+  int layer = 0;
+  const int unit = item_unit<CHAIN>(p, item, layer);
+  if (layer_out) *layer_out = layer;
   const int mt = unit * (p.tpc * p.cg) + rank * p.tpc + tile;
   const TileOrg o = tile_origin(p, mt);
   const int y = o.y0 + (m >> 3), x = o.x0 + (m & 7);
@@ -169,16 +231,21 @@ __device__ __forceinline__ EpiPix epi_pixel(const HaloParams& p, int item, int t
   return e;
 }
 
-template <bool RES>
+template <bool RES, bool CHAIN = false>
 __device__ __forceinline__ void epi_fetch_round(Chunk32 (&r)[4], const __nv_bfloat16* rp,
                                                 bool valid, int c0, int nchunks) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    if (RES && valid && c0 + j < nchunks) r[j] = ld_chunk32(rp + (c0 + j) * 16, true);
+    if (RES && valid && c0 + j < nchunks) {
+      r[j] = ld_chunk32(rp + (c0 + j) * 16, true);
+    } else if (CHAIN) {                       // a layer without residual follows one with: zeros
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[j].w[i] = 0u;
+    }
   }
 }
 
-template <bool RES, bool RELU, bool ADD>
+template <bool RES, bool RELU, bool ADD, bool CHAIN = false>
 __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const float* bias_s,
                                                    uint32_t tmem_base, uint64_t* tfull,
                                                    uint32_t tempty_addr, int group, int lg,
@@ -210,21 +277,40 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const fl
   const bool tma_out = p.tma_out != 0;
   int slab_sel = 0;   // the accumulator-free barrier lives in the leader CTA
   int item = item0;
-  EpiPix px = epi_pixel(p, item, tile_sel, m, rank);
-  int nt = item - (int)fdiv((uint32_t)item, p.fd_nt) * n_tiles;
-  epi_fetch_round<RES>(nxt, RES ? e.res + px.opix * e.res_ld + e.res_coff + nt * BN : nullptr,
-                       px.valid, cbeg, nchunks);
+  int pend_n = -1;              // chain mode: image whose completion count this warp still owes
+  int lay = 0;                  // chain mode: layer of the current item (0: no residual, out = the
+                                // intermediate tensor; 1: residual + the block's output)
+  EpiPix px = epi_pixel<CHAIN>(p, item, tile_sel, m, rank, &lay);
+  int nt = CHAIN ? 0 : item - (int)fdiv((uint32_t)item, p.fd_nt) * n_tiles;
+  if constexpr (CHAIN)
+    epi_fetch_round<RES, true>(nxt, p.res1 + px.opix * p.res1_ld + p.res1_coff, px.valid && lay == 1,
+                               cbeg, nchunks);
+  else
+    epi_fetch_round<RES>(nxt, RES ? e.res + px.opix * e.res_ld + e.res_coff + nt * BN : nullptr,
+                         px.valid, cbeg, nchunks);
   int it = 0;
   for (; item < num_items; item += istep, ++it) {
     const int next_item = item + istep;
-    const EpiPix npx = epi_pixel(p, next_item, tile_sel, m, rank);
-    const int nnt = next_item - (int)fdiv((uint32_t)next_item, p.fd_nt) * n_tiles;
+    int nlay = 0;
+    const EpiPix npx = epi_pixel<CHAIN>(p, next_item, tile_sel, m, rank, &nlay);
+    const int nnt = CHAIN ? 0 : next_item - (int)fdiv((uint32_t)next_item, p.fd_nt) * n_tiles;
     const int co0 = nt * BN;
-    const __nv_bfloat16* rp = RES ? e.res + px.opix * e.res_ld + e.res_coff + co0 : nullptr;
-    const __nv_bfloat16* nrp = RES ? e.res + npx.opix * e.res_ld + e.res_coff + nnt * BN : nullptr;
+    const __nv_bfloat16* rp;
+    const __nv_bfloat16* nrp;
+    bool rvalid = px.valid, nrvalid = npx.valid;
+    if constexpr (CHAIN) {
+      rp = p.res1 + px.opix * p.res1_ld + p.res1_coff;
+      nrp = p.res1 + npx.opix * p.res1_ld + p.res1_coff;
+      rvalid = px.valid && lay == 1;
+      nrvalid = npx.valid && nlay == 1;
+    } else {
+      rp = RES ? e.res + px.opix * e.res_ld + e.res_coff + co0 : nullptr;
+      nrp = RES ? e.res + npx.opix * e.res_ld + e.res_coff + nnt * BN : nullptr;
+    }
     // origin of this warp's 8 x 4 pixel slab (TMA clips what lies outside the image / batch)
+    int lay_unused = 0;
     const TileOrg org = tile_origin(
-        p, (int)fdiv((uint32_t)item, p.fd_nt) * (p.tpc * p.cg) + rank * p.tpc + tile_sel);
+        p, item_unit<CHAIN>(p, item, lay_unused) * (p.tpc * p.cg) + rank * p.tpc + tile_sel);
     const int oy = org.y0 + 4 * lg;
     const int acc = (acc_stages == 2) ? (it & 1) : 0;
     const uint32_t accph = (acc_stages == 2) ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
@@ -233,6 +319,17 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const fl
     HL_TIMED(10, mbar_wait(smem_u32(&tfull[acc]), accph));
     if (PROF) pc[11] += 1;
     tc_fence_after();
+    if constexpr (CHAIN) {
+      // deferred completion count of the previous (layer-0) item: its stores were issued one work
+      // item ago, so the fence does not wait, and none of this item's stores is in flight yet
+      if (pend_n >= 0) {
+        __threadfence();
+        fence_proxy_async_all();
+        __syncwarp();
+        if (lane == 0) red_release_gpu_add(p.ch_count + pend_n, 1);
+        pend_n = -1;
+      }
+    }
     if (cbeg >= nchunks) {                             // this group has no chunk of the tile
       tc_fence_before();
       __syncwarp();
@@ -246,8 +343,8 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const fl
       Chunk32 cur[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
-      if (c0 + 4 < nchunks) epi_fetch_round<RES>(nxt, rp, px.valid, c0 + 4, nchunks);
-      else epi_fetch_round<RES>(nxt, nrp, npx.valid, cbeg, nchunks);
+      if (c0 + 4 < nchunks) epi_fetch_round<RES, CHAIN>(nxt, rp, rvalid, c0 + 4, nchunks);
+      else epi_fetch_round<RES, CHAIN>(nxt, nrp, nrvalid, cbeg, nchunks);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = c0 + 2 * h;
@@ -291,8 +388,14 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const fl
             // 16-channel tail of a Cout tile that has a neighbour: the 32-channel store box
             // would spill into the neighbour's channels, so this chunk is stored directly
             if (px.valid) {
-              const uint32_t bs = bias_u32 + (uint32_t)((co0 + c * 16) * 4);
+              uint32_t bs = bias_u32 + (uint32_t)((co0 + c * 16) * 4);
               __nv_bfloat16* op = e.out + px.opix * e.out_ld + e.out_coff + co0 + c * 16;
+              if constexpr (CHAIN) {
+                if (lay == 1) {
+                  bs += (uint32_t)(BN * 4);
+                  op = p.out1 + px.opix * p.out1_ld + p.out1_coff + c * 16;
+                }
+              }
               if (dual) {
                 __nv_bfloat16* op2 = e.out2 + px.opix * e.out2_ld + co0 + c * 16;
                 float s[16];
@@ -343,8 +446,32 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const fl
         }
       }
     }
+    if constexpr (CHAIN) {
+      // layer 0: this warp's 32 pixels of the intermediate tensor are stored -> count them on the
+      // tile's image (release: the stores of all 32 lanes; the layer-1 producer that waits for
+      // the image reads them through TMA = the async proxy)
+      if (lay == 0 && !(p.ch_dbg & 1) && org.n < p.N) {
+        if (p.ch_defer) {
+          pend_n = org.n;
+        } else {
+          __threadfence();
+          fence_proxy_async_all();
+          __syncwarp();
+          if (lane == 0) red_release_gpu_add(p.ch_count + org.n, 1);
+        }
+      }
+    }
     px = npx;
     nt = nnt;
+    lay = nlay;
+  }
+  if constexpr (CHAIN) {
+    if (pend_n >= 0) {
+      __threadfence();
+      fence_proxy_async_all();
+      __syncwarp();
+      if (lane == 0) red_release_gpu_add(p.ch_count + pend_n, 1);
+    }
   }
   if (lane == 0) bulk_wait0();                      // every TMA store of this warp has landed
   __syncwarp();
@@ -470,6 +597,7 @@ template <bool SPLIT, bool PROFT, int EPI>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
   const bool PROF = PROFT && p.prof != nullptr;   // debug counters (brtpe_debug_halo_prof), warp-uniform
+  constexpr bool CHAIN = (EPI == 8);              // two layers per launch (HaloParams::chain)
   extern __shared__ uint8_t smem_raw[];
   long long pc[HL_PROF_SLOTS];
 #pragma unroll
@@ -517,6 +645,10 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
     tma_prefetch_desc(&p.tmap_a);
     tma_prefetch_desc(&p.tmap_b);
     tma_prefetch_desc(&p.tmap_o);
+    if constexpr (CHAIN) {
+      tma_prefetch_desc(&p.tmap_a1);
+      tma_prefetch_desc(&p.tmap_b1);
+    }
     for (int s = 0; s < HL_MAX_A; ++s) {
       mbar_init(smem_u32(&full_a[s]), 1);
       mbar_init(smem_u32(&empty_a[s]), 1);
@@ -534,6 +666,10 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
   }
   for (int i = threadIdx.x; i < n_tiles * BN; i += HL_THREADS)
     bias_s[i] = (p.bias && i < p.epi.Cout) ? p.bias[i] : 0.0f;
+  if constexpr (CHAIN) {
+    for (int i = threadIdx.x; i < BN; i += HL_THREADS)
+      bias_s[BN + i] = (p.bias1 && i < p.epi.Cout) ? p.bias1[i] : 0.0f;
+  }
   if (warp == 1) {
     if (cg2) tmem_alloc_cg2(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
     else tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
@@ -544,6 +680,9 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const long long t_loop = PROF ? clock64() : 0;
+  // PDL: the next kernel of the lane may be scheduled as soon as every CTA of this one is past its
+  // prologue (its CTAs take the SMs this kernel's CTAs leave and run THEIR prologue under our tail)
+  if (threadIdx.x == 0) pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform loop, one elected lane issues) ========
@@ -563,16 +702,19 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
       // every tap of every channel block, once per kernel
       if (elect_one()) {
         const uint32_t fb = smem_u32(&full_b[0]);
-        if (leader) mbar_expect_tx(fb, (uint32_t)(num_kb * 9 * BN * 128));
+        if (leader) mbar_expect_tx(fb, (uint32_t)((CHAIN ? 2 : 1) * num_kb * 9 * BN * 128));
         const uint32_t fbs = sig(&full_b[0]);
         for (int kb = 0; kb < num_kb; ++kb) {
           const uint32_t dst = smem_u32(b_ring) + (uint32_t)(kb * 9 * BNh * 128);
           if (cg2) tma_load_3d_cg2(dst, &p.tmap_b, fbs, kb * 64, brow0, 0);
           else tma_load_3d(dst, &p.tmap_b, fb, kb * 64, 0, 0);
         }
+        if constexpr (CHAIN)                        // (num_kb == 1) layer 1 behind layer 0
+          tma_load_3d(smem_u32(b_ring) + (uint32_t)(9 * BNh * 128), &p.tmap_b1, fb, 0, 0, 0);
       }
       __syncwarp();
     }
+    pdl_wait();                                     // activations / residual: the predecessor's output
     // The activation tiles of step s+1 (a step = one channel block of one item) are requested as
     // soon as their stage is free, in between the weight stages of step s: the weight loads
     // block on the MMA's progress, and the activation load must neither queue behind all of
@@ -586,19 +728,53 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
       } else if (!mbar_test(eb, aph ^ 1u)) {
         return false;
       }
-      const int unit = (int)fdiv((uint32_t)nx_item, p.fd_nt);
+      int layer = 0;
+      const int unit = item_unit<CHAIN>(p, nx_item, layer);
       const TileOrg o0 = tile_origin(p, unit * tpi + rank * tpc);
       const TileOrg o1 = tile_origin(p, unit * tpi + rank * tpc + 1);      // unused when tpc == 1
       // channel block nx_kb of the reduction: segment (hi, lo, hi again) and block inside it
       const int seg = (nx_kb >= nkb_seg) + (nx_kb >= 2 * nkb_seg);
-      const int ch0 = in_coff + (nx_kb - seg * nkb_seg) * 64 + (seg == 1 ? lo_off : 0);
+      int ch0 = in_coff + (nx_kb - seg * nkb_seg) * 64 + (seg == 1 ? lo_off : 0);
+      const CUtensorMap* amap = &p.tmap_a;
+      if constexpr (CHAIN) {
+        if (layer == 1) {
+          amap = &p.tmap_a1;
+          ch0 = p.in_coff1;
+        }
+      }
       if (elect_one()) {
-        if (res_prefetch && nx_kb == 0) {
+        if constexpr (CHAIN) {
+          if (layer == 1 && !(p.ch_dbg & 2)) {
+            // the intermediate tiles of these images (halo included) must be complete: every
+            // epilogue warp that stored a layer-0 tile of image n has counted itself on ch_count[n]
+            if (o0.n < p.N)
+              while (ld_acquire_gpu(p.ch_count + o0.n) < p.ch_need) __nanosleep(64);
+            if (o1.n < p.N && o1.n != o0.n)
+              while (ld_acquire_gpu(p.ch_count + o1.n) < p.ch_need) __nanosleep(64);
+            fence_proxy_async_all();
+          }
+        }
+        if (res_prefetch && nx_kb == 0 && (!CHAIN || layer == 1)) {
           // the residual tiles of this item will be read by the epilogue one to two items from
           // now: pull them into L2 so that those loads do not pay the HBM latency
-          const int rc0 = p.epi.res_coff + (nx_item - unit * n_tiles) * BN;
+          const int rc0 = CHAIN ? p.res1_coff : p.epi.res_coff + (nx_item - unit * n_tiles) * BN;
           if (o0.n < p.N) tma_prefetch_l2_4d(&p.tmap_r, rc0, o0.x0, o0.y0, o0.n);
           if (o1.n < p.N) tma_prefetch_l2_4d(&p.tmap_r, rc0, o1.x0, o1.y0, o1.n);
+        }
+        if constexpr (CHAIN) {
+          // two activation stages cannot cover the HBM latency of the block input: pull the
+          // layer-0 tiles of a later item into L2 now (layer 1 reads what was just written)
+          const int pf_item = nx_item + p.ch_pf * istep;
+          if (p.ch_pf > 0 && pf_item < num_items) {
+            int pl = 0;
+            const int pu = item_unit<true>(p, pf_item, pl);
+            if (pl == 0) {
+              const TileOrg q0 = tile_origin(p, pu * tpi);
+              const TileOrg q1 = tile_origin(p, pu * tpi + 1);
+              tma_prefetch_l2_5d(&p.tmap_a, in_coff, q0.x0 - 1, 0, q0.y0 - 1, q0.n);
+              tma_prefetch_l2_5d(&p.tmap_a, in_coff, q1.x0 - 1, 0, q1.y0 - 1, q1.n);
+            }
+          }
         }
         const uint32_t fa = smem_u32(&full_a[as_]);
         if (dbg & 8) {
@@ -624,9 +800,9 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
             if (tpc == 2)
               tma_load_5d_cg2(dst + (uint32_t)p.a_tile_bytes, &p.tmap_a, fas, ch0, o1.x0 - 1, 0, o1.y0 - 1, o1.n);
           } else {
-            tma_load_5d(dst, &p.tmap_a, fa, ch0, o0.x0 - 1, 0, o0.y0 - 1, o0.n);
+            tma_load_5d(dst, amap, fa, ch0, o0.x0 - 1, 0, o0.y0 - 1, o0.n);
             if (tpc == 2)
-              tma_load_5d(dst + (uint32_t)p.a_tile_bytes, &p.tmap_a, fa, ch0, o1.x0 - 1, 0, o1.y0 - 1, o1.n);
+              tma_load_5d(dst + (uint32_t)p.a_tile_bytes, amap, fa, ch0, o1.x0 - 1, 0, o1.y0 - 1, o1.n);
           }
         }
       }
@@ -738,6 +914,11 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
             uint32_t b_lo;
             if (resident) {
               b_lo = b_ring_lo + (uint32_t)(kb * 9) * b_tap_lo;
+              if constexpr (CHAIN) {
+                int layer = 0;
+                item_unit<true>(p, item, layer);
+                b_lo += (uint32_t)(layer * 9) * b_tap_lo;
+              }
             } else {
               HL_TIMED(7, mbar_wait(smem_u32(&full_b[bs_]), bph));
               b_lo = b_ring_lo + (uint32_t)bs_ * b_stage_lo;
@@ -792,6 +973,7 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
     // the accumulator-free barrier of the pair lives in the leader CTA
     const uint32_t tempty_addr = cg2 ? mapa_u32(smem_u32(&tempty[0]), 0u) : smem_u32(&tempty[0]);
     const uint32_t stage_slab = smem_u32(stage_out) + (uint32_t)((warp - 2) * p.out_slabs * HL_STAGE_OUT);
+    pdl_wait();                                     // residual loads and output stores
     if (dbg & 2) {
       int it = 0;
       for (int item = item0; item < num_items; item += istep, ++it) {
@@ -814,6 +996,8 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
         if (e.relu) halo_epilogue_split<false, true>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep);
         else halo_epilogue_split<false, false>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep);
       }
+    } else if (CHAIN) {
+      halo_epilogue_fast<true, true, false, true>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
     } else if (EPI >= 0) {
       halo_epilogue_fast<((EPI >> 1) & 1) != 0, (EPI & 1) != 0, (EPI >= 4)>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
     } else if (e.fast) {
@@ -854,6 +1038,18 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
     tc_fence_after();
     if (cg2) tmem_dealloc_cg2(tmem_base, (uint32_t)p.tmem_cols);
     else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+  if constexpr (CHAIN) {
+    // the last CTA to finish zeroes the image counters for the next launch (every other CTA is past
+    // its last counter read: it has counted itself as done after its final CTA-wide sync)
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const int done = atomicAdd(p.ch_count + p.N, 1);
+      if (done == (int)gridDim.x - 1) {
+        for (int n = 0; n <= p.N; ++n) p.ch_count[n] = 0;
+        __threadfence();
+      }
+    }
   }
   if (PROF && threadIdx.x == 0) {
     long long* o = p.prof + (size_t)blockIdx.x * HL_PROF_SLOTS;
@@ -917,7 +1113,7 @@ static bool HL_NAME(g_halo_attr_set) = false;
 // kernel instantiations: 0..3 fast epilogue with (RES, RELU) = (v >> 1, v & 1); 4 run-time epilogue
 // choice (general path); 5 split (BRTPE_DT_BF16X2); 6 with the debug cycle counters; 7..10 = 0..3 with
 // the HRNet fuse addends
-constexpr int HL_NUM_VARIANTS = 11;
+constexpr int HL_NUM_VARIANTS = (HL_CG == 1) ? 12 : 11;     // 11: chain mode (single-CTA kernel only)
 #define HL_FOR_VARIANT(v, CALL)                                                   \
   switch (v) {                                                                    \
     case 0: CALL((HL_NAME(conv_halo_kernel)<false, false, 0>)); break;            \
@@ -930,6 +1126,7 @@ constexpr int HL_NUM_VARIANTS = 11;
     case 8: CALL((HL_NAME(conv_halo_kernel)<false, false, 5>)); break;            \
     case 9: CALL((HL_NAME(conv_halo_kernel)<false, false, 6>)); break;            \
     case 10: CALL((HL_NAME(conv_halo_kernel)<false, false, 7>)); break;           \
+    case 11: CALL((HL_NAME(conv_halo_kernel)<false, false, (HL_CG == 1 ? 8 : 7)>)); break; \
     default: CALL((HL_NAME(conv_halo_kernel)<false, true, -2>)); break;           \
   }
 
@@ -1314,13 +1511,18 @@ int HL_NAME(halo_conv_launch)(const HaloConvPrepared* P, const float* bias, cons
   cfg.blockDim = dim3(HL_THREADS);
   cfg.dynamicSmemBytes = P->smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.cg;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (pdl_enabled()) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   int variant;
   if (p.epi.split) variant = 5;
   else if (p.prof != nullptr && p.epi.fast) variant = 6;
@@ -1337,5 +1539,169 @@ int HL_NAME(halo_conv_launch)(const HaloConvPrepared* P, const float* bias, cons
   }
   return BRTPE_OK;
 }
+
+#if HL_CG == 1
+// ------------------------------------------------------------------------------------------
+// chain mode: conv1 -> conv2 (+ residual) of a BasicBlock (pose_higher_hrnet.py:46-75) in one launch
+// ------------------------------------------------------------------------------------------
+// At the bench's 64 forwards per plan the 48-channel tensors (157 MB at 160^2, 629 MB at 320^2) do
+// not fit the 126 MB L2, so the two launches of a block move five tensor passes through HBM (conv1:
+// x in, t out; conv2: t + x in, y out) and conv2 is HBM-bound.  One launch that walks the batch in
+// sub-batches, layer 1 one phase behind layer 0, finds t and x of a sub-batch still in L2: three
+// passes (x in, t and y written back).  Both weight sets stay resident (2 x 54 KB at 48 channels),
+// which leaves two activation stages.
+bool halo_chain_eligible(const HaloConvPrepared* P0, const brtpe_conv_desc* d0, const brtpe_conv_desc* d1) {
+  const HaloParams& p = P0->p;
+  if (p.cg != 1 || p.tpc != 2 || p.n_tiles != 1 || !p.resident || p.num_kb != 1 || p.s2 || p.tma_out ||
+      !p.epi.fast || p.epi.split || p.epi.n_add || d0->out2_ld > 0 || p.dbg)
+    return false;
+  if (!d0->relu || !d1->relu) return false;
+  if (!halo_conv_supported(d1) || conv_is_split(d1) || d1->in_stride != 1 || d1->n_add || d1->out2_ld > 0 ||
+      !epi_fast_ok(d1))
+    return false;
+  if (d1->N != d0->N || d1->Hm != d0->Hm || d1->Wm != d0->Wm || d1->Cin != d0->Cout ||
+      d1->Cout != d0->Cout || d1->Cout_store != d0->Cout_store || d1->in_ld != d0->out_ld ||
+      d1->in_coff != d0->out_coff || d1->Cin > 64)
+    return false;
+  return (p.m_tiles & 1) == 0;
+}
+
+HaloConvPrepared* halo_chain_prepare(const brtpe_conv_desc* d0, const void* in, const void* w0, void* mid,
+                                     const brtpe_conv_desc* d1, const void* w1, void* out) {
+  HaloConvPrepared* P = halo_conv_prepare_cg1(d0, in, w0, mid);
+  if (!P) return nullptr;
+  if (!halo_chain_eligible(P, d0, d1)) {
+    delete P;
+    set_error("halo chain: the two layers are not a chainable pair");
+    return nullptr;
+  }
+  HaloParams& p = P->p;
+  P->d1 = *d1;
+  P->mid = mid;
+  // shared memory: two resident weight sets + at least two activation stages
+  const int tap_bytes = p.BN * 128;
+  const int resident2 = 2 * 9 * tap_bytes;
+  const int budget = HL_SMEM_MAX - HL_TAIL - 1024;
+  p.b_stage_bytes = (int)align_up((size_t)resident2, 1024);
+  p.a_stages = std::min(HL_MAX_A, (budget - p.b_stage_bytes) / p.a_stage_bytes);
+  if (p.a_stages < 2 || 2 * p.BN * 4 + 64 > HL_TAIL - 512) {
+    delete P;
+    set_error("halo chain: two weight sets of %d bytes leave fewer than two activation stages", resident2 / 2);
+    return nullptr;
+  }
+  P->smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stage_bytes + HL_TAIL + 1024;
+  // images per sub-batch: the smallest divisor G of N whose phase (G images of one layer) is a whole
+  // number of tile pairs and at least two rounds of the grid (a layer-1 item then depends on items
+  // that were handed out >= two rounds earlier), within ~16 MB per tensor and sub-batch
+  const int tiles_xy = p.tiles_x * p.tiles_y;
+  const int workers = num_sms();
+  const long long img_bytes = (long long)p.H * p.W * d0->out_ld * 2;
+  int G = 0;
+  for (int g = 1; g <= p.N; ++g) {
+    if (p.N % g || ((g * tiles_xy) & 1)) continue;
+    if (G && g * img_bytes > (16ll << 20)) break;
+    G = g;
+    if (g * tiles_xy / 2 >= 2 * workers) break;
+  }
+  if (getenv("BRTPE_CHAIN_G")) {
+    const int g = atoi(getenv("BRTPE_CHAIN_G"));
+    if (g >= 1 && p.N % g == 0 && ((g * tiles_xy) & 1) == 0) G = g;
+  }
+  if (!G) {
+    delete P;
+    set_error("halo chain: no sub-batch size divides the batch into whole tile pairs");
+    return nullptr;
+  }
+  p.chain = 1;
+  p.ch_dbg = getenv("BRTPE_CHAIN_DBG") ? atoi(getenv("BRTPE_CHAIN_DBG")) : 0;
+  p.ch_ip = G * tiles_xy / 2;
+  p.ch_defer = (p.ch_ip >= 2 * workers) ? 1 : 0;
+  if (getenv("BRTPE_CHAIN_DEFER") && atoi(getenv("BRTPE_CHAIN_DEFER")) == 0) p.ch_defer = 0;
+  p.ch_pf = getenv("BRTPE_CHAIN_PF") ? atoi(getenv("BRTPE_CHAIN_PF")) : 2;
+  p.ch_S = p.N / G;
+  p.fd_ip = make_fastdiv((uint32_t)p.ch_ip, 2ull * p.num_units + 4ull * workers + 4);
+  p.num_items = 2 * p.ch_S * p.ch_ip;
+  p.ch_need = tiles_xy * 4;
+  P->grid = std::max(1, std::min(p.num_items, workers));
+  p.in_coff1 = d1->in_coff;
+  p.out1_ld = d1->out_ld; p.out1_coff = d1->out_coff;
+  p.res1_ld = d1->res_ld; p.res1_coff = d1->res_coff;
+  // tensor maps of layer 1: the intermediate tensor as activation operand, its weights
+  auto encode = halo_encode_fn();
+  {
+    const cuuint64_t ld_b = (cuuint64_t)d1->in_ld * 2;
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    cuuint64_t gdim[5] = {(cuuint64_t)(d1->in_coff + d1->Cin), (cuuint64_t)d1->Win, 1,
+                          (cuuint64_t)d1->Hin, (cuuint64_t)d1->N};
+    cuuint64_t gstr[4] = {ld_b, ld_b * d1->Win, ld_b * d1->Win, ld_b * d1->Win * d1->Hin};
+    cuuint32_t box[5] = {64, (cuuint32_t)HL_PITCH, 1, (cuuint32_t)(HL_TH + 2), 1};
+    CUresult r = encode(&p.tmap_a1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, mid, gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    int cin_pad = 0, cout_pad = 0;
+    brtpe_umma_weight_dims(d1->Cin, d1->Cout_store, &cin_pad, &cout_pad);
+    cuuint64_t wdim[3] = {(cuuint64_t)cin_pad, (cuuint64_t)cout_pad, 9};
+    cuuint64_t wstr[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)cin_pad * 2 * cout_pad};
+    cuuint32_t wbox[3] = {64, (cuuint32_t)p.BN, 9};
+    cuuint32_t westr[3] = {1, 1, 1};
+    if (r == CUDA_SUCCESS)
+      r = encode(&p.tmap_b1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w1), wdim, wstr, wbox,
+                 westr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("halo chain: cuTensorMapEncodeTiled failed with %d", (int)r);
+      delete P;
+      return nullptr;
+    }
+  }
+  (void)out;
+  if (cudaMalloc(&P->counters, (size_t)(p.N + 1) * sizeof(int)) != cudaSuccess ||
+      cudaMemset(P->counters, 0, (size_t)(p.N + 1) * sizeof(int)) != cudaSuccess) {
+    set_error("halo chain: counter allocation failed");
+    delete P;
+    return nullptr;
+  }
+  p.ch_count = P->counters;
+  return P;
+}
+
+int halo_chain_launch(const HaloConvPrepared* P, const float* bias0, const float* bias1,
+                      const void* residual, void* out, cudaStream_t st) {
+  HaloParams p = P->p;
+  if (!p.chain || !residual || !out) {
+    set_error("halo chain: not a prepared chain / null tensor");
+    return BRTPE_EINVAL;
+  }
+  p.bias = bias0;
+  p.bias1 = bias1;
+  p.epi.res = nullptr;
+  p.epi.out = reinterpret_cast<__nv_bfloat16*>(P->mid);
+  p.res1 = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.out1 = reinterpret_cast<__nv_bfloat16*>(out);
+  p.res_prefetch = 0;
+  static int res_pf = -1;
+  if (res_pf < 0) {
+    const char* e = getenv("BRTPE_HALO_RES_PREFETCH");
+    res_pf = e ? (atoi(e) ? 1 : 0) : 0;       // the residual was read as layer 0's input one phase ago
+  }
+  if (res_pf) {
+    HaloConvPrepared* PM = const_cast<HaloConvPrepared*>(P);
+    if (residual != PM->res_encoded) {
+      if (!halo_encode_res(&P->d1, residual, p.BN, &PM->tmap_r_cache)) return BRTPE_ECUDA;
+      PM->res_encoded = residual;
+    }
+    p.tmap_r = PM->tmap_r_cache;
+    p.res_prefetch = 1;
+  }
+  p.prof = nullptr;
+  cudaError_t e = launch_ex(conv_halo_kernel_cg1<false, false, 8>, dim3(P->grid), dim3(HL_THREADS), P->smem,
+                            st, 1, true, p);
+  if (e != cudaSuccess) {
+    set_error("conv_halo_kernel (chain) launch failed: %s", cudaGetErrorString(e));
+    return BRTPE_ECUDA;
+  }
+  return BRTPE_OK;
+}
+#endif  // HL_CG == 1
 
 }  // namespace brtpe

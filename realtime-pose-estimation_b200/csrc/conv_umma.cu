@@ -123,6 +123,8 @@ conv_umma_kernel(const __grid_constant__ UmmaParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tx_bytes = (uint32_t)(TW * TH * TN * 128 + BN * 128);
+  if (threadIdx.x == 0) pdl_trigger();              // PDL (common.cuh): successor may start its prologue
+  if (warp != 1) pdl_wait();                        // producer + epilogue touch the predecessor's output
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform, elected lane issues) ================
@@ -540,10 +542,14 @@ int umma_conv_launch(const UmmaConvPrepared* P, const float* bias, const void* r
     p.epi.add[k] = reinterpret_cast<const __nv_bfloat16*>(add_ptrs[k]);
   }
   (void)out2;
-  if (p.epi.split) conv_umma_kernel<true, false><<<P->grid, UM_THREADS, P->smem, st>>>(p);
-  else if (p.epi.n_add > 0) conv_umma_kernel<false, true><<<P->grid, UM_THREADS, P->smem, st>>>(p);
-  else conv_umma_kernel<false, false><<<P->grid, UM_THREADS, P->smem, st>>>(p);
-  BRTPE_LAUNCH_CHECK();
+  cudaError_t e;
+  if (p.epi.split) e = launch_ex(conv_umma_kernel<true, false>, dim3(P->grid), dim3(UM_THREADS), P->smem, st, 0, true, p);
+  else if (p.epi.n_add > 0) e = launch_ex(conv_umma_kernel<false, true>, dim3(P->grid), dim3(UM_THREADS), P->smem, st, 0, true, p);
+  else e = launch_ex(conv_umma_kernel<false, false>, dim3(P->grid), dim3(UM_THREADS), P->smem, st, 0, true, p);
+  if (e != cudaSuccess) {
+    set_error("conv_umma_kernel launch failed: %s", cudaGetErrorString(e));
+    return BRTPE_ECUDA;
+  }
   return BRTPE_OK;
 }
 

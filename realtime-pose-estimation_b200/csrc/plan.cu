@@ -24,6 +24,10 @@ struct Op {
   void* out;
   UmmaConvPrepared* umma;  // non-null: tcgen05 per-tap path
   HaloConvPrepared* halo;  // non-null: tcgen05 halo-tile path
+  HaloConvPrepared* chain; // non-null: this conv and the next conv of its lane (op `chain_with`) run as ONE
+                           // launch (halo chain mode: conv1 -> conv2 of a BasicBlock, L2-blocked)
+  int chain_with;
+  bool nop;                // the second conv of a chain: done by the first one's launch
   const void* add_ptrs[3]; // HRNet fuse addends of the epilogue (d.n_add of them)
   void* out2;              // second output (d.out2_ld > 0)
   // stem / tonchw / fuse
@@ -91,6 +95,8 @@ static int choose_engine(const brtpe_conv_desc* d) {
 static int run_op(const Op& op, cudaStream_t st) {
   switch (op.kind) {
     case OP_CONV:
+      if (op.nop) return BRTPE_OK;
+      if (op.chain) return BRTPE_EINVAL;     // (run through run_plan_op, which knows the partner op)
       if (op.halo) return halo_conv_launch(op.halo, op.bias, op.res, op.out, st, op.add_ptrs, op.out2);
       if (op.umma) return umma_conv_launch(op.umma, op.bias, op.res, op.out, st, op.add_ptrs, op.out2);
       if (op.d.n_add > 0 || op.d.out2_ld > 0) {
@@ -121,6 +127,7 @@ using namespace brtpe;
 
 struct brtpe_plan {
   std::vector<Op> ops;
+  bool chains_done = false;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   cudaStream_t lanes[PLAN_MAX_LANES] = {nullptr};
@@ -130,11 +137,79 @@ struct brtpe_plan {
     for (auto& op : ops) {
       if (op.umma) umma_conv_release(op.umma);
       if (op.halo) halo_conv_release(op.halo);
+      if (op.chain) halo_conv_release(op.chain);
     }
     if (exec) cudaGraphExecDestroy(exec);
     if (graph) cudaGraphDestroy(graph);
   }
 };
+
+// One op of a plan (a chained pair runs through its first op).
+static int run_plan_op(const brtpe_plan* pl, size_t i, cudaStream_t st) {
+  const Op& op = pl->ops[i];
+  if (op.kind == OP_CONV && op.chain && !op.nop) {
+    const Op& o2 = pl->ops[op.chain_with];
+    return halo_chain_launch(op.chain, op.bias, o2.bias, o2.res, o2.out, st);
+  }
+  return run_op(op, st);
+}
+
+// Chain pass (once, before the first run / capture): conv1 -> conv2 (+ residual) of a BasicBlock whose
+// tensors do not fit the L2 become one launch of the halo engine's chain mode.  Op j = the next op of
+// op i's lane; it must read what i writes, and everything else it waits for must precede i (the pair
+// runs at i's position).  BRTPE_CHAIN: 0 off (default: measured slower, profiles/r02_chain.md), 1 tensors of
+// >= 48 MB only, 2 every chainable pair.
+static void fuse_chains(brtpe_plan* pl) {
+  if (pl->chains_done) return;
+  pl->chains_done = true;
+  const char* e = getenv("BRTPE_CHAIN");       // read per plan (tests switch it between plans)
+  const int mode = e ? atoi(e) : 0;
+  if (mode <= 0) return;
+  const int n = (int)pl->ops.size();
+  for (int i = 0; i < n; ++i) {
+    Op& a = pl->ops[i];
+    if (a.kind != OP_CONV || !a.halo || a.nop || a.chain || a.res || a.d.n_add || a.d.out2_ld) continue;
+    int j = -1;
+    for (int k = i + 1; k < n; ++k)
+      if (pl->ops[k].lane == a.lane) { j = k; break; }
+    if (j < 0) continue;
+    Op& b = pl->ops[j];
+    if (b.kind != OP_CONV || !b.halo || b.in != a.out || !b.res || b.out == a.out || b.out == a.in) continue;
+    const double tensor_bytes = (double)a.d.N * a.d.Hm * a.d.Wm * a.d.out_ld * 2.0;
+    if (mode == 1 && tensor_bytes < 48e6) continue;
+    bool ok = true;
+    for (int dep : b.deps)
+      if (dep >= i) ok = false;               // an op between i and j (other lane) that j waits for
+    if (!ok) continue;
+    HaloConvPrepared* c = halo_chain_prepare(&a.d, a.in, a.w, a.out, &b.d, b.w, b.out);
+    if (!c) continue;                         // not a chainable pair: two launches as before
+    a.chain = c;
+    a.chain_with = j;
+    b.nop = true;
+    for (int dep : b.deps)
+      if (std::find(a.deps.begin(), a.deps.end(), dep) == a.deps.end()) a.deps.push_back(dep);
+  }
+}
+
+extern "C" int brtpe_conv_chain_run(const brtpe_conv_desc* d0, const void* in, const void* w0,
+                                    const float* bias0, void* mid, const brtpe_conv_desc* d1,
+                                    const void* w1, const float* bias1, const void* residual,
+                                    void* out, void* stream) {
+  int rc = conv_validate(d0);
+  if (rc) return rc;
+  rc = conv_validate(d1);
+  if (rc) return rc;
+  BRTPE_CHECK_ARG(in && w0 && mid && w1 && residual && out, "brtpe_conv_chain_run: null tensor");
+  BRTPE_CHECK_ARG(halo_conv_supported(d0) && halo_conv_supported(d1),
+                  "brtpe_conv_chain_run: both layers must be 3x3 / stride-1 bf16 convs of the halo engine");
+  HaloConvPrepared* c = halo_chain_prepare(d0, in, w0, mid, d1, w1, out);
+  if (!c) return BRTPE_EINVAL;
+  rc = halo_chain_launch(c, bias0, bias1, residual, out, (cudaStream_t)stream);
+  // the prepared state owns device counters the launch uses: keep it until the stream has drained
+  if (!rc && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) rc = BRTPE_ECUDA;
+  halo_conv_release(c);
+  return rc;
+}
 
 extern "C" int brtpe_conv_run(const brtpe_conv_desc* d, const void* in, const void* weights,
                               const float* bias, const void* residual, void* out, void* stream) {
@@ -247,6 +322,9 @@ extern "C" int brtpe_plan_add_conv(brtpe_plan* pl, const brtpe_conv_desc* d, con
   op.in = in; op.w = weights; op.bias = bias; op.res = residual; op.out = out;
   op.umma = nullptr;
   op.halo = nullptr;
+  op.chain = nullptr;
+  op.chain_with = -1;
+  op.nop = false;
   if (eng == BRTPE_ENGINE_UMMA_HALO) {
     op.halo = halo_conv_prepare(d, in, weights, out);
     if (!op.halo) return BRTPE_ECUDA;
@@ -362,8 +440,9 @@ extern "C" double brtpe_plan_conv_flops(const brtpe_plan* pl) {
 
 extern "C" int brtpe_plan_run(brtpe_plan* pl, void* stream) {
   BRTPE_CHECK_ARG(pl, "brtpe_plan_run: null plan");
-  for (auto& op : pl->ops) {
-    int rc = run_op(op, (cudaStream_t)stream);
+  fuse_chains(pl);
+  for (size_t i = 0; i < pl->ops.size(); ++i) {
+    int rc = run_plan_op(pl, i, (cudaStream_t)stream);
     if (rc) return rc;
   }
   return BRTPE_OK;
@@ -375,6 +454,7 @@ extern "C" int brtpe_plan_run(brtpe_plan* pl, void* stream) {
 // branches of the graph.  Lane 0 is the origin of the capture; every other lane forks from
 // it at its first op and joins it again at the end.
 static int capture_graph(brtpe_plan* pl) {
+  fuse_chains(pl);
   const int n = (int)pl->ops.size();
   int nl = 1;
   for (auto& op : pl->ops) nl = std::max(nl, op.lane + 1);
@@ -422,7 +502,7 @@ static int capture_graph(brtpe_plan* pl) {
       joined[op.lane] = 1;
     }
     if (rc) break;
-    rc = run_op(op, st);
+    rc = run_plan_op(pl, (size_t)i, st);
     if (!rc && need_event[i]) {
       if (new_event(&ev[i]) != cudaSuccess || cudaEventRecord(ev[i], st) != cudaSuccess) rc = BRTPE_ECUDA;
     }
@@ -458,6 +538,12 @@ extern "C" int brtpe_plan_graph_launch(brtpe_plan* pl, void* stream) {
     // captured on private streams: the caller's stream may be the legacy default stream,
     // which cannot be captured; the instantiated graph is then launched into `stream`.
     int rc = capture_graph(pl);
+    if (rc && pdl_enabled()) {
+      // programmatic (PDL) edges could not be captured / instantiated here: plain edges instead
+      cudaGetLastError();
+      pdl_set(false);
+      rc = capture_graph(pl);
+    }
     if (rc) return rc;
   }
   BRTPE_CUDA(cudaGraphLaunch(pl->exec, (cudaStream_t)stream));
@@ -468,13 +554,14 @@ extern "C" int brtpe_plan_profile(brtpe_plan* pl, void* stream, float* ms_out, i
                                   double* flops_out) {
   BRTPE_CHECK_ARG(pl && ms_out, "brtpe_plan_profile: null argument");
   cudaStream_t st = (cudaStream_t)stream;
+  fuse_chains(pl);
   const size_t n = pl->ops.size();
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) BRTPE_CUDA(cudaEventCreate(&e));
   int rc = BRTPE_OK;
   BRTPE_CUDA(cudaEventRecord(ev[0], st));
   for (size_t i = 0; i < n && !rc; ++i) {
-    rc = run_op(pl->ops[i], st);
+    rc = run_plan_op(pl, i, st);
     cudaEventRecord(ev[i + 1], st);
   }
   cudaError_t e = cudaStreamSynchronize(st);
@@ -485,8 +572,14 @@ extern "C" int brtpe_plan_profile(brtpe_plan* pl, void* stream, float* ms_out, i
   for (size_t i = 0; i < n && !rc; ++i) {
     cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
     const Op& op = pl->ops[i];
-    if (kinds_out) kinds_out[i] = op.kind == OP_CONV ? (op.halo ? 3 : (op.umma ? 0 : 1)) : 2;
-    if (flops_out) flops_out[i] = op.kind == OP_CONV ? conv_flops(&op.d) : 0.0;
+    // kinds: 0 per-tap tcgen05, 1 CUDA cores, 3 halo tcgen05, 2 other, 4 second conv of a chained pair
+    // (no launch of its own: its FLOPs are reported with the first conv)
+    if (kinds_out) kinds_out[i] = op.kind == OP_CONV ? (op.nop ? 4 : (op.halo ? 3 : (op.umma ? 0 : 1))) : 2;
+    if (flops_out) {
+      double f = (op.kind == OP_CONV && !op.nop) ? conv_flops(&op.d) : 0.0;
+      if (op.kind == OP_CONV && op.chain) f += conv_flops(&pl->ops[op.chain_with].d);
+      flops_out[i] = f;
+    }
   }
   for (auto& evt : ev) cudaEventDestroy(evt);
   return rc;

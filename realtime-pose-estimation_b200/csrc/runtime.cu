@@ -1,6 +1,7 @@
 // Library-wide runtime helpers: error string, device properties.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace brtpe {
 
@@ -12,6 +13,16 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("BRTPE_PDL");
+    g_pdl = (e && atoi(e) != 0) ? 1 : 0;      // opt-in: measured neutral to -1.5 % (profiles/r02_chain.md)
+  }
+  return g_pdl != 0;
+}
+void pdl_set(bool on) { g_pdl = on ? 1 : 0; }
 
 int num_sms() {
   static int cached = 0;

@@ -309,6 +309,13 @@ __device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* map, int c
                : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_l2_5d(const CUtensorMap* map, int c0, int c1, int c2,
+                                                   int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+
 // 1-D bulk async copy global -> shared (no tensor map): 16-byte aligned source, destination
 // and size; completion is counted in bytes on an mbarrier like a tensor TMA load.
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes,

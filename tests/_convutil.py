@@ -182,3 +182,32 @@ def run_conv_fused(engine, n, h, w, cin, cout, k, stride, relu, use_res, shifts,
     r1 = ref + tot
     r1 = F.relu(r1) if relu else r1
     return got, None, r1.float(), None, eng
+
+
+def run_chain(n, h, w, c, seed=0, device="cuda", env_g=None):
+    """BasicBlock body (conv1 + relu -> conv2 + residual + relu, bf16, halo engine) as ONE chained launch
+    (brtpe_conv_chain_run) and as two brtpe_conv_run calls -> (mid, out) of both, NHWC bf16."""
+    lib = L.load()
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn((n, h, w, c), generator=g).to(device).to(torch.bfloat16)
+    ws = [(torch.randn((c, c, 3, 3), generator=g) / (c * 9) ** 0.5).to(device) for _ in range(2)]
+    bs = [(torch.randn((c,), generator=g) * 0.1).to(device) for _ in range(2)]
+    d0, taps = make_desc(L.DT_BF16, L.ENGINE_UMMA_HALO, n, h, w, c, c, 3, 1, True)
+    d1, _ = make_desc(L.DT_BF16, L.ENGINE_UMMA_HALO, n, h, w, c, c, 3, 1, True, res_ld=c)
+    pk = [pack_weights(lib, ws[i], taps, 3, d0, L.ENGINE_UMMA_HALO, True) for i in range(2)]
+    res = {}
+    for name in ("two", "chain"):
+        mid = torch.full((n, h, w, d0.out_ld), float("nan"), dtype=torch.bfloat16, device=device)
+        out = torch.full((n, h, w, d1.out_ld), float("nan"), dtype=torch.bfloat16, device=device)
+        if name == "two":
+            L.check(lib.brtpe_conv_run(C.byref(d0), L.ptr(x), L.ptr(pk[0]), L.ptr(bs[0]), None,
+                                       L.ptr(mid), L.stream_ptr()), "brtpe_conv_run")
+            L.check(lib.brtpe_conv_run(C.byref(d1), L.ptr(mid), L.ptr(pk[1]), L.ptr(bs[1]), L.ptr(x),
+                                       L.ptr(out), L.stream_ptr()), "brtpe_conv_run")
+        else:
+            L.check(lib.brtpe_conv_chain_run(C.byref(d0), L.ptr(x), L.ptr(pk[0]), L.ptr(bs[0]), L.ptr(mid),
+                                             C.byref(d1), L.ptr(pk[1]), L.ptr(bs[1]), L.ptr(x),
+                                             L.ptr(out), L.stream_ptr()), "brtpe_conv_chain_run")
+        torch.cuda.synchronize()
+        res[name] = (mid, out)
+    return res

@@ -235,3 +235,28 @@ def test_fuse_addends_in_epilogue(cuda_device, case):
     if ref2 is not None:
         assert torch.isfinite(got2).all()
         assert _err(got2, ref2) <= 6e-3
+
+
+@pytest.mark.parametrize("shape", [(8, 32, 32, 48), (6, 48, 40, 48), (64, 16, 24, 48), (6, 80, 80, 48),
+                                   (4, 40, 24, 32), (16, 160, 160, 48), (2, 21, 35, 48)])
+def test_halo_chain_bit_identical(cuda_device, shape):
+    """BasicBlock body as one chained launch (conv1 -> conv2 + residual, sub-batches interleaved, layer 1
+    waiting on per-image completion counters) == the two single launches, bit for bit, for the
+    intermediate tensor and the output; ragged tiles, one / many items per CTA, several sub-batches"""
+    from _convutil import run_chain
+    r = run_chain(*shape)
+    assert torch.isfinite(r["two"][1].float()).all()
+    assert torch.equal(r["chain"][0], r["two"][0])
+    assert torch.equal(r["chain"][1], r["two"][1])
+
+
+@pytest.mark.parametrize("g", ["1", "2", "4"])
+def test_halo_chain_sub_batch_sizes(cuda_device, g, monkeypatch):
+    """the sub-batch size is a tuning choice; repeated launches re-use the self-resetting counters"""
+    from _convutil import run_chain
+    monkeypatch.setenv("BRTPE_CHAIN_G", g)
+    for rep in range(2):
+        r = run_chain(8, 48, 48, 48, seed=rep)
+        assert torch.equal(r["chain"][0], r["two"][0])
+        assert torch.equal(r["chain"][1], r["two"][1])
+

@@ -154,3 +154,31 @@ def test_constructor_variants_vs_oracle(cuda_device, name, mode, tol):
     assert [tuple(o.shape) for o in out] == [tuple(r.shape) for r in ref]
     for o, r in zip(out, ref):
         assert _rel(o, r) <= tol
+
+
+def test_chained_blocks_agree(cuda_device, model_and_ref, monkeypatch):
+    """the plan's chain pass (conv1 -> conv2 of every BasicBlock of the 48-channel branches as one
+    L2-blocked launch, plan.cu fuse_chains) changes the schedule, not one bit of the result; graph and
+    eager replay, programmatic dependent launch on and off"""
+    net, x, ref = model_and_ref
+    import copy
+    half = rtpe_b200.network_to_half(copy.deepcopy(net).float()).cuda().eval()
+    half[1].chunk_size = 4
+    xs = torch.cat([x, x.flip(3)], 0)[:4].cuda()
+    outs = {}
+    with torch.no_grad():
+        for chain in ("0", "2"):
+            for graph in (True, False):
+                monkeypatch.setenv("BRTPE_CHAIN", chain)
+                half[1].use_cuda_graph = graph
+                half[1].invalidate_plans()
+                outs[(chain, graph)] = [o.clone() for o in half(xs)]
+                again = half(xs)
+                for u, v in zip(outs[(chain, graph)], again):
+                    assert torch.equal(u, v)
+    base = outs[("0", True)]
+    for key, val in outs.items():
+        for u, v in zip(base, val):
+            assert torch.equal(u, v), key
+    for o, r in zip(base, ref):
+        assert _rel(o[:3], r) <= TOL_BF16
