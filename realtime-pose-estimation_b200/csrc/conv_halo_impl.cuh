@@ -53,6 +53,11 @@ struct alignas(64) HaloParams {
   CUtensorMap tmap_o;           // output (C, W, H, N), box 32 ch x 8 px x 4 rows, SWIZZLE_64B
   CUtensorMap tmap_r;           // residual (C, W, H, N), box BN ch x 8 px x 16 rows: L2 prefetch only
   int res_prefetch;             // 1: the producer prefetches every item's residual tiles into L2
+  CUtensorMap tmap_r4;          // residual (C, W, H, N), box BN ch x 8 px x 4 rows = one epilogue warp's pixels
+  int res_staged;               // 1: every epilogue warp pulls the residual of its 32 pixels of the NEXT item
+                                // into its own shared-memory slab by TMA (narrow resident-weight layers: the
+                                // register-prefetched global loads were latency bound, profiles/r02_mma_issue.md)
+  int res_slab_bytes;
   int N, H, W;
   int tiles_x, tiles_y, m_tiles, n_tiles, BN, num_items;
   int num_kb, last_k16, in_coff;
@@ -137,6 +142,8 @@ struct HaloConvPrepared {
   const void* out_encoded;      // output pointer tmap_o was encoded for
   const void* res_encoded;      // residual pointer tmap_r was encoded for (mutable cache)
   CUtensorMap tmap_r_cache;
+  const void* res4_encoded = nullptr;   // same for tmap_r4 (staged residual)
+  CUtensorMap tmap_r4_cache;
   // chain mode (halo_chain_prepare): second layer + the intermediate tensor + the image counters
   brtpe_conv_desc d1;
   void* mid = nullptr;
@@ -245,12 +252,13 @@ __device__ __forceinline__ void epi_fetch_round(Chunk32 (&r)[4], const __nv_bflo
   }
 }
 
-template <bool RES, bool RELU, bool ADD, bool CHAIN = false>
+template <bool RES, bool RELU, bool ADD, bool CHAIN = false, bool STAGED = false>
 __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const float* bias_s,
                                                    uint32_t tmem_base, uint64_t* tfull,
                                                    uint32_t tempty_addr, int group, int lg,
                                                    int lane, int rank, int item0, int istep,
-                                                   uint32_t stage_buf, bool PROF, long long* pc) {
+                                                   uint32_t stage_buf, bool PROF, long long* pc,
+                                                   uint32_t res_full = 0, uint32_t res_empty = 0) {
   const EpiParams& e = p.epi;
   const int m = lg * 32 + lane;
   const int BN = p.BN, n_tiles = p.n_tiles, num_items = p.num_items;
@@ -282,7 +290,17 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const fl
                                 // intermediate tensor; 1: residual + the block's output)
   EpiPix px = epi_pixel<CHAIN>(p, item, tile_sel, m, rank, &lay);
   int nt = CHAIN ? 0 : item - (int)fdiv((uint32_t)item, p.fd_nt) * n_tiles;
-  if constexpr (CHAIN)
+  // STAGED: stage_buf is this warp's residual slab (32 pixels x BN channels, pixel-major); the warp
+  // itself requests the slab of its next item as soon as it has copied the current one to registers
+  auto res_request = [&](int it_) {
+    int lu = 0;
+    const TileOrg o = tile_origin(p, item_unit<CHAIN>(p, it_, lu) * (p.tpc * p.cg) + rank * p.tpc + tile_sel);
+    mbar_expect_tx(res_full, (uint32_t)(32 * BN * 2));
+    tma_load_4d(stage_buf, &p.tmap_r4, res_full, e.res_coff, o.x0, o.y0 + 4 * lg, o.n);
+  };
+  if constexpr (STAGED) {
+    if (lane == 0 && item < num_items) res_request(item);
+  } else if constexpr (CHAIN)
     epi_fetch_round<RES, true>(nxt, p.res1 + px.opix * p.res1_ld + p.res1_coff, px.valid && lay == 1,
                                cbeg, nchunks);
   else
@@ -316,6 +334,29 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const fl
     const uint32_t accph = (acc_stages == 2) ? ((uint32_t)(it >> 1) & 1u) : ((uint32_t)it & 1u);
     const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) +
                             (uint32_t)(acc * acc_cols + tile_sel * BN);
+    if constexpr (STAGED) {
+      // residual of this item: slab -> registers, then the slab is free for the next item's TMA (while
+      // the MMAs of this item are still running)
+      mbar_wait(res_full, (uint32_t)it & 1u);
+      const uint32_t row = stage_buf + (uint32_t)(lane * BN * 2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < nchunks) {
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(nxt[j].w[0]), "=r"(nxt[j].w[1]), "=r"(nxt[j].w[2]), "=r"(nxt[j].w[3])
+                       : "r"(row + (uint32_t)(j * 32)));
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(nxt[j].w[4]), "=r"(nxt[j].w[5]), "=r"(nxt[j].w[6]), "=r"(nxt[j].w[7])
+                       : "r"(row + (uint32_t)(j * 32 + 16)));
+        }
+      }
+      mbar_arrive(res_empty);                           // all 32 lanes: their reads are done
+      if (lane == 0 && next_item < num_items) {
+        mbar_wait(res_empty, (uint32_t)it & 1u);
+        res_request(next_item);
+      }
+      __syncwarp();
+    }
     HL_TIMED(10, mbar_wait(smem_u32(&tfull[acc]), accph));
     if (PROF) pc[11] += 1;
     tc_fence_after();
@@ -343,8 +384,10 @@ __device__ __forceinline__ void halo_epilogue_fast(const HaloParams& p, const fl
       Chunk32 cur[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
-      if (c0 + 4 < nchunks) epi_fetch_round<RES, CHAIN>(nxt, rp, rvalid, c0 + 4, nchunks);
-      else epi_fetch_round<RES, CHAIN>(nxt, nrp, nrvalid, cbeg, nchunks);
+      if constexpr (!STAGED) {
+        if (c0 + 4 < nchunks) epi_fetch_round<RES, CHAIN>(nxt, rp, rvalid, c0 + 4, nchunks);
+        else epi_fetch_round<RES, CHAIN>(nxt, nrp, nrvalid, cbeg, nchunks);
+      }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = c0 + 2 * h;
@@ -598,6 +641,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1)
 HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
   const bool PROF = PROFT && p.prof != nullptr;   // debug counters (brtpe_debug_halo_prof), warp-uniform
   constexpr bool CHAIN = (EPI == 8);              // two layers per launch (HaloParams::chain)
+  constexpr bool STAGED = (EPI == 9);             // residual through per-warp TMA slabs (HaloParams::res_staged)
   extern __shared__ uint8_t smem_raw[];
   long long pc[HL_PROF_SLOTS];
 #pragma unroll
@@ -628,14 +672,17 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
   const int a_stage_bytes = p.a_stage_bytes;
   uint8_t* b_ring = smem + (size_t)a_stages * a_stage_bytes;
   uint8_t* stage_out = b_ring + (size_t)b_stages * b_stage_bytes;     // 8 epilogue-warp slabs
-  uint8_t* tail = stage_out + (size_t)p.out_slabs * HL_STAGE_BYTES;
+  // (the residual slabs of the staged epilogue take the place of the output slabs: never both)
+  uint8_t* tail = stage_out + (size_t)p.out_slabs * HL_STAGE_BYTES + (STAGED ? 8 * (size_t)p.res_slab_bytes : 0);
   uint64_t* full_a = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_a = full_a + HL_MAX_A;
   uint64_t* full_b = empty_a + HL_MAX_A;
   uint64_t* empty_b = full_b + HL_MAX_B;
   uint64_t* tfull = empty_b + HL_MAX_B;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* full_r = tempty + 2;                   // staged residual: one pair per epilogue warp
+  uint64_t* empty_r = full_r + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty_r + 8);
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5;
@@ -660,6 +707,13 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tfull[s]), 1);
       mbar_init(smem_u32(&tempty[s]), (uint32_t)(8 * p.cg));   // 8 epilogue warps per CTA
+    }
+    if constexpr (STAGED) {
+      tma_prefetch_desc(&p.tmap_r4);
+      for (int s = 0; s < 8; ++s) {
+        mbar_init(smem_u32(&full_r[s]), 1);
+        mbar_init(smem_u32(&empty_r[s]), 32);
+      }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -996,6 +1050,11 @@ HL_NAME(conv_halo_kernel)(const __grid_constant__ HaloParams p) {
         if (e.relu) halo_epilogue_split<false, true>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep);
         else halo_epilogue_split<false, false>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep);
       }
+    } else if (STAGED) {
+      halo_epilogue_fast<true, true, false, false, true>(
+          p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep,
+          smem_u32(stage_out) + (uint32_t)((warp - 2) * p.res_slab_bytes), PROF, pc,
+          smem_u32(&full_r[warp - 2]), smem_u32(&empty_r[warp - 2]));
     } else if (CHAIN) {
       halo_epilogue_fast<true, true, false, true>(p, bias_s, tmem_base, tfull, tempty_addr, group, lg, lane, rank, item0, istep, stage_slab, PROF, pc);
     } else if (EPI >= 0) {
@@ -1113,7 +1172,7 @@ static bool HL_NAME(g_halo_attr_set) = false;
 // kernel instantiations: 0..3 fast epilogue with (RES, RELU) = (v >> 1, v & 1); 4 run-time epilogue
 // choice (general path); 5 split (BRTPE_DT_BF16X2); 6 with the debug cycle counters; 7..10 = 0..3 with
 // the HRNet fuse addends
-constexpr int HL_NUM_VARIANTS = (HL_CG == 1) ? 12 : 11;     // 11: chain mode (single-CTA kernel only)
+constexpr int HL_NUM_VARIANTS = (HL_CG == 1) ? 13 : 11;     // 11: chain mode, 12: staged residual (single-CTA kernel only)
 #define HL_FOR_VARIANT(v, CALL)                                                   \
   switch (v) {                                                                    \
     case 0: CALL((HL_NAME(conv_halo_kernel)<false, false, 0>)); break;            \
@@ -1127,6 +1186,7 @@ constexpr int HL_NUM_VARIANTS = (HL_CG == 1) ? 12 : 11;     // 11: chain mode (s
     case 9: CALL((HL_NAME(conv_halo_kernel)<false, false, 6>)); break;            \
     case 10: CALL((HL_NAME(conv_halo_kernel)<false, false, 7>)); break;           \
     case 11: CALL((HL_NAME(conv_halo_kernel)<false, false, (HL_CG == 1 ? 8 : 7)>)); break; \
+    case 12: CALL((HL_NAME(conv_halo_kernel)<false, false, (HL_CG == 1 ? 9 : 7)>)); break; \
     default: CALL((HL_NAME(conv_halo_kernel)<false, true, -2>)); break;           \
   }
 
@@ -1149,6 +1209,25 @@ static bool halo_encode_res(const brtpe_conv_desc* d, const void* res, int bn, C
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("halo conv: cuTensorMapEncodeTiled(residual) failed with %d", (int)r);
+    return false;
+  }
+  return true;
+}
+
+// Residual tensor map of the staged epilogue: box BN ch x 8 px x 4 rows = the 32 pixels of one epilogue warp
+static bool halo_encode_res4(const brtpe_conv_desc* d, const void* res, int bn, CUtensorMap* map) {
+  auto encode = halo_encode_fn();
+  const cuuint64_t ld_b = (cuuint64_t)d->res_ld * 2;
+  cuuint64_t gdim[4] = {(cuuint64_t)(d->res_coff + d->Cout), (cuuint64_t)d->Wout,
+                        (cuuint64_t)d->Hout, (cuuint64_t)d->N};
+  cuuint64_t gstr[3] = {ld_b, ld_b * d->Wout, ld_b * d->Wout * d->Hout};
+  cuuint32_t box[4] = {(cuuint32_t)bn, (cuuint32_t)HL_TW, 4, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(res), gdim, gstr,
+                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("halo conv: cuTensorMapEncodeTiled(residual slab) failed with %d", (int)r);
     return false;
   }
   return true;
@@ -1348,6 +1427,25 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
   }
   P->smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes +
             (size_t)p.out_slabs * HL_STAGE_BYTES + HL_TAIL + 1024;
+  // Staged residual (opt-in, BRTPE_HALO_RES_STAGED=1): narrow single-CTA layers with direct stores whose
+  // shared memory still has room for eight slabs of 32 pixels x BN channels (48 channels: 3 activation
+  // stages + resident weights + 24 KB).  Measured neutral (48 -> 48 + residual, 64 images: 0.0964 vs
+  // 0.0963-0.0977 ms): conv2 of a 48-channel block is bound by its 472 MB of HBM traffic (76 % of the copy
+  // bandwidth), not by the latency of its residual loads (profiles/r02_chain.md).
+  p.res_staged = 0;
+  p.res_slab_bytes = (int)align_up((size_t)32 * p.BN * 2, 128);
+  {
+    static int rs = -1;
+    if (rs < 0) rs = getenv("BRTPE_HALO_RES_STAGED") ? atoi(getenv("BRTPE_HALO_RES_STAGED")) : 0;
+    const bool fast_exact = epi_fast_ok(d) && p.n_tiles * p.BN == d->Cout;
+    if (rs && HL_CG == 1 && p.tpc == 2 && p.n_tiles == 1 && p.BN <= 64 && !p.tma_out && !split && !p.s2 &&
+        fast_exact && d->n_add == 0 && d->out2_ld == 0 && d->relu && d->res_ld > 0 && p.dbg == 0 &&
+        (d->res_ld * 2) % 16 == 0 && (d->res_coff * 2) % 16 == 0 && (p.BN * 2) % 16 == 0 &&
+        P->smem + 8 * (size_t)p.res_slab_bytes <= (size_t)HL_SMEM_MAX) {
+      p.res_staged = 1;
+      P->smem += 8 * (size_t)p.res_slab_bytes;
+    }
+  }
   P->grid = p.cg * std::max(1, std::min(p.num_items, workers));
 
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
@@ -1505,6 +1603,18 @@ int HL_NAME(halo_conv_launch)(const HaloConvPrepared* P, const float* bias, cons
   }
   const bool prof = g_halo_prof != nullptr && P->grid <= g_halo_prof_ctas;
   p.prof = prof ? g_halo_prof : nullptr;
+  // staged residual: only the residual + ReLU instantiation exists, and not with the debug counters
+  const bool staged = p.res_staged && residual != nullptr && p.epi.relu && p.epi.fast && p.prof == nullptr &&
+                      p.epi.n_add == 0 && p.dbg == 0;
+  p.res_staged = staged ? 1 : 0;
+  if (staged) {
+    HaloConvPrepared* PM = const_cast<HaloConvPrepared*>(P);
+    if (residual != PM->res4_encoded) {
+      if (!halo_encode_res4(&P->d, residual, p.BN, &PM->tmap_r4_cache)) return BRTPE_ECUDA;
+      PM->res4_encoded = residual;
+    }
+    p.tmap_r4 = PM->tmap_r4_cache;
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(P->grid);
@@ -1525,6 +1635,7 @@ int HL_NAME(halo_conv_launch)(const HaloConvPrepared* P, const float* bias, cons
   }
   int variant;
   if (p.epi.split) variant = 5;
+  else if (staged) variant = 12;
   else if (p.prof != nullptr && p.epi.fast) variant = 6;
   else if (p.epi.n_add > 0) variant = 7 + (p.epi.res != nullptr ? 2 : 0) + (p.epi.relu ? 1 : 0);
   else if (p.epi.fast && p.dbg == 0) variant = (p.epi.res != nullptr ? 2 : 0) + (p.epi.relu ? 1 : 0);

@@ -737,7 +737,13 @@ extern "C" int brtpe_nms_topk_gather(const float* det, const float* tag, int N, 
   {
     int sr_shift, ns_shift, ssplits, nc;
     size_t smem;
-    if (vec && !getenv("BRTPE_TOPK_V1") &&
+    // Many small planes (config 5: 17 408 planes of 320 x 320): a streaming CTA lives ~20 us, its
+    // prologue / list merge shows, and the register-window kernel is faster (3.98 vs 4.50 ms for the
+    // 1024-image batch; the bench's 544 planes of 640 x 640: 0.54 vs 0.345 ms the other way round).
+    // BRTPE_TOPK_STREAM=1 forces the streaming kernel, BRTPE_TOPK_V1=1 the first one.
+    const bool small_planes = (size_t)H * W * 4 <= 512 * 1024 && (long long)N * J >= 8ll * num_sms() &&
+                              !getenv("BRTPE_TOPK_STREAM");
+    if (vec && !getenv("BRTPE_TOPK_V1") && !small_planes &&
         topk_stream_geometry(N * J, H, W, R, &sr_shift, &ns_shift, &ssplits, &smem, &nc)) {
       const size_t keys = (size_t)N * J * ssplits * 32 * S * sizeof(unsigned long long);
       const size_t sneed = align_up(keys, 256) + (size_t)N * J * sizeof(unsigned int);

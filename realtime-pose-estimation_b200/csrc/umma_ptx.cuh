@@ -271,6 +271,15 @@ __device__ __forceinline__ void umma_commit_cg2(uint32_t bar, uint16_t mask) {
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // ---- TMA store (shared -> global) of an epilogue staging tile, bulk-group completion
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src_smem, int c0,
                                              int c1, int c2, int c3) {
