@@ -82,3 +82,4 @@ extern "C" int brtpe_debug_halo_prof(void* buf, int max_ctas) {
   brtpe::halo_set_prof(reinterpret_cast<long long*>(buf), max_ctas);
   return BRTPE_OK;
 }
+BRTPE_MBAR_DEBUG_EXPORT(brtpe_debug_mbar_halo1)

@@ -1425,6 +1425,14 @@ HaloConvPrepared* HL_NAME(halo_conv_prepare)(const brtpe_conv_desc* d, const voi
       more_b(HL_MAX_B);
     }
   }
+  // Two issuing warps observe each other's activation fills through parity waits, which can only tell a
+  // barrier's next phase from the current one.  When one work item takes more fills than the ring has
+  // stages (split 3x3 / stride-2 layers: 3 channel blocks, two 72 KB stages), two fills of the OTHER warp's
+  // item land in the same stage and a warp that is still issuing its own item can miss one: it then waits for
+  // a fill that needs its own progress.  Seen as an intermittent launch failure (spin-limit trap) of the
+  // fp32 mode, 48 -> 48 stride 2, on some boxes only, ~1 in 300 launches inside the network and never
+  // stand-alone; gone with one issuer (tools/stress_fp32.py, profiles/r02_fp32_hang.md).
+  if (p.dual && p.a_stages < p.num_kb) p.dual = 0;
   P->smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes +
             (size_t)p.out_slabs * HL_STAGE_BYTES + HL_TAIL + 1024;
   // Staged residual (opt-in, BRTPE_HALO_RES_STAGED=1): narrow single-CTA layers with direct stores whose

@@ -3,3 +3,4 @@
 #define HL_CG 2
 #define HL_NAME(x) x##_cg2
 #include "conv_halo_impl.cuh"
+BRTPE_MBAR_DEBUG_EXPORT(brtpe_debug_mbar_halo2)

@@ -565,3 +565,4 @@ extern "C" int brtpe_umma_weight_dims(int Cin, int Cout_store, int* cin_pad, int
   if (cout_pad) *cout_pad = nt * bn;
   return BRTPE_OK;
 }
+BRTPE_MBAR_DEBUG_EXPORT(brtpe_debug_mbar_umma)

@@ -441,9 +441,22 @@ extern "C" double brtpe_plan_conv_flops(const brtpe_plan* pl) {
 extern "C" int brtpe_plan_run(brtpe_plan* pl, void* stream) {
   BRTPE_CHECK_ARG(pl, "brtpe_plan_run: null plan");
   fuse_chains(pl);
+  static int sync_each = -1;               // BRTPE_PLAN_SYNC=1 (debug): synchronise after every op and name
+  if (sync_each < 0) sync_each = getenv("BRTPE_PLAN_SYNC") ? atoi(getenv("BRTPE_PLAN_SYNC")) : 0;   // the one that faults
   for (size_t i = 0; i < pl->ops.size(); ++i) {
     int rc = run_plan_op(pl, i, (cudaStream_t)stream);
     if (rc) return rc;
+    if (sync_each) {
+      cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+      if (e != cudaSuccess) {
+        const Op& op = pl->ops[i];
+        set_error("plan op %zu (kind %d, engine %s, N %d %dx%d Cin %d Cout %d taps %d stride %d dtype %d res %d) failed: %s",
+                  i, op.kind, op.halo ? (op.halo ? "halo" : "") : (op.umma ? "umma" : "other"), op.d.N, op.d.Hm,
+                  op.d.Wm, op.d.Cin, op.d.Cout, op.d.ntaps, op.d.in_stride, op.d.dtype, op.res != nullptr,
+                  cudaGetErrorString(e));
+        return BRTPE_ECUDA;
+      }
+    }
   }
   return BRTPE_OK;
 }

@@ -20,6 +20,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+#ifdef BRTPE_MBAR_DEBUG
+// Debug build (make MBAR_DEBUG=1): a wait that times out records who waited on what in a TU-local
+// device array (read back through brtpe_debug_mbar_*) and every later wait gives up at once, so the
+// kernel ends (with garbage) instead of trapping and the host can report the hand-off that hung.
+static __device__ unsigned int g_mbar_dbg[8];
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
   while (true) {
@@ -31,9 +37,35 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
+#ifdef BRTPE_MBAR_DEBUG
+    ++spins;
+    if ((spins & 255u) == 0u && *(volatile unsigned int*)&g_mbar_dbg[0] != 0u) break;
+    if (spins > (1u << 22)) {
+      if (atomicCAS(&g_mbar_dbg[0], 0u, 1u) == 0u) {
+        g_mbar_dbg[1] = blockIdx.x; g_mbar_dbg[2] = threadIdx.x; g_mbar_dbg[3] = bar;
+        g_mbar_dbg[4] = parity; g_mbar_dbg[5] = gridDim.x; g_mbar_dbg[6] = blockDim.x;
+        g_mbar_dbg[7] = (unsigned int)clock64();
+      }
+      break;
+    }
+#else
     if (++spins > (1u << 22)) __trap();  // a protocol bug becomes an error, not a hung GPU
+#endif
   }
 }
+#ifdef BRTPE_MBAR_DEBUG
+#define BRTPE_MBAR_DEBUG_EXPORT(name)                                                         \
+  extern "C" int name(unsigned int* out8, int reset) {                                        \
+    if (cudaMemcpyFromSymbol(out8, brtpe::g_mbar_dbg, 8 * sizeof(unsigned int)) != cudaSuccess) return -1; \
+    if (reset) {                                                                              \
+      unsigned int z[8] = {0, 0, 0, 0, 0, 0, 0, 0};                                           \
+      if (cudaMemcpyToSymbol(brtpe::g_mbar_dbg, z, sizeof(z)) != cudaSuccess) return -1;             \
+    }                                                                                         \
+    return 0;                                                                                 \
+  }
+#else
+#define BRTPE_MBAR_DEBUG_EXPORT(name)
+#endif
 // non-blocking phase test
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   uint32_t done;
@@ -210,6 +242,10 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 }
 // wait on a barrier whose arrivals come from both CTAs of the pair
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+#ifdef BRTPE_MBAR_DEBUG
+  mbar_wait(bar, parity);
+  return;
+#endif
   uint32_t done = 0, spins = 0;
   while (true) {
     asm volatile(
