@@ -423,9 +423,35 @@ refine_stream_kernel(RefineArgs a, int splits, int NS) {
             for (int t = 0; t < T; ++t) tv[2 * m + e][t] = 0.0f;
         }
       }
+      // Scalar tags (T == 1; the sparse planted maps of config 5): the range of the warp's 128 tags bounds
+      // every score of the chunk for a person from above -- score = det - rint(|tag - mean|) <= max det -
+      // rint(distance of the mean to the range), with the SAME float operations (each monotone), so a chunk
+      // whose bound is below the person's best so far cannot hold a winner or a tie.  Persons whose tag does
+      // not occur in a chunk (almost all chunks of a sparse map) then cost ~10 instructions instead of four
+      // score evaluations per lane.  Not for T >= 2: on the bench's dense two-dimensional tags the bound
+      // rarely prunes and cost 10 % (profiles/r01l_decode.md).
+      float wtmin = 0.0f, wtmax = 0.0f, wdmax = 0.0f;
+      if constexpr (T == 1) {
+        float tmn = tv[0][0], tmx = tv[0][0];
+#pragma unroll
+        for (int e = 1; e < 2 * RF_PAIRS; ++e) {
+          tmn = fminf(tmn, tv[e][0]);
+          tmx = fmaxf(tmx, tv[e][0]);
+        }
+        wtmin = float_from_order_key(__reduce_min_sync(FULL_MASK, float_order_key(tmn)));
+        wtmax = float_from_order_key(__reduce_max_sync(FULL_MASK, float_order_key(tmx)));
+        wdmax = float_from_order_key(wkmax);
+      }
       for (int q = 0; q < nq; ++q) {
         const unsigned lb = *(volatile unsigned int*)&slb[q];
         if (wkmax < lb) continue;
+        if constexpr (T == 1) {
+          const float pv0 = sprev[q][0];
+          const float tb = pv0 < wtmin ? wtmin : (pv0 > wtmax ? wtmax : pv0);
+          const float df = __fsub_rn(tb, pv0);
+          const float bound = __fsub_rn(wdmax, rintf(__fsqrt_rn(__fmul_rn(df, df))));
+          if (float_order_key(bound) < lb) continue;
+        }
         float pv[T];
 #pragma unroll
         for (int t = 0; t < T; ++t) pv[t] = sprev[q][t];

@@ -266,3 +266,25 @@ def test_person_capacity_overflow_retry(cuda_device):
     ans, count, pmax, flag = small.match_device(val_k, ind_k, tag_k, w, defer_overflow=True)
     assert pmax == small._pmax_full() and flag is None
     assert_people_equal(small.parse_batch(det.cuda(), tag.cuda(), True, True), want)
+
+
+def test_refine_ties_scalar_tags(cuda_device):
+    """scalar tags + quantised heat maps: thousands of pixels tie in det - rint(|tag - mean|), the winner is
+    the first index (np.argmax).  Guards the chunk-level tag-range bound of the streaming refine kernel
+    (T == 1): a chunk may only be skipped when its bound is strictly below the person's best so far."""
+    h, w = 96, 160
+    g = torch.Generator().manual_seed(11)
+    det = (torch.randint(0, 3, (2, 17, h, w), generator=g).float() * 0.0125)          # {0, .0125, .025}
+    tag = torch.randint(0, 4, (2, 17, h, w, 1), generator=g).float() * 2.0            # {0, 2, 4, 6}
+    for n in range(2):
+        for pid in range(5):
+            for j in range(17):
+                if (j + pid) % 3 == 0:
+                    continue                                  # joints this person misses
+                y, x = 8 + 16 * pid + (j % 5), 10 + 8 * j
+                det[n, j, y, x] = 0.5 + 0.01 * pid
+                tag[n, j, y - 1:y + 2, x - 1:x + 2, 0] = 2.0 * pid
+    hp, p = make_parser()
+    got = hp.parse_batch(det.cuda(), tag.cuda(), True, True)
+    want = G.parse_batch_ref(det.numpy().copy(), tag.numpy().copy(), p, True, True)
+    assert_people_equal(got, want)
