@@ -44,8 +44,8 @@ bool halo_conv_supported(const brtpe_conv_desc* d) {
 
 // Pair mode (each SM reads and receives only half of the weight operand) pays off where the
 // weight operand is a large share of the shared-memory traffic: Cout tiles of >= 96 channels.
-// Measured (profiles/r01e_halo_pair.md): 96ch +10 %, 48ch -25 % (the leader's single MMA thread
-// then issues for both SMs).  BRTPE_HALO_CG=1 / 2 forces a mode.
+// Measured in round 1 (profiles/r01e_halo_pair.md): 96ch +10 %, 48ch -25 % (the leader's single MMA
+// thread then issued for both SMs).  BRTPE_HALO_CG=1 / 2 forces a mode.
 HaloConvPrepared* halo_conv_prepare(const brtpe_conv_desc* d, const void* in, const void* weights,
                                     void* out) {
   if (!halo_conv_supported(d)) {
@@ -53,6 +53,17 @@ HaloConvPrepared* halo_conv_prepare(const brtpe_conv_desc* d, const void* in, co
     return nullptr;
   }
   int cg = (d->Cout_store >= 96) ? 2 : 1;
+  // Round 2, with two MMA-issuing warps (the single issuing thread was what made the pair mode 25 % slower
+  // on narrow layers in round 1): stride-1 layers of fewer than 96 channels on large batches of tiles gain too
+  // -- 64 images: 48 -> 48 @160^2 (+ residual) 0.0939 -> 0.0891 ms, @320^2 0.366 -> 0.353, 64 -> 64 @160^2
+  // 0.138 -> 0.134, 256 -> 48 @160^2 0.400 -> 0.342; the forward 28.0 -> 27.5 ms per 64.  Stride 2: neutral;
+  // 2 images @160^2: 0.0110 -> 0.0128 ms, so only from eight tiles per SM on.  BRTPE_HALO_CG_NARROW=0 = round-1 rule.
+  {
+    static int narrow = -1;
+    if (narrow < 0) narrow = getenv("BRTPE_HALO_CG_NARROW") ? atoi(getenv("BRTPE_HALO_CG_NARROW")) : 1;
+    const long tiles = (long)((d->Wm + 7) / 8) * ((d->Hm + 15) / 16) * d->N;
+    if (cg == 1 && narrow && d->in_stride == 1 && tiles >= 8L * num_sms()) cg = 2;
+  }
   if (getenv("BRTPE_HALO_CG")) {
     const int v = atoi(getenv("BRTPE_HALO_CG"));
     if (v == 1 || v == 2) cg = v;
