@@ -32,7 +32,14 @@
 
 namespace brtpe {
 
-constexpr int UM_THREADS = 192;
+constexpr int UM_THREADS = 320;           // TMA warp, MMA warp, 2 x 4 epilogue warps (UmmaParams::epi_groups == 2)
+// Four epilogue warps (192 threads, two CTAs per SM by registers) unless the layer is a 1x1 conv with a Cout
+// tile of >= 64 channels on a large map: those are pure streaming layers (K <= 256: a handful of MMAs per
+// tile, then 128 pixels x BN channels of residual + output), bound by the bytes their epilogue warps keep in
+// flight; one CTA per SM with eight warps, each group draining half of the channel chunks, measured (64
+// images): 64 -> 256 + residual @160^2 0.427 -> 0.404 ms, 256 -> 64 0.201 -> 0.193.  Everywhere else the
+// second CTA per SM is worth more (48 -> 32 @320^2 0.245 -> 0.419 ms with 320 threads).
+constexpr int UM_THREADS_NARROW = 192;
 constexpr int UM_MAX_STAGES = 8;
 constexpr int UM_A_BYTES = 128 * 128;   // 128 rows x 64 bf16
 constexpr int UM_MAX_COUT_PAD = 512;
@@ -53,6 +60,7 @@ struct alignas(64) UmmaParams {
   const float* bias;
   int Hout, Wout, out_scale, out_oy, out_ox;
   int res_l2_prefetch;    // epilogue prefetches the next tile's residual rows into L2
+  int epi_groups;         // 1: four epilogue warps (192 threads), 2: eight (320 threads)
   EpiParams epi;
 };
 
@@ -110,12 +118,12 @@ conv_umma_kernel(const __grid_constant__ UmmaParams p) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tfull_bar[s]), 1);
-      mbar_init(smem_u32(&tempty_bar[s]), 4);
+      mbar_init(smem_u32(&tempty_bar[s]), 4u * (uint32_t)p.epi_groups);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < n_tiles * BN; i += UM_THREADS)
+  for (int i = threadIdx.x; i < n_tiles * BN; i += blockDim.x)
     bias_s[i] = (p.bias && i < p.epi.Cout) ? p.bias[i] : 0.0f;
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
   tc_fence_before();
@@ -205,14 +213,21 @@ conv_umma_kernel(const __grid_constant__ UmmaParams p) {
       __syncwarp();
     }
   } else {
-    // ===================== epilogue (4 warps, one TMEM lane quarter each) ===================
+    // ===================== epilogue (1 or 2 groups of 4 warps, one TMEM lane quarter each) ===
+    // two groups: group g drains the channel chunks [cbeg, cend) of every tile
     const int lg = warp & 3;
+    const int grp = (warp - 2) >> 2;
     const int m = lg * 32 + lane;
     const int tn = (int)fdiv((uint32_t)m, p.fd_twh);
     const int th = (int)fdiv((uint32_t)(m - tn * TW * TH), p.fd_tw);
     const int tw = m - tn * TW * TH - th * TW;
     const EpiParams e = p.epi;
-    const int nchunks = BN >> 4;
+    const int allchunks = BN >> 4;
+    const bool two_groups = p.epi_groups == 2;
+    const int csplit = two_groups ? (((allchunks + 3) >> 2) << 1) : allchunks;   // even: chunks go in pairs
+    const int cbeg = grp == 0 ? 0 : (csplit < allchunks ? csplit : allchunks);
+    const int cend = grp == 0 ? (csplit < allchunks ? csplit : allchunks) : allchunks;
+    const int nchunks = cend - cbeg;
     const int Wm = p.Wm, Hm = p.Hm, N = p.N, Hout = p.Hout, Wout = p.Wout;
     const int out_scale = p.out_scale, out_oy = p.out_oy, out_ox = p.out_ox, acc_cols = p.acc_cols;
     int it = 0;
@@ -246,14 +261,24 @@ conv_umma_kernel(const __grid_constant__ UmmaParams p) {
         int co0_n;
         if (locate(tile + (int)gridDim.x, opix_n, co0_n)) {
           const char* rp = reinterpret_cast<const char*>(e.res + opix_n * e.res_ld + e.res_coff + co0_n);
-          for (int b = 0; b < BN * 2; b += 128)
+          for (int b = cbeg * 32; b < cend * 32; b += 128)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + b));
         }
       }
       const bool valid = locate(tile, opix, co0);    // (after the prefetch: it leaves pn / py / px)
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * acc_cols);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * acc_cols) +
+                              (uint32_t)(cbeg * 16);
+      co0 += cbeg * 16;
+      if (nchunks <= 0) {                            // (host never selects two groups for such tiles)
+        mbar_wait(smem_u32(&tfull_bar[as]), aphase);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+        continue;
+      }
       if (SPLIT)
         epi_tile_split(e, bias_s, t_addr, nchunks, co0, valid, opix, smem_u32(&tfull_bar[as]), aphase,
                        smem_u32(&tempty_bar[as]), lane);
@@ -426,6 +451,14 @@ UmmaConvPrepared* umma_conv_prepare(const brtpe_conv_desc* d, const void* in, co
   p.stages = stages;
   P->smem = (size_t)stages * stage_bytes + tail + 1024;
   P->grid = (int)std::min<long>(p.total_tiles, (long)num_sms() * (two_per_sm ? 2 : 1));
+  {
+    static int eg = -1;                            // BRTPE_UMMA_EPI8=0: four epilogue warps everywhere
+    if (eg < 0) eg = getenv("BRTPE_UMMA_EPI8") ? atoi(getenv("BRTPE_UMMA_EPI8")) : 1;
+    const bool stream_1x1 = d->ntaps == 1 && d->in_stride == 1 && p.BN >= 64 && (p.BN >> 4) % 2 == 0 &&
+                            d->Cin >= 64 && d->Cin <= 256 && (long)p.total_tiles >= 8L * num_sms() &&
+                            d->n_add == 0;     // (the stem's K = 32 GEMM @320^2 loses: 0.431 -> 0.488 ms)
+    p.epi_groups = (eg && stream_1x1) ? 2 : 1;
+  }
 
   // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
@@ -543,9 +576,9 @@ int umma_conv_launch(const UmmaConvPrepared* P, const float* bias, const void* r
   }
   (void)out2;
   cudaError_t e;
-  if (p.epi.split) e = launch_ex(conv_umma_kernel<true, false>, dim3(P->grid), dim3(UM_THREADS), P->smem, st, 0, true, p);
-  else if (p.epi.n_add > 0) e = launch_ex(conv_umma_kernel<false, true>, dim3(P->grid), dim3(UM_THREADS), P->smem, st, 0, true, p);
-  else e = launch_ex(conv_umma_kernel<false, false>, dim3(P->grid), dim3(UM_THREADS), P->smem, st, 0, true, p);
+  if (p.epi.split) e = launch_ex(conv_umma_kernel<true, false>, dim3(P->grid), dim3(p.epi_groups == 2 ? UM_THREADS : UM_THREADS_NARROW), P->smem, st, 0, true, p);
+  else if (p.epi.n_add > 0) e = launch_ex(conv_umma_kernel<false, true>, dim3(P->grid), dim3(p.epi_groups == 2 ? UM_THREADS : UM_THREADS_NARROW), P->smem, st, 0, true, p);
+  else e = launch_ex(conv_umma_kernel<false, false>, dim3(P->grid), dim3(p.epi_groups == 2 ? UM_THREADS : UM_THREADS_NARROW), P->smem, st, 0, true, p);
   if (e != cudaSuccess) {
     set_error("conv_umma_kernel launch failed: %s", cudaGetErrorString(e));
     return BRTPE_ECUDA;
